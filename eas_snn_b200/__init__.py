@@ -1,0 +1,12 @@
+"""eas_snn_b200 -- B200 (sm_100a) implementation of the EAS-SNN data-parallel hot path.
+
+event binning -> adaptive spiking sampler -> multi-step LIF (+ conv) of the spiking backbone,
+behind the reference's own module surface.  The kernels live in ``lib/libeas_b200.so`` (C ABI:
+``include/eas_b200.h``); this package is the thin PyTorch host side.  No CPU fallback.
+"""
+from . import _lib  # noqa: F401
+from .binning import bin_events, HostEventBatch  # noqa: F401
+from .embedding import AdaptiveRSNNEmbedding  # noqa: F401
+from .neuron import ATan, Sigmoid, Rect, ParametricLIFNode, plif_multistep, is_spiking_neuron, reset_net  # noqa: F401
+
+__version__ = "0.1.0"

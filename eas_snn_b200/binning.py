@@ -1,0 +1,70 @@
+"""Event binning on the GPU: ``(x, y, t, p)`` windows -> ``[B, Tm, 2, H, W]`` int32 histograms.
+
+Drop-in for the reference's CPU path ``GEN1Dataset.slice_events`` + ``agrregate('micro_sum')``
+(``yolox/data/datasets/gen1.py:313-360``), called through ``eas_bin_events`` of the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+STRATEGY = {"auto": 0, "reds": 1, "tiles": 2}
+
+
+def bin_events(x: torch.Tensor, y: torch.Tensor, t: torch.Tensor, p: torch.Tensor, offsets: torch.Tensor,
+               H: int, W: int, Tm: int, strategy: str = "auto", out: torch.Tensor | None = None) -> torch.Tensor:
+    """Histogram B time-sorted windows.
+
+    x, y : int16 ``[N]``; t : int64 ``[N]`` (sorted inside each window); p : uint8/bool ``[N]``;
+    offsets : int64 ``[B+1]`` with ``offsets[0] == 0`` and ``offsets[B] == N``.  All CUDA tensors.
+    Returns int32 ``[B, Tm, 2, H, W]`` (counts; cast with ``.float()`` for the reference's dtype).
+    """
+    _lib.require_cuda(x, y, t, p, offsets)
+    if p.dtype == torch.bool:
+        p = p.view(torch.uint8)
+    if x.dtype != torch.int16 or y.dtype != torch.int16 or t.dtype != torch.int64 or p.dtype != torch.uint8:
+        raise TypeError("bin_events expects x,y int16, t int64, p uint8/bool (events_struct, util.py:119-121)")
+    if offsets.dtype != torch.int64 or offsets.dim() != 1 or offsets.numel() < 1:
+        raise TypeError("offsets must be int64 [B+1]")
+    n = x.numel()
+    if not (y.numel() == n and t.numel() == n and p.numel() == n):
+        raise ValueError("x, y, t, p must have the same length")
+    x, y, t, p, offsets = (a.contiguous() for a in (x, y, t, p, offsets))
+    B = offsets.numel() - 1
+    if out is None:
+        out = torch.empty((B, Tm, 2, H, W), dtype=torch.int32, device=x.device)
+    elif out.shape != (B, Tm, 2, H, W) or out.dtype != torch.int32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous int32 [B, Tm, 2, H, W] tensor")
+    L = _lib.lib()
+    ws_bytes = L.eas_bin_events_ws_bytes(B, Tm)
+    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.eas_bin_events_ex(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), _lib.ptr(offsets),
+                                 B, n, H, W, Tm, _lib.ptr(out), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(),
+                                 STRATEGY[strategy])
+    _lib.check(rc, "eas_bin_events")
+    return out
+
+
+class HostEventBatch:
+    """Pinned host staging for one batch of windows (the host side of the e2e path)."""
+
+    def __init__(self, x: np.ndarray, y: np.ndarray, t: np.ndarray, p: np.ndarray, offsets: np.ndarray):
+        self.n = int(x.shape[0])
+        self.B = int(offsets.shape[0]) - 1
+        self.x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.int16)).pin_memory()
+        self.y = torch.from_numpy(np.ascontiguousarray(y, dtype=np.int16)).pin_memory()
+        self.t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.int64)).pin_memory()
+        self.p = torch.from_numpy(np.ascontiguousarray(p).astype(np.uint8)).pin_memory()
+        self.offsets = torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64)).pin_memory()
+
+    @property
+    def nbytes(self) -> int:
+        return self.n * 13 + (self.B + 1) * 8
+
+    def to_device(self, device):
+        return tuple(a.to(device, non_blocking=True) for a in (self.x, self.y, self.t, self.p, self.offsets))

@@ -1,0 +1,227 @@
+// (a-1) Event binning: time-sorted (x, y, t, p) windows -> per-pixel micro-bin histograms.
+// Replaces GEN1Dataset.slice_events + agrregate('micro_sum') (yolox/data/datasets/gen1.py:313-360).
+//
+// Data layout in HBM: events are SoA (x:i16, y:i16, t:i64, p:u8), B windows back to back with
+// offsets[B+1]; output hist[B][Tm][2][H][W] int32.
+//
+// Two kernels run per call:
+//   1. bin_bounds_kernel: per window, tw = (t_last - t_first)/Tm and Tm+1 lower_bound searches on
+//      the sorted timestamps.  After this nobody reads t again: membership of an event in a
+//      micro-bin is an index-range test, exactly like the reference's searchsorted slicing.
+//   2. one of
+//      bin_hist_smem_kernel  ("tiles"): one CTA owns one (window, micro-bin, polarity) output tile,
+//         counts it in shared memory as packed 16-bit lanes (H*W*2 B <= 200 KB) and writes the tile
+//         once with 16 B stores: no global atomics, no pre-zeroing, HBM traffic = 5 B/event (x2 in
+//         L2) + 4 B/bin.  Chunks of <= 65535 events make 16-bit overflow impossible.
+//      bin_hist_global_kernel ("reds"): event-parallel, 8 events per thread with 16 B loads,
+//         red.global.add.u32 into the (L2-resident when it fits) histogram after a memset.  Used for
+//         frames that do not fit in shared memory and for very long windows.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kSmemThreads = 1024;
+constexpr int kSmemMaxBytes = 200 * 1024;
+constexpr int kChunk = 65535;
+
+__global__ void bin_bounds_kernel(const int64_t* __restrict__ t, const int64_t* __restrict__ offsets,
+                                  int64_t B, int Tm, int64_t* __restrict__ bounds) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= B * (Tm + 1)) return;
+  const int64_t b = gid / (Tm + 1);
+  const int k = (int)(gid - b * (Tm + 1));
+  const int64_t s = offsets[b], e = offsets[b + 1];
+  if (e <= s) {
+    bounds[gid] = s;
+    return;
+  }
+  const int64_t t0 = t[s];
+  const int64_t tw = (t[e - 1] - t0) / Tm;  // sorted => non-negative => trunc == floor
+  const int64_t key = t0 + (int64_t)k * tw;
+  int64_t lo = s, hi = e;  // first index with t[i] >= key
+  while (lo < hi) {
+    const int64_t mid = lo + ((hi - lo) >> 1);
+    if (t[mid] < key) lo = mid + 1;
+    else hi = mid;
+  }
+  bounds[gid] = lo;
+}
+
+// ---- strategy "tiles" ---------------------------------------------------------------------
+__global__ void __launch_bounds__(kSmemThreads, 1)
+bin_hist_smem_kernel(const int16_t* __restrict__ x, const int16_t* __restrict__ y,
+                     const uint8_t* __restrict__ p, const int64_t* __restrict__ bounds, int64_t n_items,
+                     int H, int W, int Tm, int32_t* __restrict__ hist) {
+  extern __shared__ __align__(16) uint32_t cnt[];  // ceil(H*W/2) words, two 16-bit counters per word
+  const int HW = H * W;
+  const int nwords = (HW + 1) >> 1;
+  const int nwords4 = (nwords + 3) & ~3;  // allocation is rounded up to 16 B
+  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int c = (int)(item & 1);
+    const int64_t bk = item >> 1;  // b*Tm + k
+    const int64_t b = bk / Tm;
+    const int k = (int)(bk - b * Tm);
+    const int64_t s = bounds[b * (Tm + 1) + k], e = bounds[b * (Tm + 1) + k + 1];
+    int32_t* __restrict__ out = hist + item * (int64_t)HW;
+    bool first = true;
+    for (int64_t cs = s; first || cs < e; cs += kChunk) {
+      for (int w = threadIdx.x * 4; w < nwords4; w += kSmemThreads * 4)
+        *reinterpret_cast<uint4*>(cnt + w) = make_uint4(0u, 0u, 0u, 0u);
+      __syncthreads();
+      const int64_t ce = (e - cs > kChunk) ? cs + kChunk : e;
+#pragma unroll 4
+      for (int64_t i = cs + threadIdx.x; i < ce; i += kSmemThreads) {
+        const int xi = x[i], yi = y[i];
+        const int ci = p[i] != 0;
+        if (ci == c && (unsigned)xi < (unsigned)W && (unsigned)yi < (unsigned)H) {
+          const int pix = yi * W + xi;
+          atomicAdd(cnt + (pix >> 1), 1u << ((pix & 1) << 4));
+        }
+      }
+      __syncthreads();
+      if ((HW & 3) == 0) {
+        // 2 words = 4 counters -> one 16 B store
+        for (int w = threadIdx.x * 2; w < nwords; w += kSmemThreads * 2) {
+          const uint2 v = *reinterpret_cast<const uint2*>(cnt + w);
+          uint4 o = make_uint4(v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16);
+          uint4* dst = reinterpret_cast<uint4*>(out + 2 * w);
+          if (!first) {
+            const uint4 old = *dst;
+            o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
+          }
+          st_stream_u4(dst, o);
+        }
+      } else {
+        for (int q = threadIdx.x; q < HW; q += kSmemThreads) {
+          const uint32_t v = (cnt[q >> 1] >> ((q & 1) << 4)) & 0xffffu;
+          out[q] = first ? (int32_t)v : out[q] + (int32_t)v;
+        }
+      }
+      __syncthreads();
+      first = false;
+    }
+  }
+}
+
+// ---- strategy "reds" ----------------------------------------------------------------------
+constexpr int kEpt = 8;  // events per thread per iteration (one 16 B load of x and of y)
+
+__global__ void __launch_bounds__(256)
+bin_hist_global_kernel(const int16_t* __restrict__ x, const int16_t* __restrict__ y,
+                       const uint8_t* __restrict__ p, const int64_t* __restrict__ offsets,
+                       const int64_t* __restrict__ bounds, int64_t B, int64_t n, int H, int W, int Tm,
+                       int32_t* __restrict__ hist) {
+  const int64_t HW = (int64_t)H * W;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * kEpt;
+  for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kEpt; i0 < n; i0 += stride) {
+    // window of the first event: largest b with offsets[b] <= i0
+    int64_t lo = 0, hi = B;  // invariant: offsets[lo] <= i0 < offsets[hi]
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (offsets[mid] <= i0) lo = mid;
+      else hi = mid;
+    }
+    int64_t b = lo;
+    int64_t off_next = offsets[b + 1];
+    const int64_t* bnd = bounds + b * (Tm + 1);
+    int k = 0;
+    __align__(16) int16_t xs[kEpt];
+    __align__(16) int16_t ys[kEpt];
+    __align__(8) uint8_t ps[kEpt];
+    const int cnt = (n - i0 >= kEpt) ? kEpt : (int)(n - i0);
+    if (cnt == kEpt) {
+      *reinterpret_cast<uint4*>(xs) = ld_stream_u4(reinterpret_cast<const uint4*>(x + i0));
+      *reinterpret_cast<uint4*>(ys) = ld_stream_u4(reinterpret_cast<const uint4*>(y + i0));
+      *reinterpret_cast<uint2*>(ps) = ld_stream_u2(reinterpret_cast<const uint2*>(p + i0));
+    } else {
+#pragma unroll
+      for (int j = 0; j < kEpt; ++j)
+        if (j < cnt) xs[j] = x[i0 + j], ys[j] = y[i0 + j], ps[j] = p[i0 + j];
+    }
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) {
+      if (j >= cnt) break;
+      const int64_t i = i0 + j;
+      while (i >= off_next && b + 1 < B) {  // also skips empty windows
+        ++b;
+        off_next = offsets[b + 1];
+        bnd += Tm + 1;
+        k = 0;
+      }
+      if (i >= off_next) break;  // past the last window
+      while (k < Tm && i >= bnd[k + 1]) ++k;
+      const int xi = xs[j], yi = ys[j];
+      if (k < Tm && i >= bnd[0] && (unsigned)xi < (unsigned)W && (unsigned)yi < (unsigned)H) {
+        const int c = ps[j] != 0;
+        atomicAdd(hist + ((b * Tm + k) * 2 + c) * HW + (int64_t)yi * W + xi, 1);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" size_t eas_bin_events_ws_bytes(int64_t B, int Tm) {
+  if (B <= 0 || Tm <= 0) return 0;
+  return eas_align_up((size_t)B * (size_t)(Tm + 1) * sizeof(int64_t), 256);
+}
+
+extern "C" int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64_t* t, const uint8_t* p,
+                                 const int64_t* offsets, int64_t B, int64_t n_events, int H, int W, int Tm,
+                                 int32_t* hist, void* ws, size_t ws_bytes, void* stream_, int strategy) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EAS_REQUIRE(B >= 0 && n_events >= 0, EAS_E_SHAPE);
+  EAS_REQUIRE(H > 0 && W > 0 && Tm > 0 && Tm <= 1024, EAS_E_SHAPE);
+  EAS_REQUIRE((int64_t)H * W < (1ll << 30), EAS_E_SHAPE);
+  EAS_REQUIRE(strategy >= 0 && strategy <= 2, EAS_E_UNSUPPORTED);
+  if (B == 0) return EAS_OK;
+  EAS_REQUIRE(offsets && hist && ws, EAS_E_NULL);
+  EAS_REQUIRE(n_events == 0 || (x && y && t && p), EAS_E_NULL);
+  EAS_REQUIRE(ws_bytes >= eas_bin_events_ws_bytes(B, Tm), EAS_E_WORKSPACE);
+  EAS_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)p % 8 == 0) &&
+                  ((uintptr_t)hist % 16 == 0) && ((uintptr_t)ws % 8 == 0),
+              EAS_E_ALIGN);
+  int64_t* bounds = (int64_t*)ws;
+  const int64_t HW = (int64_t)H * W;
+  const int64_t nb = B * (Tm + 1);
+  bin_bounds_kernel<<<(unsigned)eas_ceil_div(nb, 128), 128, 0, stream>>>(t, offsets, B, Tm, bounds);
+  EAS_LAUNCH_CHECK();
+
+  const size_t smem = (size_t)(((HW + 1) / 2 + 3) / 4 * 4) * 4;
+  const int64_t n_items = B * Tm * 2;
+  if (strategy == 0) {
+    const bool fits = smem <= (size_t)kSmemMaxBytes;
+    // one CTA per (window, micro-bin, polarity): only when that gives the machine enough CTAs and
+    // no single segment is long enough to serialise the launch.
+    const bool enough = n_items >= EAS_NUM_SMS / 2 && n_events / (B * Tm) <= (1 << 18);
+    strategy = (fits && enough) ? 2 : 1;
+  }
+  if (strategy == 2) {
+    EAS_REQUIRE(smem <= (size_t)kSmemMaxBytes, EAS_E_UNSUPPORTED);
+    cudaError_t e = cudaFuncSetAttribute(bin_hist_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const unsigned grid = (unsigned)(n_items < 16 * EAS_NUM_SMS ? n_items : 16 * EAS_NUM_SMS);
+    bin_hist_smem_kernel<<<grid, kSmemThreads, smem, stream>>>(x, y, p, bounds, n_items, H, W, Tm, hist);
+    EAS_LAUNCH_CHECK();
+  } else {
+    cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)B * Tm * 2 * HW * sizeof(int32_t), stream);
+    if (e != cudaSuccess) return (int)e;
+    if (n_events > 0) {
+      const int64_t threads = eas_ceil_div(n_events, kEpt);
+      int64_t blocks = eas_ceil_div(threads, 256);
+      const int64_t cap = (int64_t)EAS_NUM_SMS * 8 * 4;  // 8 resident CTAs/SM, a few waves
+      if (blocks > cap) blocks = cap;
+      bin_hist_global_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, y, p, offsets, bounds, B, n_events, H, W,
+                                                                   Tm, hist);
+      EAS_LAUNCH_CHECK();
+    }
+  }
+  return EAS_OK;
+}
+
+extern "C" int eas_bin_events(const int16_t* x, const int16_t* y, const int64_t* t, const uint8_t* p,
+                              const int64_t* offsets, int64_t B, int64_t n_events, int H, int W, int Tm,
+                              int32_t* hist, void* ws, size_t ws_bytes, void* stream) {
+  return eas_bin_events_ex(x, y, t, p, offsets, B, n_events, H, W, Tm, hist, ws, ws_bytes, stream, 0);
+}

@@ -1,0 +1,189 @@
+"""``AdaptiveRSNNEmbedding``: the EAS adaptive event sampler on sm_100a kernels.
+
+Drop-in for ``yolox.models.embedding.AdaptiveRSNNEmbedding`` (``yolox/models/embedding.py:79-226``):
+same constructor, same parameter / state-dict layout (``gate_conv.{0,2}.*``, ``input_conv.{0,2}.*``),
+same ``forward`` contract (4-D passthrough, 5-D ``[B,Tm,2,H,W]``, 6-D ``[B,Tl,Tm,2,H,W]`` ->
+``[Ts, B*Tl, 2, H, W]`` fp32).  New front door: :meth:`forward_events` takes the raw
+``(x, y, t, p)`` stream and runs binning + sampling without the dense tensor ever leaving the GPU
+or being converted to floating point.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .binning import bin_events
+
+
+def _cfg(B, H, W, Tm, mod, in_dtype):
+    return _lib.SamplerCfg(B=B, H=H, W=W, Tm=Tm, Ts=mod.Ts, ksize=mod.kernel_size, depth=mod.depth,
+                           readout=_lib.READOUT[mod.readout], hard_reset=0 if mod.vreset is None else 1,
+                           vreset=0.0 if mod.vreset is None else float(mod.vreset), thresh=float(mod.thresh),
+                           spike_attach=int(bool(mod.spike_attach)), write_zero=int(bool(mod.write_zero)),
+                           use_abs=int(bool(mod.abs)), in_dtype=in_dtype)
+
+
+def _pack_ptrs(tensors):
+    """[in_w0, in_b0, in_w1, in_b1, gate_w0, gate_b0, gate_w1, gate_b1] (None allowed) -> struct."""
+    s = _lib.SamplerPtrs()
+    for name, t in zip(("in_w0", "in_b0", "in_w1", "in_b1", "gate_w0", "gate_b0", "gate_w1", "gate_b1"), tensors):
+        setattr(s, name, None if t is None else t.data_ptr())
+    return s
+
+
+class _SamplerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, events, mod, *params):
+        # params: in_w0, in_b0, [in_w1, in_b1], gate_w0, gate_b0, [gate_w1, gate_b1]
+        L = _lib.lib()
+        B, Tm, Cc, H, W = events.shape
+        in_dtype = _lib.EAS_I32 if events.dtype == torch.int32 else _lib.EAS_F32
+        cfg = _cfg(B, H, W, Tm, mod, in_dtype)
+        if mod.depth == 2:
+            iw0, ib0, iw1, ib1, gw0, gb0, gw1, gb1 = params
+        else:
+            iw0, ib0, gw0, gb0 = params
+            iw1 = ib1 = gw1 = gb1 = None
+        plist = [iw0, ib0, iw1, ib1, gw0, gb0, gw1, gb1]
+        plist = [None if q is None else q.detach().contiguous().float() for q in plist]
+        wstruct = _pack_ptrs(plist)
+        need_grad = torch.is_grad_enabled() and any(q is not None and q.requires_grad for q in params)
+        need_grad = need_grad or (torch.is_grad_enabled() and events.requires_grad)
+        dev = events.device
+        out = torch.empty((mod.Ts, B, 2, H, W), dtype=torch.float32, device=dev)
+        v_seq = gate_seq = None
+        if need_grad:
+            v_seq = torch.empty((Tm, B, 2, H, W), dtype=torch.float32, device=dev)
+            gate_seq = torch.empty_like(v_seq)
+        ws_bytes = L.eas_sampler_fwd_ws_bytes(C.byref(cfg))
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = L.eas_sampler_fwd(C.byref(cfg), _lib.ptr(events), C.byref(wstruct), _lib.ptr(out),
+                                   _lib.ptr(v_seq), _lib.ptr(gate_seq), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+        _lib.check(rc, "eas_sampler_fwd")
+        if need_grad:
+            ctx.mod, ctx.cfg, ctx.plist = mod, cfg, plist
+            ctx.save_for_backward(events, v_seq, gate_seq)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        L = _lib.lib()
+        events, v_seq, gate_seq = ctx.saved_tensors
+        mod, cfg, plist = ctx.mod, ctx.cfg, ctx.plist
+        dev = events.device
+        grad_out = grad_out.contiguous().float()
+        grads = [None if q is None else torch.empty_like(q) for q in plist]
+        gstruct = _pack_ptrs(grads)
+        wstruct = _pack_ptrs(plist)
+        g_ev = None
+        if ctx.needs_input_grad[0]:
+            g_ev = torch.empty(events.shape, dtype=torch.float32, device=dev)
+        ws_bytes = L.eas_sampler_bwd_ws_bytes(C.byref(cfg))
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = L.eas_sampler_bwd(C.byref(cfg), _lib.ptr(events), C.byref(wstruct), _lib.ptr(v_seq),
+                                   _lib.ptr(gate_seq), _lib.ptr(grad_out), C.byref(gstruct), _lib.ptr(g_ev),
+                                   _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+        _lib.check(rc, "eas_sampler_bwd")
+        if mod.depth == 2:
+            gp = grads
+        else:
+            gp = [grads[0], grads[1], grads[4], grads[5]]
+        return (g_ev, None) + tuple(gp)
+
+
+class AdaptiveRSNNEmbedding(nn.Module):
+    """Same signature as the reference class (embedding.py:80-104)."""
+
+    def __init__(self, kernel_size, in_channel=2, out_channel=2, Ts=1, split=False, spike_attach=False,
+                 write_zero=False, abs=False, depth=1, readout="sum", **kwargs_spikes):
+        super().__init__()
+        if in_channel != 2 or out_channel != 2:
+            # the reference's own state is zeros_like(events[0]) (embedding.py:159-160): out == in;
+            # event polarity gives 2 channels (in_dim = 2, event_yolox_base.py:34)
+            raise NotImplementedError("the sm_100a sampler is built for 2 polarity channels")
+        if int(depth) not in (1, 2) or int(kernel_size) not in (3, 5, 7):
+            raise NotImplementedError("sampler kernels are built for depth in {1,2}, kernel_size in {3,5,7}")
+        if readout not in _lib.READOUT:
+            raise NotImplementedError(readout)
+        self.kernel_size = int(kernel_size)
+        self.kwargs_spikes = kwargs_spikes
+        self.Ts = int(Ts)
+        self.abs = abs
+        self.split = split
+        self.readout = readout
+        self.write_zero = write_zero
+        self.nb_steps = kwargs_spikes["nb_steps"] if "Tm" not in kwargs_spikes else kwargs_spikes["Tm"]
+        self.thresh = kwargs_spikes["thresh"]
+        self.vreset = copy.deepcopy(kwargs_spikes["vreset"])
+        fn = kwargs_spikes.get("spike_fn", None)
+        if fn is not None and getattr(fn, "__name__", type(fn).__name__) != "Rectangle":
+            raise NotImplementedError("the sampler kernel implements the Rectangle spike function "
+                                      "(hard-wired by the reference, event_yolox_base.py:156)")
+        self.depth = int(depth)
+        self.gate_conv = self.build_conv(out_channel, out_channel * 2, self.kernel_size, depth=self.depth)
+        self.input_conv = self.build_conv(in_channel, out_channel * 2, self.kernel_size, depth=self.depth)
+        if self.split:  # created but never used by the reference forward (embedding.py:100-102)
+            self.gate_conv_agg = nn.Conv2d(out_channel, out_channel * 2, self.kernel_size,
+                                           padding=self.kernel_size // 2)
+            self.input_conv_agg = nn.Conv2d(in_channel, out_channel * 2, self.kernel_size,
+                                            padding=self.kernel_size // 2)
+        self.spike_attach = spike_attach
+        self._init_weight()
+
+    @staticmethod
+    def build_conv(in_channel, out_channel, kernel_size, depth=1):
+        convs = [nn.Conv2d(in_channel, out_channel, kernel_size, padding=kernel_size // 2)]
+        for _ in range(depth - 1):
+            convs.append(nn.ReLU(inplace=True))
+            convs.append(nn.Conv2d(out_channel, out_channel, kernel_size, padding=kernel_size // 2))
+        return nn.Sequential(*convs)
+
+    def _init_weight(self):
+        for m in self.input_conv.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.orthogonal_(m.weight, gain=nn.init.calculate_gain("relu"))
+        for m in self.gate_conv.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_uniform_(m.weight, nonlinearity="sigmoid")
+
+    def _params(self):
+        ic = [m for m in self.input_conv if isinstance(m, nn.Conv2d)]
+        gc = [m for m in self.gate_conv if isinstance(m, nn.Conv2d)]
+        out = []
+        for convs in (ic, gc):
+            for m in convs:
+                out += [m.weight, m.bias]
+        return out
+
+    def forward(self, events, record=False, v_record=False):
+        if record or v_record:
+            raise NotImplementedError("record / v_record are analysis-only outputs of the reference "
+                                      "(embedding.py:198-199, 221-224) and are not produced by the fused kernel")
+        if events.dim() < 5:  # parameter-registering passthrough (embedding.py:144-146)
+            events, _ = torch.broadcast_tensors(events, torch.zeros((self.Ts,) + events.shape,
+                                                                    device=events.device))
+            return events
+        if events.dim() > 5:
+            events = events.flatten(end_dim=-5)
+        _lib.require_cuda(events)
+        if events.shape[2] != 2:
+            raise ValueError("expected [B, Tm, 2, H, W] micro-bin tensor")
+        if events.dtype not in (torch.float32, torch.int32):
+            events = events.float()
+        events = events.contiguous()
+        return _SamplerFn.apply(events, self, *self._params())
+
+    def forward_events(self, x, y, t, p, offsets, H: int, W: int, strategy: str = "auto"):
+        """Raw time-sorted event windows -> adaptive frames ``[Ts, B, 2, H, W]``.
+
+        Binning (gen1.py:313-360) and sampling (embedding.py:141-226) back to back on the GPU;
+        the int32 histogram is consumed directly by the sampler kernel.
+        """
+        hist = bin_events(x, y, t, p, offsets, H, W, self.nb_steps, strategy=strategy)
+        return self.forward(hist)

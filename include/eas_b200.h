@@ -1,0 +1,178 @@
+/*
+ * eas_b200.h -- C ABI of libeas_b200.so: the B200 (sm_100a) hot path of EAS-SNN.
+ *
+ * The reference (Windere/EAS-SNN) has no FFI on this path: its seam is Python nn.Module
+ * substitution.  These entry points are what a ctypes binding on the
+ * reference side calls; each one names the reference code it replaces.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked "host";
+ *   - the caller owns every buffer including the workspace; the library never allocates,
+ *     never synchronises, keeps no mutable global state; all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*, e.g. torch.cuda.current_stream().cuda_stream);
+ *   - return value: 0 = ok; negative = argument/shape contract violation detected on the host
+ *     before anything is launched (EAS_E_*); positive = cudaError_t of a failed launch;
+ *   - reentrant: safe from several host threads / streams of one process (one process per GPU).
+ */
+#ifndef EAS_B200_H_
+#define EAS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EAS_ABI_VERSION 1
+
+enum {
+  EAS_OK = 0,
+  EAS_E_NULL = -1,        /* a required pointer is NULL                     */
+  EAS_E_SHAPE = -2,       /* a dimension is out of the supported range      */
+  EAS_E_UNSUPPORTED = -3, /* flag / dtype / kernel-size combination missing */
+  EAS_E_WORKSPACE = -4,   /* workspace too small                            */
+  EAS_E_ALIGN = -5        /* pointer not aligned as required                */
+};
+
+enum { EAS_F32 = 0, EAS_I32 = 1, EAS_BF16 = 2, EAS_U8 = 3 };
+enum { EAS_READOUT_SUM = 0, EAS_READOUT_LAST = 1, EAS_READOUT_AVG = 2 };
+enum { EAS_SG_ATAN = 0, EAS_SG_SIGMOID = 1, EAS_SG_RECT = 2 };
+
+int eas_abi_version(void);
+/* Human readable text for a negative EAS_E_* code or a positive cudaError_t. */
+const char* eas_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * (a-1) Event binning.  Replaces GEN1Dataset.slice_events + agrregate('micro_sum' -> 'sum')
+ *       yolox/data/datasets/gen1.py:313-328, 330-360 (same code: gen4.py, rvt_gen4.py:411-454).
+ *
+ * B independent, time-sorted windows stored back to back in SoA form (the reference's
+ * events_struct, yolox/utils/util.py:119-121); window b is events [offsets[b], offsets[b+1]).
+ * Output hist[B][Tm][2][H][W] int32 counts, written completely (no pre-zeroing needed):
+ *   tw = (t_last - t_first) / Tm (integer), micro-bin k = [t0 + k*tw, t0 + (k+1)*tw),
+ *   events at or after t0 + Tm*tw are dropped, tw == 0 -> all bins empty,
+ *   channel 0 <- p == 0, channel 1 <- p != 0, pixel = y*W + x.
+ * Events whose (x, y) fall outside [0,W) x [0,H) are ignored (the reference would raise).
+ * n_events = offsets[B] (known to the host from the array length) sizes the launch.
+ * ---------------------------------------------------------------------------------------- */
+size_t eas_bin_events_ws_bytes(int64_t B, int Tm);
+int eas_bin_events(const int16_t* x, const int16_t* y, const int64_t* t, const uint8_t* p,
+                   const int64_t* offsets, int64_t B, int64_t n_events, int H, int W, int Tm,
+                   int32_t* hist, void* ws, size_t ws_bytes, void* stream);
+/* Same, forcing one strategy: 0 = auto, 1 = global reductions, 2 = shared-memory tiles. */
+int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64_t* t, const uint8_t* p,
+                      const int64_t* offsets, int64_t B, int64_t n_events, int H, int W, int Tm,
+                      int32_t* hist, void* ws, size_t ws_bytes, void* stream, int strategy);
+
+/* ------------------------------------------------------------------------------------------
+ * (a-2) Adaptive event sampler.  Replaces AdaptiveRSNNEmbedding.forward / update,
+ *       yolox/models/embedding.py:132-226 with the Rectangle surrogate, activation.py:17-30.
+ *
+ * events [B][Tm][2][H][W] (f32, or the int32 histogram of eas_bin_events);
+ * weights of input_conv / gate_conv in PyTorch layout: w0 [4][2][k][k], b0 [4] and, for
+ * depth == 2, w1 [4][4][k][k], b1 [4] (pass NULL for depth 1);
+ * out [Ts][B][2][H][W] f32, fully written.
+ * For training pass v_seq / gate_seq ([Tm][B][2][H][W] f32 each, in the sampler's own
+ * newest-first step order); for inference pass NULL.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, H, W, Tm, Ts;
+  int32_t ksize;        /* 3, 5 or 7                                            */
+  int32_t depth;        /* 1 or 2                                               */
+  int32_t readout;      /* EAS_READOUT_*                                        */
+  int32_t hard_reset;   /* 1: vm = v*(1-s) + vreset*s ; 0: vm = v - thresh*s     */
+  float vreset;
+  float thresh;
+  int32_t spike_attach; /* SAT: read-out multiplied by the spike                 */
+  int32_t write_zero;   /* RPD: residual potential of silent pixels dropped      */
+  int32_t use_abs;      /* relu on the aggregated frames                         */
+  int32_t in_dtype;     /* EAS_F32 or EAS_I32                                    */
+} eas_sampler_cfg;
+
+typedef struct {
+  const float *in_w0, *in_b0, *in_w1, *in_b1;
+  const float *gate_w0, *gate_b0, *gate_w1, *gate_b1;
+} eas_sampler_weights;
+
+size_t eas_sampler_fwd_ws_bytes(const eas_sampler_cfg* cfg);
+int eas_sampler_fwd(const eas_sampler_cfg* cfg, const void* events, const eas_sampler_weights* w,
+                    float* out, float* v_seq, float* gate_seq, void* ws, size_t ws_bytes, void* stream);
+
+/* Backward (BPTT, Rectangle surrogate window |v - thresh| < 0.5).  grad_out [Ts][B][2][H][W];
+ * v_seq / gate_seq as saved by the forward; the eight gradient buffers have the shapes of the
+ * corresponding weights and are OVERWRITTEN; grad_events may be NULL. */
+typedef struct {
+  float *in_w0, *in_b0, *in_w1, *in_b1;
+  float *gate_w0, *gate_b0, *gate_w1, *gate_b1;
+} eas_sampler_grads;
+size_t eas_sampler_bwd_ws_bytes(const eas_sampler_cfg* cfg);
+int eas_sampler_bwd(const eas_sampler_cfg* cfg, const void* events, const eas_sampler_weights* w,
+                    const float* v_seq, const float* gate_seq, const float* grad_out,
+                    const eas_sampler_grads* gw, float* grad_events, void* ws, size_t ws_bytes,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (a-4) Multi-step parametric LIF.  Replaces spikingjelly 0.0.0.0.14
+ *       neuron.ParametricLIFNode (step_mode 'm', backend 'torch') as configured at
+ *       yolox/utils/utils_snn.py:44-53.
+ *
+ * x, spikes: [T][N] (N = product of the remaining dims), f32 or bf16.  w: device scalar (f32).
+ *   decay_input == 0:  h = v*(1-sigmoid(w)) + x        (v_reset None/0)
+ *   decay_input == 1:  h = v + (x - v)*sigmoid(w)
+ *   s = (h - v_th >= 0);  soft reset v = h - s*v_th  |  hard reset v = (1-s)*h + s*v_reset
+ * v0 (optional, [N] f32) initial potential, NULL = zeros(+v_reset); v_out (optional, [N] f32)
+ * final potential.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t T, N;
+  float v_threshold;
+  int32_t hard_reset;
+  float v_reset;
+  int32_t decay_input;
+  int32_t detach_reset;
+  int32_t surrogate;    /* EAS_SG_*  (backward only) */
+  float alpha;
+  int32_t dtype;        /* EAS_F32 or EAS_BF16 (x, spikes, grads) */
+} eas_plif_cfg;
+
+int eas_plif_fwd(const eas_plif_cfg* cfg, const void* x, const float* w, const float* v0,
+                 void* spikes, float* v_out, void* stream);
+size_t eas_plif_bwd_ws_bytes(const eas_plif_cfg* cfg);
+/* grad_w: device scalar, OVERWRITTEN with d loss / d w. */
+int eas_plif_bwd(const eas_plif_cfg* cfg, const void* x, const float* w, const float* v0,
+                 const void* grad_spikes, void* grad_x, float* grad_w, void* ws, size_t ws_bytes,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (a-5) conv -> BatchNorm (folded) -> multi-step PLIF, inference.  Replaces
+ *       BaseConv.forward after convert_to_spiking: SeqToANNContainer(Conv2d) ->
+ *       layer.BatchNorm2d('m') -> ParametricLIFNode, yolox/models/network_blocks.py:52-53,
+ *       yolox/utils/utils_snn.py:25-53; BN folding per yolox/utils/model_utils.py:61-75.
+ *
+ * Activations are channels-last bf16: x [Tx][B][H][W][Cin] with Tx == T, or Tx == 1 when the
+ * input is the same for every time step (sampler output broadcast, spiking_yolox.py:54-55).
+ * Weights: n_wsplit bf16 planes [n_wsplit][Cout][kh][kw][Cin] whose sum is the BN-folded fp32
+ * weight (1 plane = "fast", 3 planes = fp32-equivalent for integer-valued spike inputs);
+ * n_xsplit input planes likewise for real-valued inputs.  bias [Cout] f32 (folded BN shift).
+ * Output spikes [T][B][Ho][Wo][Cout] bf16 (0/1).  Tensor-core path (tcgen05 + TMEM + TMA).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t T, Tx, B, H, W, Cin, Cout, ksize, stride;
+  int32_t n_wsplit, n_xsplit;
+  float v_threshold;
+  int32_t hard_reset;
+  float v_reset;
+  int32_t decay_input;
+  int32_t out_mode;     /* 0: spikes bf16; 1: pre-activation f32 (debug / non-spiking) */
+} eas_conv_cfg;
+
+size_t eas_conv_bn_plif_ws_bytes(const eas_conv_cfg* cfg);
+int eas_conv_bn_plif_fwd(const eas_conv_cfg* cfg, const void* x, const void* w_planes,
+                         const float* bias, const float* plif_w, void* out, void* ws,
+                         size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EAS_B200_H_ */

@@ -1,0 +1,176 @@
+"""Generate the committed golden vectors by EXECUTING THE REFERENCE in the authoring container.
+
+    python tests/golden/make_golden.py          # needs /root/reference (read-only)
+
+Outputs (small, committed): tests/golden/binning.npz, sampler.npz, backbone.npz.
+The reference is imported in place through ``oracle/ref_loader.py``; nothing is copied from it.
+``/root/reference`` does not exist on the GPU box, so tests only ever read the .npz files.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+from eas_snn_b200 import synth  # noqa: E402
+
+
+def struct_events(x, y, t, p):
+    from yolox.utils.util import events_struct
+    ev = np.zeros(len(x), dtype=events_struct)
+    ev["x"], ev["y"], ev["t"], ev["p"] = x, y, t, p.astype(bool)
+    return ev
+
+
+def binning_cases():
+    rng = np.random.default_rng(7)
+    cases = []
+
+    def add(name, x, y, t, p, H, W, Tm):
+        cases.append(dict(name=name, x=np.asarray(x, np.int16), y=np.asarray(y, np.int16),
+                          t=np.asarray(t, np.int64), p=np.asarray(p, np.uint8), H=H, W=W, Tm=Tm))
+
+    x, y, t, p = synth.make_window(rng, 5000, 40, 48)
+    add("uniform_40x48_tm4", x, y, t, p, 40, 48, 4)
+    x, y, t, p = synth.make_window(rng, 3000, 40, 48, span_us=300)           # many duplicate timestamps
+    add("dupes_40x48_tm5", x, y, t, p, 40, 48, 5)
+    x, y, t, p = synth.make_window(rng, 4001, 33, 47, span_us=7919)          # odd H*W (scalar store path)
+    add("odd_33x47_tm6", x, y, t, p, 33, 47, 6)
+    add("single_event", [3], [2], [1000], [1], 8, 8, 4)                      # tw == 0 -> all empty
+    add("three_events_tm4", [1, 2, 3], [1, 2, 3], [10, 11, 12], [0, 1, 0], 8, 8, 4)  # tw == 0
+    add("same_timestamp", rng.integers(0, 8, 50), rng.integers(0, 8, 50), np.full(50, 77), rng.integers(0, 2, 50),
+        8, 8, 4)
+    add("exact_windows", np.arange(8) % 8, np.zeros(8), np.arange(8) * 10, np.arange(8) % 2, 8, 8, 4)
+    add("offset_t0", rng.integers(0, 16, 400), rng.integers(0, 12, 400),
+        np.sort(rng.integers(10**12, 10**12 + 50_000, 400)), rng.integers(0, 2, 400), 12, 16, 4)
+    x, y, t, p = synth.make_window(rng, 20000, 240, 304)
+    add("gen1_240x304_tm4", x, y, t, p, 240, 304, 4)
+    # one pixel receiving > 65535 events in a micro-bin: exercises the 16-bit chunking of the tile kernel
+    n = 150_000
+    add("hot_pixel_overflow", np.full(n, 5), np.full(n, 6), np.sort(rng.integers(0, 1000, n)), np.ones(n), 16, 16, 2)
+    return cases
+
+
+def make_binning(gen1):
+    out = {}
+    cases = binning_cases()
+    for c in cases:
+        ds = ref_loader.make_ref_dataset(gen1, c["H"], c["W"], c["Tm"])
+        ref = ds.agrregate(struct_events(c["x"], c["y"], c["t"], c["p"]), "micro_sum")
+        assert ref.shape == (c["Tm"], 2, c["H"], c["W"]) and ref.dtype == np.float64
+        assert np.all(ref == np.round(ref))
+        n = c["name"]
+        for k in ("x", "y", "t", "p"):
+            out[f"{n}/{k}"] = c[k]
+        out[f"{n}/dims"] = np.array([c["H"], c["W"], c["Tm"]], np.int64)
+        out[f"{n}/hist"] = ref.astype(np.int32)
+    # reference behaviour for "no events": zeros (gen1.py:356-358)
+    ds = ref_loader.make_ref_dataset(gen1, 8, 8, 4)
+    assert not ds.agrregate(None, "micro_sum").any()
+    out["names"] = np.array([c["name"] for c in cases])
+    np.savez_compressed(os.path.join(HERE, "binning.npz"), **out)
+    print("binning.npz:", len(cases), "cases")
+
+
+SAMPLER_CASES = [
+    # name, B, H, W, Tm, Ts, ksize, depth, readout, vreset, spike_attach, write_zero, abs, rate
+    ("published_sat_rpd", 2, 40, 48, 4, 1, 5, 2, "sum", 0, True, True, False, 1.5),
+    ("ts2_avg_soft_abs", 2, 40, 48, 5, 2, 5, 2, "avg", None, False, False, True, 1.5),
+    ("ts3_last_hard", 2, 40, 48, 6, 3, 5, 2, "last", 0, True, False, False, 1.5),
+    ("depth1_k7_default", 2, 40, 48, 4, 1, 7, 1, "sum", 0, False, False, False, 1.0),
+    ("depth1_k3_ts2", 1, 37, 70, 4, 2, 3, 1, "sum", None, True, True, False, 2.0),
+    ("depth2_k3_ragged", 1, 19, 67, 3, 1, 3, 2, "sum", 0, True, True, False, 2.0),
+    ("depth2_k7", 1, 24, 40, 4, 1, 7, 2, "sum", 0.25, False, False, False, 1.0),
+]
+
+
+def make_sampler(emb, act):
+    from yolox.utils.util import warp_decay
+    out = {}
+    names = []
+    for (name, B, H, W, Tm, Ts, k, depth, readout, vreset, sa, wz, ab, rate) in SAMPLER_CASES:
+        torch.manual_seed(80)
+        m = emb.AdaptiveRSNNEmbedding(kernel_size=k, in_channel=2, out_channel=2, readout=readout, split=False,
+                                      write_zero=wz, abs=ab, depth=depth, nb_steps=Tm, vreset=vreset, thresh=1,
+                                      spike_fn=act.Rectangle, decay=nn.Parameter(warp_decay(0.5)),
+                                      embedding="arsnn", Ts=Ts, spike_attach=sa)
+        g = torch.Generator().manual_seed(1234)
+        x = torch.poisson(torch.full((B, Tm, 2, H, W), rate), generator=g)
+        y = m(x)
+        with torch.no_grad():  # fraction of pixels that fired at least once (t_last >= 0 at the end)
+            _, rec = m(x, record=True)
+        nz = float((rec[-1] >= 0).float().mean())
+        assert 0.05 < nz < 0.95, (name, nz)
+        wgt = torch.linspace(-1.0, 1.0, y.numel()).view_as(y)
+        grads = torch.autograd.grad((y * wgt).sum(), list(m.parameters()))
+        cfg = dict(B=B, H=H, W=W, Tm=Tm, Ts=Ts, ksize=k, depth=depth, readout=readout,
+                   vreset=-1e30 if vreset is None else vreset, spike_attach=sa, write_zero=wz, abs=ab)
+        out[f"{name}/cfg"] = np.array([repr(cfg)])
+        out[f"{name}/x"] = x.numpy().astype(np.uint8)
+        out[f"{name}/y"] = y.detach().numpy()
+        for (pn, pv), gv in zip(m.named_parameters(), grads):
+            out[f"{name}/param/{pn}"] = pv.detach().numpy()
+            out[f"{name}/grad/{pn}"] = gv.numpy()
+        names.append(name)
+        print(" sampler", name, "fired %.3f" % nz, "out", tuple(y.shape))
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "sampler.npz"), **out)
+    print("sampler.npz:", len(names), "cases")
+
+
+def make_backbone():
+    """Tiny-width spiking CSPDarknet built by the REFERENCE code (darknet.py + utils_snn.py) through
+    the spikingjelly shim; BN calibrated so that every stage fires."""
+    exp, model = ref_loader.load_full_model("e-yolox-s", ["T", 3, "embedding", "arsnn", "embedding_depth", 2,
+                                                          "embedding_ksize", 5, "spike_attach", True,
+                                                          "write_zero", True, "spike_fn", "atan",
+                                                          "use_spike", True, "num_classes", 2])
+    from yolox.models.darknet import CSPDarknet
+    from yolox.utils.utils_snn import convert_to_spiking
+    from spikingjelly.activation_based import surrogate, functional
+    from oracle.backbone import calibrate_bn
+    torch.manual_seed(80)
+    bb = CSPDarknet(0.33, 0.125, in_dim=2, act="silu")
+    bb = convert_to_spiking(bb, surrogate.ATan(2.0))
+    for m in bb.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.eps, m.momentum = 1e-3, 0.03
+    g = torch.Generator().manual_seed(5)
+    frame = torch.rand((1, 2, 2, 64, 96), generator=g) * 3.0
+    x = frame.expand(3, -1, -1, -1, -1).contiguous()     # Ts == 1 broadcast to T == 3 (spiking_yolox.py:54-55)
+    calibrate_bn(bb, x, seed=3)
+    # perturb the PLIF decay parameter so sigmoid(w) != 0.5 is exercised
+    for i, m in enumerate(mm for mm in bb.modules() if hasattr(mm, "w") and isinstance(mm.w, nn.Parameter)):
+        m.w.data.fill_(0.3 * ((i % 5) - 2))
+    with torch.no_grad():
+        outs = bb(x)
+        functional.reset_net(bb)
+    out = {"x": x.numpy()}
+    for k, v in bb.state_dict().items():
+        out["sd/" + k] = v.numpy()
+    for k, v in outs.items():
+        rate = float(v.mean())
+        assert 0.01 < rate < 0.9, (k, rate)
+        out["out/" + k] = v.numpy().astype(np.uint8)
+        print(" backbone", k, tuple(v.shape), "rate %.3f" % rate)
+    np.savez_compressed(os.path.join(HERE, "backbone.npz"), **out)
+    print("backbone.npz written, params:", sum(p.numel() for p in bb.parameters()))
+
+
+if __name__ == "__main__":
+    assert ref_loader.available(), "reference tree not found"
+    torch.set_num_threads(8)
+    emb, act, gen1 = ref_loader.load_hot_modules()
+    make_binning(gen1)
+    make_sampler(emb, act)
+    make_backbone()
+    for f in ("binning.npz", "sampler.npz", "backbone.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

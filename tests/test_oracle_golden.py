@@ -1,0 +1,67 @@
+"""CPU: the oracle restatements reproduce the golden vectors generated from the reference itself
+(tests/golden/make_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import binning, sampler, backbone
+from oracle.plif import ATan
+from helpers import load_golden, sampler_case, sampler_kwargs
+
+
+def test_binning_golden_all_cases():
+    z = load_golden("binning")
+    for name in z["names"]:
+        H, W, Tm = (int(v) for v in z[f"{name}/dims"])
+        got = binning.micro_sum(z[f"{name}/x"], z[f"{name}/y"], z[f"{name}/t"], z[f"{name}/p"], H, W, Tm)
+        assert got.dtype == np.float64 and got.shape == (Tm, 2, H, W)
+        assert np.array_equal(got.astype(np.int32), z[f"{name}/hist"]), name
+
+
+def test_binning_tail_drop_and_empty():
+    z = load_golden("binning")
+    # events at or after t0 + Tm*tw are dropped: the uniform case loses a few
+    n = "uniform_40x48_tm4"
+    assert 0 < len(z[f"{n}/x"]) - int(z[f"{n}/hist"].sum()) < 100
+    assert int(z["single_event/hist"].sum()) == 0 and int(z["same_timestamp/hist"].sum()) == 0
+    e = np.zeros(0, np.int16)
+    assert not binning.micro_sum(e, e, np.zeros(0, np.int64), np.zeros(0, np.uint8), 8, 8, 4).any()
+
+
+def test_binning_batch_matches_per_window():
+    z = load_golden("binning")
+    names = ["uniform_40x48_tm4", "dupes_40x48_tm5"]
+    xs = [z[f"{n}/x"] for n in names]
+    offs = np.array([0, len(xs[0]), len(xs[0]), len(xs[0]) + len(xs[1])])  # middle window empty
+    cat = lambda k: np.concatenate([z[f"{n}/{k}"] for n in names])
+    got = binning.micro_sum_batch(cat("x"), cat("y"), cat("t"), cat("p"), offs, 40, 48, 4)
+    assert np.array_equal(got[0].astype(np.int32), z[f"{names[0]}/hist"])
+    assert not got[1].any()
+    assert got[2].sum() > 0
+
+
+@pytest.mark.parametrize("name", list(load_golden("sampler")["names"]))
+def test_sampler_golden(name):
+    z = load_golden("sampler")
+    cfg, params, grads, x, y = sampler_case(z, name)
+    m = sampler.OracleSampler(**sampler_kwargs(cfg))
+    m.load_state_dict(params)
+    out = m(x)
+    assert torch.equal(out, y), name
+    wgt = torch.linspace(-1.0, 1.0, out.numel()).view_as(out)
+    got = torch.autograd.grad((out * wgt).sum(), list(m.parameters()))
+    for (pn, _), g in zip(m.named_parameters(), got):
+        assert torch.allclose(g, grads[pn], rtol=1e-6, atol=1e-6), (name, pn)
+
+
+def test_backbone_golden():
+    z = load_golden("backbone")
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    net = backbone.SpikingCSPDarknet(0.33, 0.125, in_dim=2, spike_fn=ATan(2.0))
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    with torch.no_grad():
+        outs = net(torch.from_numpy(z["x"]))
+    for k in ("dark3", "dark4", "dark5"):
+        assert torch.equal(outs[k], torch.from_numpy(z["out/" + k]).float()), k
+        assert 0.01 < float(outs[k].mean()) < 0.9
