@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the EAS-SNN hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): "Mevents/s sampled+encoded" = events / (t_binning + t_sampler) on
+BASELINE config[1]: Gen1 (240x304) windows at Gen1 event rate, batch 64 per GPU, Tm=4 micro-bins,
+published sampler flags (depth 2, k 5, SAT + RPD, Ts=1).  One "step" = eas_bin_events +
+eas_sampler_fwd over one batch of 64 synthetic windows.  Windows shard by sequence across ranks with
+no collective -> weak scaling (64 windows per GPU).
+
+  value : inputs already resident in HBM, CUDA-event timed, max over ranks
+  e2e   : same step through the public module API from pinned HOST buffers: H2D of (x,y,t,p,offsets)
+          and D2H of the sampled frames inside the timed region (3-stream pipeline)
+  roofline / cpu_baseline / clocks: see DESIGN.md "Measurement"
+--impl reference times the reference algorithm's CPU restatement (oracle/, numpy + torch CPU, all
+host threads) on the same workload; the reference itself is Python that cannot travel to the GPU
+box, so kind = "port".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, TM, TS, BATCH = 240, 304, 4, 1, 64
+NSETS = 4  # rotating input batches: 4 x ~60 MB events (+150 MB histogram per step) > 126 MB L2
+SAMPLER_KW = dict(kernel_size=5, in_channel=2, out_channel=2, readout="sum", split=False, write_zero=True,
+                  abs=False, depth=2, nb_steps=TM, vreset=0, thresh=1, embedding="arsnn", Ts=TS, spike_attach=True)
+WORKLOAD = "gen1_240x304_b64_Tm4_sampler_d2k5_sat_rpd"
+METRIC, UNIT = "Mevents/s sampled+encoded", "Mevents/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def host_batches(rank: int, batch: int):
+    from eas_snn_b200 import synth
+    return [synth.gen1_batch(batch, cfg=2, first_sample=(rank * NSETS + s) * batch) for s in range(NSETS)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        rows = []
+        for line in open(self.path):
+            f = [c.strip() for c in line.split(",")]
+            if len(f) >= 9:
+                rows.append(f)
+        os.unlink(self.path)
+        if not rows:
+            return out
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in rows:
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if r[col].lower().startswith("active"):
+                    reasons.add(name)
+        out.update(sm_mhz=float(np.median(sm)) if sm else None,
+                   sm_max_mhz=float(rows[0][2]) if rows[0][2].replace(".", "").isdigit() else None,
+                   reasons=sorted(reasons), samples=len(rows))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU restatement of the reference path (oracle/): the cpu_baseline leg and the --impl reference arm
+# ------------------------------------------------------------------------------------------------
+def cpu_step(model, batch):
+    from oracle import binning as ob
+    x, y, t, p, off = batch
+    hist = ob.micro_sum_batch(x, y, t, p, off, H, W, TM)           # gen1.py:313-360 (numpy, 1 thread)
+    with torch.no_grad():
+        frames = model(torch.from_numpy(hist).float())             # embedding.py:141-226 (torch CPU, all threads)
+    return frames
+
+
+def make_cpu_model():
+    from oracle.sampler import OracleSampler
+    torch.manual_seed(80)
+    return OracleSampler(**SAMPLER_KW).eval()
+
+
+def cpu_baseline(budget_s: float = 12.0, windows: int = 16):
+    """Bounded sample: `windows` windows of the rank-0 workload, repeated until ~budget_s."""
+    from eas_snn_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = make_cpu_model()
+    batch = synth.gen1_batch(windows, cfg=2, first_sample=0)
+    n = int(batch[4][-1])
+    cpu_step(model, synth.gen1_batch(2, cfg=2, first_sample=0))   # warm-up
+    times, t_end = [], time.perf_counter() + budget_s
+    while len(times) < 2 or (time.perf_counter() < t_end and len(times) < 50):
+        t0 = time.perf_counter()
+        cpu_step(model, batch)
+        times.append(time.perf_counter() - t0)
+    med = float(np.median(times))
+    return {"value": n / med / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d of the %d windows of one batch (%d events), median of %d passes; numpy binning "
+                      "(1 thread) + torch-CPU sampler (%d threads)" % (windows, BATCH, n, len(times), cores)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from eas_snn_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = make_cpu_model()
+    windows = 16   # bounded sample of the 64-window batch so K steps end within minutes
+    sets = [synth.gen1_batch(windows, cfg=2, first_sample=s * BATCH) for s in range(NSETS)]
+    for w in range(args.warmup):
+        cpu_step(model, sets[w % NSETS])
+    n_ev, t0 = 0, time.perf_counter()
+    for k in range(args.steps):
+        cpu_step(model, sets[k % NSETS])
+        n_ev += int(sets[k % NSETS][4][-1])
+    dt = time.perf_counter() - t0
+    val = n_ev / dt / 1e6
+    sample = ("each step = %d of the %d windows of a batch; numpy binning (1 thread) + torch-CPU sampler "
+              "(%d threads)" % (windows, BATCH, cores))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "H": H, "W": W, "Tm": TM, "Ts": TS,
+                       "note": "CPU restatement (oracle/) of the reference path; the Python reference cannot "
+                               "travel to the GPU box"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import eas_snn_b200 as eas
+    from eas_snn_b200 import parallel
+    from eas_snn_b200.binning import HostEventBatch
+
+    rank, world, local = parallel.init_distributed("nccl")
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    peak_gbs, peak_src, sm_max_mhz = load_peaks()
+
+    torch.manual_seed(80)
+    model = eas.AdaptiveRSNNEmbedding(**SAMPLER_KW).to(dev).eval()
+    host = [HostEventBatch(*b) for b in host_batches(rank, BATCH)]
+    devb = [hb.to_device(dev) for hb in host]
+    hist_buf = torch.empty((BATCH, TM, 2, H, W), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    def step(db):
+        hist = eas.bin_events(*db, H, W, TM, out=hist_buf)
+        with torch.no_grad():
+            return model(hist)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM ---------------------------------------------------------
+    for w in range(max(args.warmup, 3)):
+        step(devb[w % NSETS])
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_ev = 0
+    e0.record()
+    for k in range(args.steps):
+        step(devb[k % NSETS])
+        n_ev += host[k % NSETS].n
+    e1.record()
+    barrier()
+    ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
+    clk = clocks.stop()
+    total_ev = parallel.sum_over_ranks(n_ev, dev)
+    value = total_ev / ms / 1e3
+
+    # ---- e2e: pinned host buffers -> H2D -> bin -> sample -> D2H, 3-stream pipeline ------------
+    nmax = max(h.n for h in host)
+    s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    slots = []
+    for _ in range(2):
+        slots.append(dict(x=torch.empty(nmax, dtype=torch.int16, device=dev),
+                          y=torch.empty(nmax, dtype=torch.int16, device=dev),
+                          t=torch.empty(nmax, dtype=torch.int64, device=dev),
+                          p=torch.empty(nmax, dtype=torch.uint8, device=dev),
+                          off=torch.empty(BATCH + 1, dtype=torch.int64, device=dev),
+                          hist=torch.empty((BATCH, TM, 2, H, W), dtype=torch.int32, device=dev),
+                          host_out=torch.empty((TS, BATCH, 2, H, W), dtype=torch.float32).pin_memory(),
+                          in_ready=torch.cuda.Event(), cmp_done=torch.cuda.Event(), out_done=torch.cuda.Event()))
+    h2d_bytes = int(np.mean([h.nbytes for h in host]))
+    d2h_bytes = TS * BATCH * 2 * H * W * 4
+
+    def e2e_loop(steps):
+        n = 0
+        for k in range(steps):
+            sl, hb = slots[k % 2], host[k % NSETS]
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(sl["cmp_done"])          # slot's previous compute finished reading inputs
+                sl["x"][:hb.n].copy_(hb.x, non_blocking=True)
+                sl["y"][:hb.n].copy_(hb.y, non_blocking=True)
+                sl["t"][:hb.n].copy_(hb.t, non_blocking=True)
+                sl["p"][:hb.n].copy_(hb.p, non_blocking=True)
+                sl["off"].copy_(hb.offsets, non_blocking=True)
+                sl["in_ready"].record(s_in)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(sl["in_ready"])
+                hist = eas.bin_events(sl["x"][:hb.n], sl["y"][:hb.n], sl["t"][:hb.n], sl["p"][:hb.n], sl["off"],
+                                      H, W, TM, out=sl["hist"])
+                with torch.no_grad():
+                    frames = model(hist)                 # public module API
+                frames.record_stream(s_out)
+                sl["cmp_done"].record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(sl["cmp_done"])
+                sl["host_out"].copy_(frames, non_blocking=True)
+                sl["out_done"].record(s_out)
+            n += hb.n
+        return n
+
+    e2e_loop(max(args.warmup, 3))
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = e2e_loop(args.steps)
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = parallel.max_over_ranks(wall_ms, dev)
+    e2e_val = parallel.sum_over_ranks(n_e2e, dev) / e2e_ms / 1e3
+    checksum = float(slots[(args.steps - 1) % 2]["host_out"].abs().sum())
+
+    # ---- per-kernel durations (CUDA events on the launching stream) for the roofline -----------
+    def time_call(fn, reps=10):
+        ts = []
+        for r in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(r)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+
+    t_bin = time_call(lambda r: eas.bin_events(*devb[r % NSETS], H, W, TM, out=hist_buf))
+    hist_fixed = eas.bin_events(*devb[0], H, W, TM).clone()
+    with torch.no_grad():
+        t_smp = time_call(lambda r: model(hist_fixed))
+    n_avg = float(np.mean([h.n for h in host]))
+    bins = BATCH * TM * 2 * H * W
+    bin_bytes = 13.0 * n_avg + 4.0 * bins                 # 13 B/event + 4 B/bin
+    bin_bytes_touched = 5.0 * n_avg + 4.0 * bins          # t is only touched by the Tm+1 binary searches
+    smp_launch_ms = t_smp / TM
+    smp_bytes_launch = 8.0 * H * W * (TM + TS) * BATCH / TM   # SURVEY 8d, per launch (one of Tm steps)
+    smp_flop_launch = 2400.0 * H * W * BATCH                  # 2400 FLOP per pixel-step
+    fp32_peak = EAS_FP32_PEAK(sm_max_mhz)
+    roofline = {
+        "kernel": "sampler_step_kernel (dominant: %.0f%% of the step)" % (100.0 * t_smp / (t_smp + t_bin)),
+        "bound": "hbm", "achieved": smp_bytes_launch / smp_launch_ms / 1e6, "peak": peak_gbs, "unit": "GB/s",
+        "frac": smp_bytes_launch / smp_launch_ms / 1e6 / peak_gbs, "traffic": None, "peak_source": peak_src,
+        "launch_ms": smp_launch_ms,
+        "note": "this kernel is FP32-pipe bound (240 FLOP/B), not HBM bound: see fp32",
+        "fp32": {"achieved": smp_flop_launch / smp_launch_ms / 1e9, "peak": fp32_peak, "unit": "TFLOP/s",
+                 "frac": smp_flop_launch / smp_launch_ms / 1e9 / fp32_peak,
+                 "peak_source": "148 SMs x 128 lanes x 2 x %.0f MHz" % sm_max_mhz},
+        "others": {"bin_events (bounds + tiles)": {
+            "bound": "hbm", "call_ms": t_bin, "achieved": bin_bytes / t_bin / 1e6, "peak": peak_gbs,
+            "unit": "GB/s", "frac": bin_bytes / t_bin / 1e6 / peak_gbs,
+            "achieved_bytes_touched": bin_bytes_touched / t_bin / 1e6}},
+    }
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "H": H, "W": W, "Tm": TM, "Ts": TS,
+                       "events_per_step_per_gpu": int(n_avg), "parallelism": "sequence-sharded x%d, no collective" % world,
+                       "l2": "inputs rotate over %d batches (%d MB events) + 150 MB histogram per step > 126 MB L2"
+                             % (NSETS, int(NSETS * n_avg * 13 / 1e6))},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": e2e_ms / args.steps, "pipeline": "3 streams (H2D / compute / D2H), 2 slots",
+                    "checksum": checksum},
+            "gpu_launches": args.steps * (2 + TM),
+            "clocks": clk, "roofline": roofline}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def EAS_FP32_PEAK(sm_mhz: float) -> float:
+    return 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -6,13 +6,15 @@
 //
 // Two kernels run per call:
 //   1. bin_bounds_kernel: per window, tw = (t_last - t_first)/Tm and Tm+1 lower_bound searches on
-//      the sorted timestamps.  After this nobody reads t again: membership of an event in a
-//      micro-bin is an index-range test, exactly like the reference's searchsorted slicing.
+//      the sorted timestamps (one warp per search, 32-ary).  After this nobody reads t again:
+//      membership of an event in a micro-bin is an index-range test, exactly like the reference's
+//      searchsorted slicing.
 //   2. one of
-//      bin_hist_smem_kernel  ("tiles"): one CTA owns one (window, micro-bin, polarity) output tile,
-//         counts it in shared memory as packed 16-bit lanes (H*W*2 B <= 200 KB) and writes the tile
-//         once with 16 B stores: no global atomics, no pre-zeroing, HBM traffic = 5 B/event (x2 in
-//         L2) + 4 B/bin.  Chunks of <= 65535 events make 16-bit overflow impossible.
+//      bin_hist_smem_kernel  ("tiles"): a CTA takes (window, micro-bin, polarity, row slab) work items
+//         from an atomic counter, counts a slab in shared memory as packed 16-bit lanes (<= 72 KB, so
+//         3 CTAs per SM overlap their zero / scan / write phases) and writes it once with 16 B
+//         stores: no global atomics, no pre-zeroing, HBM traffic = 5 B/event (re-read from L2 by
+//         the other slabs) + 4 B/bin.  Chunks of <= 65535 events make 16-bit overflow impossible.
 //      bin_hist_global_kernel ("reds"): event-parallel, 8 events per thread with 16 B loads,
 //         red.global.add.u32 into the (L2-resident when it fits) histogram after a memset.  Used for
 //         frames that do not fit in shared memory and for very long windows.
@@ -20,49 +22,77 @@
 
 namespace {
 
-constexpr int kSmemThreads = 1024;
-constexpr int kSmemMaxBytes = 200 * 1024;
+constexpr int kSmemThreads = 512;
+constexpr int kSlabMaxBytes = 72 * 1024;   // 3 CTAs/SM: phases of different CTAs overlap
 constexpr int kChunk = 65535;
 
-__global__ void bin_bounds_kernel(const int64_t* __restrict__ t, const int64_t* __restrict__ offsets,
-                                  int64_t B, int Tm, int64_t* __restrict__ bounds) {
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per (window, boundary): 32-ary search on the sorted timestamps (4 dependent loads for
+// 1e5 events instead of 17).  Also resets the work counter of the tile kernel.
+__global__ void __launch_bounds__(128)
+bin_bounds_kernel(const int64_t* __restrict__ t, const int64_t* __restrict__ offsets, int64_t B, int Tm,
+                  int64_t* __restrict__ bounds, unsigned int* __restrict__ work_counter) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gid == 0 && lane == 0) *work_counter = 0u;
   if (gid >= B * (Tm + 1)) return;
   const int64_t b = gid / (Tm + 1);
   const int k = (int)(gid - b * (Tm + 1));
   const int64_t s = offsets[b], e = offsets[b + 1];
   if (e <= s) {
-    bounds[gid] = s;
+    if (lane == 0) bounds[gid] = s;
     return;
   }
   const int64_t t0 = t[s];
   const int64_t tw = (t[e - 1] - t0) / Tm;  // sorted => non-negative => trunc == floor
   const int64_t key = t0 + (int64_t)k * tw;
-  int64_t lo = s, hi = e;  // first index with t[i] >= key
-  while (lo < hi) {
-    const int64_t mid = lo + ((hi - lo) >> 1);
-    if (t[mid] < key) lo = mid + 1;
-    else hi = mid;
+  int64_t lo = s, hi = e;  // answer (first index with t[i] >= key) is in [lo, hi]
+  while (hi - lo > 0) {
+    const int64_t len = hi - lo;
+    const int64_t step = (len + 31) / 32;  // probes at lo + (lane+1)*step - 1
+    const int64_t pi = lo + (int64_t)(lane + 1) * step - 1;
+    const bool less = pi < hi ? (t[pi] < key) : false;  // out-of-range probes count as ">= key"
+    const unsigned m = __ballot_sync(0xffffffffu, less);
+    const int nless = __popc(m);  // sorted => the lanes with t < key are a prefix
+    const int64_t nlo = lo + (int64_t)nless * step;
+    int64_t nhi = lo + (int64_t)(nless + 1) * step - 1;
+    if (nhi > hi) nhi = hi;
+    lo = nlo > hi ? hi : nlo;
+    hi = nhi;
   }
-  bounds[gid] = lo;
+  if (lane == 0) bounds[gid] = lo;
 }
 
 // ---- strategy "tiles" ---------------------------------------------------------------------
-__global__ void __launch_bounds__(kSmemThreads, 1)
+// work item = (window b, micro-bin k, polarity c, row slab): counted in shared memory as packed
+// 16-bit lanes, written once.  Items are handed out through an atomic counter.
+__global__ void __launch_bounds__(kSmemThreads)
 bin_hist_smem_kernel(const int16_t* __restrict__ x, const int16_t* __restrict__ y,
                      const uint8_t* __restrict__ p, const int64_t* __restrict__ bounds, int64_t n_items,
-                     int H, int W, int Tm, int32_t* __restrict__ hist) {
-  extern __shared__ __align__(16) uint32_t cnt[];  // ceil(H*W/2) words, two 16-bit counters per word
-  const int HW = H * W;
-  const int nwords = (HW + 1) >> 1;
-  const int nwords4 = (nwords + 3) & ~3;  // allocation is rounded up to 16 B
-  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int c = (int)(item & 1);
-    const int64_t bk = item >> 1;  // b*Tm + k
+                     int H, int W, int Tm, int n_slabs, int slab_rows, int32_t* __restrict__ hist,
+                     unsigned int* __restrict__ work_counter) {
+  extern __shared__ __align__(16) uint32_t cnt[];  // ceil(slab_rows*W/2) words, two 16-bit counters per word
+  __shared__ unsigned int sh_item;
+  const int64_t HW = (int64_t)H * W;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) sh_item = atomicAdd(work_counter, 1u);
+    __syncthreads();
+    const int64_t item = sh_item;
+    if (item >= n_items) break;
+    const int slab = (int)(item % n_slabs);
+    const int64_t bkc = item / n_slabs;  // (b*Tm + k)*2 + c
+    const int c = (int)(bkc & 1);
+    const int64_t bk = bkc >> 1;
     const int64_t b = bk / Tm;
     const int k = (int)(bk - b * Tm);
     const int64_t s = bounds[b * (Tm + 1) + k], e = bounds[b * (Tm + 1) + k + 1];
-    int32_t* __restrict__ out = hist + item * (int64_t)HW;
+    const int y_lo = slab * slab_rows;
+    const int rows = min(slab_rows, H - y_lo);
+    const int npix = rows * W;
+    const int nwords = (npix + 1) >> 1;
+    const int nwords4 = (nwords + 3) & ~3;
+    int32_t* __restrict__ out = hist + bkc * HW + (int64_t)y_lo * W;
+    const bool vec_ok = (npix & 3) == 0 && ((((int64_t)y_lo * W) & 3) == 0) && ((HW & 3) == 0);
     bool first = true;
     for (int64_t cs = s; first || cs < e; cs += kChunk) {
       for (int w = threadIdx.x * 4; w < nwords4; w += kSmemThreads * 4)
@@ -71,15 +101,16 @@ bin_hist_smem_kernel(const int16_t* __restrict__ x, const int16_t* __restrict__ 
       const int64_t ce = (e - cs > kChunk) ? cs + kChunk : e;
 #pragma unroll 4
       for (int64_t i = cs + threadIdx.x; i < ce; i += kSmemThreads) {
-        const int xi = x[i], yi = y[i];
+        const int yi = (int)y[i] - y_lo;
         const int ci = p[i] != 0;
-        if (ci == c && (unsigned)xi < (unsigned)W && (unsigned)yi < (unsigned)H) {
+        const int xi = x[i];
+        if (ci == c && (unsigned)xi < (unsigned)W && (unsigned)yi < (unsigned)rows) {
           const int pix = yi * W + xi;
           atomicAdd(cnt + (pix >> 1), 1u << ((pix & 1) << 4));
         }
       }
       __syncthreads();
-      if ((HW & 3) == 0) {
+      if (vec_ok) {
         // 2 words = 4 counters -> one 16 B store
         for (int w = threadIdx.x * 2; w < nwords; w += kSmemThreads * 2) {
           const uint2 v = *reinterpret_cast<const uint2*>(cnt + w);
@@ -92,13 +123,13 @@ bin_hist_smem_kernel(const int16_t* __restrict__ x, const int16_t* __restrict__ 
           st_stream_u4(dst, o);
         }
       } else {
-        for (int q = threadIdx.x; q < HW; q += kSmemThreads) {
+        for (int q = threadIdx.x; q < npix; q += kSmemThreads) {
           const uint32_t v = (cnt[q >> 1] >> ((q & 1) << 4)) & 0xffffu;
           out[q] = first ? (int32_t)v : out[q] + (int32_t)v;
         }
       }
-      __syncthreads();
       first = false;
+      if (cs + kChunk < e) __syncthreads();
     }
   }
 }
@@ -163,7 +194,8 @@ bin_hist_global_kernel(const int16_t* __restrict__ x, const int16_t* __restrict_
 
 extern "C" size_t eas_bin_events_ws_bytes(int64_t B, int Tm) {
   if (B <= 0 || Tm <= 0) return 0;
-  return eas_align_up((size_t)B * (size_t)(Tm + 1) * sizeof(int64_t), 256);
+  // bounds[B][Tm+1] int64 + one work counter
+  return eas_align_up((size_t)B * (size_t)(Tm + 1) * sizeof(int64_t), 256) + 256;
 }
 
 extern "C" int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64_t* t, const uint8_t* p,
@@ -182,27 +214,37 @@ extern "C" int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64
                   ((uintptr_t)hist % 16 == 0) && ((uintptr_t)ws % 8 == 0),
               EAS_E_ALIGN);
   int64_t* bounds = (int64_t*)ws;
+  unsigned int* counter =
+      (unsigned int*)((char*)ws + eas_align_up((size_t)B * (size_t)(Tm + 1) * sizeof(int64_t), 256));
   const int64_t HW = (int64_t)H * W;
   const int64_t nb = B * (Tm + 1);
-  bin_bounds_kernel<<<(unsigned)eas_ceil_div(nb, 128), 128, 0, stream>>>(t, offsets, B, Tm, bounds);
+  bin_bounds_kernel<<<(unsigned)eas_ceil_div(nb * 32, 128), 128, 0, stream>>>(t, offsets, B, Tm, bounds, counter);
   EAS_LAUNCH_CHECK();
 
-  const size_t smem = (size_t)(((HW + 1) / 2 + 3) / 4 * 4) * 4;
-  const int64_t n_items = B * Tm * 2;
+  // row slabs so that one slab of 16-bit counters fits the per-CTA shared memory budget
+  int n_slabs = (int)eas_ceil_div(HW * 2, kSlabMaxBytes);
+  if (n_slabs > H) n_slabs = H;
+  const int slab_rows = (int)eas_ceil_div(H, n_slabs);
+  n_slabs = (int)eas_ceil_div(H, slab_rows);
+  const size_t smem = (size_t)((((int64_t)slab_rows * W + 1) / 2 + 3) / 4 * 4) * 4;
+  const bool fits = smem <= (size_t)kSlabMaxBytes + 4096 && n_slabs <= 8;
+  const int64_t n_items = B * Tm * 2 * n_slabs;
   if (strategy == 0) {
-    const bool fits = smem <= (size_t)kSmemMaxBytes;
-    // one CTA per (window, micro-bin, polarity): only when that gives the machine enough CTAs and
-    // no single segment is long enough to serialise the launch.
-    const bool enough = n_items >= EAS_NUM_SMS / 2 && n_events / (B * Tm) <= (1 << 18);
+    // tiles: every event of a segment is scanned by 2*n_slabs CTAs (from L2); only worth it while
+    // the write-once output dominates, i.e. for short windows; long windows go event-parallel.
+    const bool enough = n_items >= EAS_NUM_SMS && n_events / (B * Tm) <= (1 << 17);
     strategy = (fits && enough) ? 2 : 1;
   }
   if (strategy == 2) {
-    EAS_REQUIRE(smem <= (size_t)kSmemMaxBytes, EAS_E_UNSUPPORTED);
+    EAS_REQUIRE(fits, EAS_E_UNSUPPORTED);
     cudaError_t e = cudaFuncSetAttribute(bin_hist_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return (int)e;
-    const unsigned grid = (unsigned)(n_items < 16 * EAS_NUM_SMS ? n_items : 16 * EAS_NUM_SMS);
-    bin_hist_smem_kernel<<<grid, kSmemThreads, smem, stream>>>(x, y, p, bounds, n_items, H, W, Tm, hist);
+    const int per_sm = (int)((220 * 1024) / (smem + 1024));
+    int64_t grid = (int64_t)EAS_NUM_SMS * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
+    if (grid > n_items) grid = n_items;
+    bin_hist_smem_kernel<<<(unsigned)grid, kSmemThreads, smem, stream>>>(x, y, p, bounds, n_items, H, W, Tm,
+                                                                        n_slabs, slab_rows, hist, counter);
     EAS_LAUNCH_CHECK();
   } else {
     cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)B * Tm * 2 * HW * sizeof(int32_t), stream);

@@ -3,19 +3,22 @@
 //
 // One launch per sampler step t (the launch boundary is the grid-wide dependency the recurrent
 // gate_conv(spike_{t-1}) needs: its two stacked KxK convolutions see a (4R+1)^2 neighbourhood of
-// the previous step's spikes).  Inside a launch one CTA owns a TH x TW pixel tile of one window and
-// fuses everything the reference does in ~35 ATen launches and 3 host syncs:
-//   load  : micro-bin counts (fp32 or the int32 histogram straight from eas_bin_events) and the
-//           previous spikes (u8), tile + 2R*depth halo, zero padded, into shared memory
+// the previous step's spikes).  A launch is a persistent grid (2 CTAs per SM) walking TH x TW pixel
+// tiles; per tile a CTA fuses everything the reference does in ~35 ATen launches and 3 host syncs:
+//   load  : micro-bin counts (fp32, or the int32 histogram straight from eas_bin_events) and the
+//           previous spikes, tile + R*depth halo, zero padded, by cp.async (zfill) into shared
+//           memory -- issued one tile ahead, so the copy overlaps the previous tile's conv 2
 //   conv 1: input_conv[0] (2->4) and gate_conv[0] (2->4) + ReLU on tile + R halo -> shared memory
 //   conv 2: input_conv[2] + gate_conv[2] as ONE 8->4 convolution (the reference adds the two
 //           stacks' outputs, embedding.py:175-176), 4 x 8 register tile per thread
 //   update: sigmoid gate, membrane update, strict threshold, reset, running no-reset sum,
 //           spike-triggered read-out into agg[seg], seg/t_last bookkeeping; on the last step the
-//           residual write (RPD: write_zero) and the optional ReLU.
-// Per-pixel state (vm, acc: f32; seg, t_last: u8; spikes: u8, double buffered) lives in the
-// caller's workspace between launches: 12 B per state element.  The kernel is FP32-pipe bound
-// (2400 FLOP per pixel-step for depth 2, k 5) not HBM bound; see DESIGN.md.
+//           residual write (RPD: write_zero) and the optional ReLU.  The per-pixel state tile is
+//           also fetched by cp.async while the convolutions run.
+// Per-pixel state between launches (caller's workspace): vm, acc, spikes x2 (f32), seg|t_last (u16)
+// = 18 B per state element.  The kernel is FP32-pipe bound (2400 FLOP per pixel-step for depth 2,
+// k 5), not HBM bound; see DESIGN.md.
+#include <type_traits>
 #include "common.cuh"
 
 namespace {
@@ -23,22 +26,40 @@ namespace {
 constexpr int ru4(int a) { return (a + 3) / 4 * 4; }
 
 struct StepArgs {
-  const void* events;   // [B][Tm][2][H][W]
-  const uint8_t* s_prev;  // [B][2][H][W]
-  uint8_t* s_next;
+  const void* events;     // [B][Tm][2][H][W]
+  const float* s_prev;    // [B][2][H][W]
+  float* s_next;
   float* vm;
   float* acc;
-  uint8_t* seg;
-  uint8_t* tl;          // t_last + 1
-  float* out;           // [Ts][B][2][H][W]
-  float* v_seq;         // [Tm][B][2][H][W] or null
+  uint16_t* meta;         // seg | (t_last + 1) << 8
+  float* out;             // [Ts][B][2][H][W]
+  float* v_seq;           // [Tm][B][2][H][W] or null
   float* gate_seq;
   eas_sampler_weights w;
   int B, H, W, Tm, Ts;
-  int t;                // sampler step (0 = newest micro-bin)
+  int t;                  // sampler step (0 = newest micro-bin)
   int readout, hard_reset, write_zero, use_abs;
   float vreset, thresh;
 };
+
+__device__ __forceinline__ void cp_async_16(void* smem, const void* g, bool pred) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(g), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem, const void* g, bool pred) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = pred ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(g), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem, const void* g, bool pred) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = pred ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(g), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // acc[co][px] += sum_{ci,ky,kx} src[ci][ky][px+kx] * w[ci][ky][kx][co]
 template <int CI, int CO, int K, int PX>
@@ -73,6 +94,7 @@ __device__ __forceinline__ void conv_acc(const float* __restrict__ src, int ch_s
 template <int K, int DEPTH, int TH, int TW>
 struct Geo {
   static constexpr int R = K / 2;
+  static constexpr int HALO = R * DEPTH;
   static constexpr int PX = 8;
   static constexpr int NT = TH * TW / PX;
   // second-layer input (h1 for depth 2, the raw tile for depth 1)
@@ -83,43 +105,49 @@ struct Geo {
   static constexpr int IR = HR + 2 * R;
   static constexpr int IC = HC + 2 * R;
   static constexpr int IS = ru4(IC) + 4;
+  // the tile that is filled from global memory
+  static constexpr int LR = DEPTH == 2 ? IR : HR;
+  static constexpr int LC = DEPTH == 2 ? IC : HC;
+  static constexpr int LS = DEPTH == 2 ? IS : HS;
   static constexpr int W1 = 2 * K * K * 4;   // one first-layer stack [2][K][K][4]
   static constexpr int W2 = (DEPTH == 2 ? 8 : 4) * K * K * 4;
   static constexpr int SM_H = (DEPTH == 2 ? 8 : 4) * HR * HS + 16;
   static constexpr int SM_I = DEPTH == 2 ? 4 * IR * IS + 16 : 0;
   static constexpr int SM_W = W2 + (DEPTH == 2 ? 2 * W1 : 0) + 16;
-  static constexpr size_t SMEM = sizeof(float) * (size_t)(SM_H + SM_I + SM_W);
+  static constexpr int SM_ST = 2 * TH * TW;  // per f32 state array
+  // floats: conv buffers + weights + vm + acc + meta (u16 -> half the floats)
+  static constexpr size_t SMEM = sizeof(float) * (size_t)(SM_H + SM_I + SM_W + 2 * SM_ST + SM_ST / 2);
 };
 
-template <typename IN_T>
-__device__ __forceinline__ float ld_in(const IN_T* p) { return (float)__ldg(p); }
-
-template <int K, int DEPTH, int TH, int TW, typename IN_T>
-__global__ void __launch_bounds__(TH* TW / 8)
+template <int K, int DEPTH, int TH, int TW, typename IN_T, bool VEC>
+__global__ void __launch_bounds__(TH* TW / 8, 2)
 sampler_step_kernel(const StepArgs a) {
   using G = Geo<K, DEPTH, TH, TW>;
   constexpr int R = G::R;
+  constexpr int PX = G::PX;
+  constexpr bool kInt = !std::is_same<IN_T, float>::value;
   extern __shared__ __align__(16) float smem[];
   float* sh_h = smem;                 // layer-2 input
   float* sh_i = sh_h + G::SM_H;       // layer-1 input (depth 2)
   float* sh_w2 = sh_i + G::SM_I;      // [CI2][K][K][4]
   float* sh_w1 = sh_w2 + G::W2;       // [2 stacks][2][K][K][4]
+  float* sh_vm = sh_w2 + G::SM_W;     // [2][TH][TW]
+  float* sh_acc = sh_vm + G::SM_ST;
+  uint16_t* sh_meta = reinterpret_cast<uint16_t*>(sh_acc + G::SM_ST);
+  float* sh_l = DEPTH == 2 ? sh_i : sh_h;  // the tile filled from global memory
   __shared__ float sh_b[16];          // [0..3] layer-2 bias sum, [4..7] in b0, [8..11] gate b0
 
   const int tid = threadIdx.x;
   const int tiles_x = (a.W + TW - 1) / TW;
   const int tiles_y = (a.H + TH - 1) / TH;
-  int bid = blockIdx.x;
-  const int tx = bid % tiles_x;
-  bid /= tiles_x;
-  const int ty = bid % tiles_y;
-  const int b = bid / tiles_y;
-  const int x0 = tx * TW, y0 = ty * TH;
+  const int ntiles = tiles_x * tiles_y * a.B;
   const int64_t HW = (int64_t)a.H * a.W;
+  const int64_t BHW2 = (int64_t)a.B * 2 * HW;
   const bool first = a.t == 0, last = a.t == a.Tm - 1;
   const int tm = a.Tm - 1 - a.t;  // newest micro-bin first (embedding.py:155-156)
+  const IN_T* ev_base = reinterpret_cast<const IN_T*>(a.events);
 
-  // ---- weights -> shared, re-laid out as [ci][ky][kx][co] -------------------------------------
+  // ---- weights -> shared (once per CTA), re-laid out as [ci][ky][kx][co] ----------------------
   if (DEPTH == 2) {
     for (int i = tid; i < 2 * G::W1; i += G::NT) {
       const int stack = i / G::W1;
@@ -164,175 +192,305 @@ sampler_step_kernel(const StepArgs a) {
     if (tid < 4) sh_b[tid] = a.w.in_b0[tid] + a.w.gate_b0[tid];
   }
 
-  // ---- input tile (events + previous spikes) -> shared, zero padded ---------------------------
-  {
-    constexpr int ROWS = DEPTH == 2 ? G::IR : G::HR;
-    constexpr int COLS = DEPTH == 2 ? G::IC : G::HC;
-    constexpr int STR = DEPTH == 2 ? G::IS : G::HS;
-    constexpr int HALO = R * DEPTH;
-    float* dst = DEPTH == 2 ? sh_i : sh_h;
-    const IN_T* ev = reinterpret_cast<const IN_T*>(a.events) + ((int64_t)b * a.Tm + tm) * 2 * HW;
-    const uint8_t* sp = a.s_prev + (int64_t)b * 2 * HW;
-    for (int i = tid; i < 4 * ROWS * COLS; i += G::NT) {
-      const int c = i / (ROWS * COLS);
-      const int rem = i - c * (ROWS * COLS);
-      const int r = rem / COLS, cc = rem - r * COLS;
-      const int gy = y0 - HALO + r, gx = x0 - HALO + cc;
-      float v = 0.0f;
-      if ((unsigned)gy < (unsigned)a.H && (unsigned)gx < (unsigned)a.W) {
-        const int64_t off = (int64_t)gy * a.W + gx;
-        if (c < 2) v = ld_in<IN_T>(ev + c * HW + off);
-        else if (!first) v = (float)sp[(c - 2) * HW + off];
+  // ---- tile loaders ---------------------------------------------------------------------------
+  // events (raw 4-byte words) and previous spikes, tile + halo, zero filled outside the image
+  auto issue_in = [&](int tile) {
+    const int tx = tile % tiles_x;
+    const int ty = (tile / tiles_x) % tiles_y;
+    const int b = tile / (tiles_x * tiles_y);
+    const int gx0 = tx * TW - G::HALO, gy0 = ty * TH - G::HALO;
+    const IN_T* ev = ev_base + ((int64_t)b * a.Tm + tm) * 2 * HW;
+    const float* sp = a.s_prev + (int64_t)b * 2 * HW;
+    const int nch = first ? 2 : 4;  // step 0: previous spikes are all zero, nothing to load
+    constexpr bool kGran4 = VEC && (G::HALO % 4 == 0) && (G::LC % 4 == 0);
+    if (kGran4) {
+      constexpr int GPR = G::LC / 4;
+      for (int i = tid; i < nch * G::LR * GPR; i += G::NT) {
+        const int c = i / (G::LR * GPR);
+        const int rem = i - c * (G::LR * GPR);
+        const int r = rem / GPR, g4 = (rem - r * GPR) * 4;
+        const int gy = gy0 + r, gx = gx0 + g4;
+        const bool ok = (unsigned)gy < (unsigned)a.H && (unsigned)gx < (unsigned)a.W;
+        const int64_t off = ok ? (int64_t)gy * a.W + gx : 0;
+        const void* src = c < 2 ? (const void*)(ev + c * HW + off) : (const void*)(sp + (c - 2) * HW + off);
+        cp_async_16(sh_l + (c * G::LR + r) * G::LS + g4, src, ok);
       }
-      dst[(c * ROWS + r) * STR + cc] = v;
+    } else {
+      for (int i = tid; i < nch * G::LR * G::LC; i += G::NT) {
+        const int c = i / (G::LR * G::LC);
+        const int rem = i - c * (G::LR * G::LC);
+        const int r = rem / G::LC, cc = rem - r * G::LC;
+        const int gy = gy0 + r, gx = gx0 + cc;
+        const bool ok = (unsigned)gy < (unsigned)a.H && (unsigned)gx < (unsigned)a.W;
+        const int64_t off = ok ? (int64_t)gy * a.W + gx : 0;
+        const void* src = c < 2 ? (const void*)(ev + c * HW + off) : (const void*)(sp + (c - 2) * HW + off);
+        cp_async_4(sh_l + (c * G::LR + r) * G::LS + cc, src, ok);
+      }
     }
-  }
-  __syncthreads();
+  };
+  // vm, acc (f32) and seg|t_last (u16) of the tile
+  auto issue_state = [&](int tile) {
+    const int tx = tile % tiles_x;
+    const int ty = (tile / tiles_x) % tiles_y;
+    const int b = tile / (tiles_x * tiles_y);
+    if (VEC) {
+      constexpr int GPR = TW / 4;
+      for (int i = tid; i < 2 * TH * GPR; i += G::NT) {
+        const int c = i / (TH * GPR);
+        const int rem = i - c * (TH * GPR);
+        const int r = rem / GPR, g4 = (rem - r * GPR) * 4;
+        const int gy = ty * TH + r, gx = tx * TW + g4;
+        const bool ok = gy < a.H && gx < a.W;
+        const int64_t e = ok ? ((int64_t)b * 2 + c) * HW + (int64_t)gy * a.W + gx : 0;
+        const int so = (c * TH + r) * TW + g4;
+        cp_async_16(sh_vm + so, a.vm + e, ok);
+        cp_async_16(sh_acc + so, a.acc + e, ok);
+        cp_async_8(sh_meta + so, a.meta + e, ok);
+      }
+    } else {
+      for (int i = tid; i < 2 * TH * TW; i += G::NT) {
+        const int c = i / (TH * TW);
+        const int rem = i - c * (TH * TW);
+        const int r = rem / TW, cc = rem - r * TW;
+        const int gy = ty * TH + r, gx = tx * TW + cc;
+        const bool ok = gy < a.H && gx < a.W;
+        const int64_t e = ok ? ((int64_t)b * 2 + c) * HW + (int64_t)gy * a.W + gx : 0;
+        sh_vm[i] = ok ? a.vm[e] : 0.0f;
+        sh_acc[i] = ok ? a.acc[e] : 0.0f;
+        sh_meta[i] = ok ? a.meta[e] : (uint16_t)0;
+      }
+    }
+  };
 
-  // ---- layer 1 (depth 2): 2->4 per stack, bias, ReLU, zero outside the image ------------------
-  if (DEPTH == 2) {
-    constexpr int PX1 = 4;
-    constexpr int NSTRIP = G::HR * (G::HC / PX1);
-    for (int idx = tid; idx < NSTRIP; idx += G::NT) {
-      const int r = idx / (G::HC / PX1);
-      const int c0 = (idx - r * (G::HC / PX1)) * PX1;
-      const int gy = y0 - R + r;
-      const bool row_in = (unsigned)gy < (unsigned)a.H;
-#pragma unroll
-      for (int stack = 0; stack < 2; ++stack) {
-        float acc[4][PX1];
-#pragma unroll
-        for (int co = 0; co < 4; ++co)
-#pragma unroll
-          for (int px = 0; px < PX1; ++px) acc[co][px] = 0.0f;
-        if (row_in && !(stack == 1 && first))
-          conv_acc<2, 4, K, PX1>(sh_i + (stack * 2 * G::IR + r) * G::IS + c0, G::IR * G::IS, G::IS,
-                                 sh_w1 + stack * G::W1, acc);
-#pragma unroll
-        for (int co = 0; co < 4; ++co) {
-          const float bias = sh_b[4 + stack * 4 + co];
-          float4 o;
-          float* op = reinterpret_cast<float*>(&o);
-#pragma unroll
-          for (int px = 0; px < PX1; ++px) {
-            const int gx = x0 - R + c0 + px;
-            const bool in_img = row_in && (unsigned)gx < (unsigned)a.W;
-            op[px] = in_img ? fmaxf(acc[co][px] + bias, 0.0f) : 0.0f;
-          }
-          *reinterpret_cast<float4*>(sh_h + ((stack * 4 + co) * G::HR + r) * G::HS + c0) = o;
-        }
-      }
-    }
+  int tile = blockIdx.x;
+  if (tile < ntiles) issue_in(tile);
+  cp_async_commit();
+
+  for (; tile < ntiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x;
+    const int ty = (tile / tiles_x) % tiles_y;
+    const int b = tile / (tiles_x * tiles_y);
+    const int x0 = tx * TW, y0 = ty * TH;
+    if (!first) issue_state(tile);
+    cp_async_commit();
+    cp_async_wait<1>();  // this tile's input has landed (the state group may still be in flight)
     __syncthreads();
-  }
 
-  // ---- layer 2: (8|4) -> 4, one 4 x 8 register tile per thread --------------------------------
-  constexpr int PX = G::PX;
-  const int r = tid / (TW / PX);
-  const int c0 = (tid - r * (TW / PX)) * PX;
-  float acc2[4][PX];
-#pragma unroll
-  for (int co = 0; co < 4; ++co)
-#pragma unroll
-    for (int px = 0; px < PX; ++px) acc2[co][px] = 0.0f;
-  conv_acc<(DEPTH == 2 ? 8 : 4), 4, K, PX>(sh_h + r * G::HS + c0, G::HR * G::HS, G::HS, sh_w2, acc2);
-
-  // ---- membrane update + spike-triggered aggregation (embedding.py:132-139, 177-217) ----------
-  const int gy = y0 + r;
-  if (gy >= a.H) return;
-  const int64_t BHW2 = (int64_t)a.B * 2 * HW;
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    const float bg = sh_b[c], bc = sh_b[2 + c];
-    const int64_t base = ((int64_t)b * 2 + c) * HW + (int64_t)gy * a.W + x0 + c0;
-#pragma unroll
-    for (int px = 0; px < PX; ++px) {
-      if (x0 + c0 + px >= a.W) break;
-      const int64_t e = base + px;
-      const float gate = eas_sigmoid(acc2[c][px] + bg);
-      const float cur = acc2[2 + c][px] + bc;
-      float vm = first ? 0.0f : a.vm[e];
-      float ac = first ? 0.0f : a.acc[e];
-      int seg = first ? 0 : (int)a.seg[e];
-      int tl = first ? -1 : (int)a.tl[e] - 1;
-      const float v = __fadd_rn(__fmul_rn(gate, vm), cur);
-      const bool s = __fsub_rn(v, a.thresh) > 0.0f;
-      if (a.hard_reset) vm = s ? a.vreset : v;
-      else vm = s ? __fsub_rn(v, a.thresh) : v;
-      ac = __fadd_rn(ac, v);
-      if (a.v_seq) {
-        const int64_t se = (int64_t)a.t * BHW2 + e;
-        a.v_seq[se] = v;
-        a.gate_seq[se] = gate;
-      }
-      const bool valid = s && seg < a.Ts;
-      float val = 0.0f;
-      if (valid) {
-        if (a.readout == EAS_READOUT_SUM) val = ac;
-        else if (a.readout == EAS_READOUT_LAST) val = vm;
-        else val = ac / (float)(a.t - tl);
-      }
-      float* outp = a.out + e;  // plane k at outp + k*BHW2
-      if (first) {
-        for (int k = 0; k < a.Ts; ++k) outp[k * BHW2] = (valid && k == 0) ? val : 0.0f;
-      } else if (valid) {
-        outp[seg * BHW2] += val;
-      }
-      if (valid) {
-        ++seg;
-        tl = a.t;
-      }
-      if (s) ac = 0.0f;
-      if (last) {
-        if (!s && seg < a.Ts && !a.write_zero) {
-          float tv;
-          if (a.readout == EAS_READOUT_SUM) tv = ac;
-          else if (a.readout == EAS_READOUT_LAST) tv = vm;
-          else tv = ac / (float)(a.Tm - 1 - tl);
-          outp[seg * BHW2] += tv;
+    if (kInt || first) {
+      // int32 counts -> fp32 in place; on step 0 also clear the spike channels
+      for (int i = tid; i < 4 * G::LR * G::LC; i += G::NT) {
+        const int c = i / (G::LR * G::LC);
+        const int rem = i - c * (G::LR * G::LC);
+        const int r = rem / G::LC, cc = rem - r * G::LC;
+        float* q = sh_l + (c * G::LR + r) * G::LS + cc;
+        if (c < 2) {
+          if (kInt) *q = (float)__float_as_int(*q);
+        } else if (first) {
+          *q = 0.0f;
         }
-        if (a.use_abs)
-          for (int k = 0; k < a.Ts; ++k) outp[k * BHW2] = fmaxf(outp[k * BHW2], 0.0f);
-      } else {
-        a.vm[e] = vm;
-        a.acc[e] = ac;
-        a.seg[e] = (uint8_t)seg;
-        a.tl[e] = (uint8_t)(tl + 1);
-        a.s_next[e] = s ? 1 : 0;
+      }
+      __syncthreads();
+    }
+
+    // ---- layer 1 (depth 2): 2->4 per stack, bias, ReLU, zero outside the image ----------------
+    if (DEPTH == 2) {
+      constexpr int PX1 = 4;
+      constexpr int NSTRIP = G::HR * (G::HC / PX1);
+      for (int idx = tid; idx < NSTRIP; idx += G::NT) {
+        const int r = idx / (G::HC / PX1);
+        const int c0 = (idx - r * (G::HC / PX1)) * PX1;
+        const int gy = y0 - R + r;
+        const bool row_in = (unsigned)gy < (unsigned)a.H;
+#pragma unroll
+        for (int stack = 0; stack < 2; ++stack) {
+          float acc[4][PX1];
+#pragma unroll
+          for (int co = 0; co < 4; ++co)
+#pragma unroll
+            for (int px = 0; px < PX1; ++px) acc[co][px] = 0.0f;
+          if (row_in && !(stack == 1 && first))
+            conv_acc<2, 4, K, PX1>(sh_i + (stack * 2 * G::IR + r) * G::IS + c0, G::IR * G::IS, G::IS,
+                                   sh_w1 + stack * G::W1, acc);
+#pragma unroll
+          for (int co = 0; co < 4; ++co) {
+            const float bias = sh_b[4 + stack * 4 + co];
+            float4 o;
+            float* op = reinterpret_cast<float*>(&o);
+#pragma unroll
+            for (int px = 0; px < PX1; ++px) {
+              const int gx = x0 - R + c0 + px;
+              const bool in_img = row_in && (unsigned)gx < (unsigned)a.W;
+              op[px] = in_img ? fmaxf(acc[co][px] + bias, 0.0f) : 0.0f;
+            }
+            *reinterpret_cast<float4*>(sh_h + ((stack * 4 + co) * G::HR + r) * G::HS + c0) = o;
+          }
+        }
+      }
+      __syncthreads();
+      // the layer-1 input buffer is free: fetch the next tile while layer 2 runs
+      if (tile + (int)gridDim.x < ntiles) issue_in(tile + gridDim.x);
+      cp_async_commit();
+    }
+
+    // ---- layer 2: (8|4) -> 4, one 4 x 8 register tile per thread ------------------------------
+    const int r = tid / (TW / PX);
+    const int c0 = (tid - r * (TW / PX)) * PX;
+    float acc2[4][PX];
+#pragma unroll
+    for (int co = 0; co < 4; ++co)
+#pragma unroll
+      for (int px = 0; px < PX; ++px) acc2[co][px] = 0.0f;
+    conv_acc<(DEPTH == 2 ? 8 : 4), 4, K, PX>(sh_h + r * G::HS + c0, G::HR * G::HS, G::HS, sh_w2, acc2);
+
+    if (DEPTH == 1) {
+      __syncthreads();  // everyone is done reading the raw tile
+      if (tile + (int)gridDim.x < ntiles) issue_in(tile + gridDim.x);
+      cp_async_commit();
+    }
+    cp_async_wait<1>();  // this tile's state has landed (the next tile's input may be in flight)
+    __syncthreads();
+
+    // ---- membrane update + spike-triggered aggregation (embedding.py:132-139, 177-217) --------
+    const int gy = y0 + r;
+    const int nv = min(PX, a.W - (x0 + c0));  // valid pixels of this strip (<= 0: none)
+    if (gy < a.H && nv > 0) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float bg = sh_b[c], bc = sh_b[2 + c];
+        const int64_t base = ((int64_t)b * 2 + c) * HW + (int64_t)gy * a.W + x0 + c0;
+        const int so = (c * TH + r) * TW + c0;
+        __align__(16) float vm8[PX], ac8[PX], v8[PX], g8[PX], s8[PX];
+        __align__(16) uint16_t m8[PX];
+        if (first) {
+#pragma unroll
+          for (int px = 0; px < PX; ++px) vm8[px] = 0.0f, ac8[px] = 0.0f, m8[px] = 0;
+        } else {
+          *reinterpret_cast<float4*>(vm8) = *reinterpret_cast<const float4*>(sh_vm + so);
+          *reinterpret_cast<float4*>(vm8 + 4) = *reinterpret_cast<const float4*>(sh_vm + so + 4);
+          *reinterpret_cast<float4*>(ac8) = *reinterpret_cast<const float4*>(sh_acc + so);
+          *reinterpret_cast<float4*>(ac8 + 4) = *reinterpret_cast<const float4*>(sh_acc + so + 4);
+          *reinterpret_cast<uint4*>(m8) = *reinterpret_cast<const uint4*>(sh_meta + so);
+        }
+        float* outp = a.out + base;  // plane k at outp + k*BHW2
+#pragma unroll
+        for (int px = 0; px < PX; ++px) {
+          const float gate = eas_sigmoid(acc2[c][px] + bg);
+          const float cur = acc2[2 + c][px] + bc;
+          int seg = m8[px] & 0xff;
+          int tl = (int)(m8[px] >> 8) - 1;
+          float vm = vm8[px], ac = ac8[px];
+          const float v = __fadd_rn(__fmul_rn(gate, vm), cur);
+          const bool s = __fsub_rn(v, a.thresh) > 0.0f;
+          if (a.hard_reset) vm = s ? a.vreset : v;
+          else vm = s ? __fsub_rn(v, a.thresh) : v;
+          ac = __fadd_rn(ac, v);
+          const bool valid = s && seg < a.Ts;
+          float val = 0.0f;
+          if (valid) {
+            if (a.readout == EAS_READOUT_SUM) val = ac;
+            else if (a.readout == EAS_READOUT_LAST) val = vm;
+            else val = ac / (float)(a.t - tl);
+          }
+          if (px < nv) {
+            if (first) {
+              for (int k = 0; k < a.Ts; ++k) outp[k * BHW2 + px] = (valid && k == 0) ? val : 0.0f;
+            } else if (valid) {
+              outp[seg * BHW2 + px] += val;
+            }
+          }
+          if (valid) {
+            ++seg;
+            tl = a.t;
+          }
+          if (s) ac = 0.0f;
+          if (last && px < nv) {
+            if (!s && seg < a.Ts && !a.write_zero) {
+              float tv;
+              if (a.readout == EAS_READOUT_SUM) tv = ac;
+              else if (a.readout == EAS_READOUT_LAST) tv = vm;
+              else tv = ac / (float)(a.Tm - 1 - tl);
+              outp[seg * BHW2 + px] += tv;
+            }
+            if (a.use_abs)
+              for (int k = 0; k < a.Ts; ++k) outp[k * BHW2 + px] = fmaxf(outp[k * BHW2 + px], 0.0f);
+          }
+          vm8[px] = vm, ac8[px] = ac, v8[px] = v, g8[px] = gate, s8[px] = s ? 1.0f : 0.0f;
+          m8[px] = (uint16_t)(seg | ((tl + 1) << 8));
+        }
+        // ---- state / training stores ----
+        if (VEC) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (nv >= 4 * (h + 1)) {
+              if (!last) {
+                *reinterpret_cast<float4*>(a.vm + base + 4 * h) = *reinterpret_cast<const float4*>(vm8 + 4 * h);
+                *reinterpret_cast<float4*>(a.acc + base + 4 * h) = *reinterpret_cast<const float4*>(ac8 + 4 * h);
+                *reinterpret_cast<uint2*>(a.meta + base + 4 * h) = *reinterpret_cast<const uint2*>(m8 + 4 * h);
+                *reinterpret_cast<float4*>(a.s_next + base + 4 * h) = *reinterpret_cast<const float4*>(s8 + 4 * h);
+              }
+              if (a.v_seq) {
+                const int64_t se = (int64_t)a.t * BHW2 + base + 4 * h;
+                *reinterpret_cast<float4*>(a.v_seq + se) = *reinterpret_cast<const float4*>(v8 + 4 * h);
+                *reinterpret_cast<float4*>(a.gate_seq + se) = *reinterpret_cast<const float4*>(g8 + 4 * h);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int px = 0; px < PX; ++px) {
+            if (px < nv) {
+              if (!last) {
+                a.vm[base + px] = vm8[px];
+                a.acc[base + px] = ac8[px];
+                a.meta[base + px] = m8[px];
+                a.s_next[base + px] = s8[px];
+              }
+              if (a.v_seq) {
+                const int64_t se = (int64_t)a.t * BHW2 + base + px;
+                a.v_seq[se] = v8[px];
+                a.gate_seq[se] = g8[px];
+              }
+            }
+          }
+        }
       }
     }
+    __syncthreads();  // state tile and layer-2 input are free for the next tile
   }
+  cp_async_wait<0>();
 }
 
-template <int K, int DEPTH, typename IN_T>
-int launch_steps(const eas_sampler_cfg* cfg, StepArgs a, uint8_t* s0, uint8_t* s1, cudaStream_t st) {
+template <int K, int DEPTH, typename IN_T, bool VEC>
+int launch_steps(const eas_sampler_cfg* cfg, StepArgs a, float* s0, float* s1, cudaStream_t st) {
   constexpr int TH = 16, TW = 64;
   using G = Geo<K, DEPTH, TH, TW>;
-  auto kern = sampler_step_kernel<K, DEPTH, TH, TW, IN_T>;
+  auto kern = sampler_step_kernel<K, DEPTH, TH, TW, IN_T, VEC>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
   if (e != cudaSuccess) return (int)e;
   const int64_t tiles = (int64_t)((cfg->W + TW - 1) / TW) * ((cfg->H + TH - 1) / TH) * cfg->B;
   EAS_REQUIRE(tiles < (1ll << 31), EAS_E_SHAPE);
+  const int per_sm = G::SMEM + 1024 <= 113 * 1024 ? 2 : 1;
+  const int64_t grid = tiles < (int64_t)EAS_NUM_SMS * per_sm ? tiles : (int64_t)EAS_NUM_SMS * per_sm;
   for (int t = 0; t < cfg->Tm; ++t) {
     a.t = t;
     a.s_prev = (t & 1) ? s0 : s1;  // step t reads what step t-1 wrote
     a.s_next = (t & 1) ? s1 : s0;
-    kern<<<(unsigned)tiles, G::NT, G::SMEM, st>>>(a);
+    kern<<<(unsigned)grid, G::NT, G::SMEM, st>>>(a);
     EAS_LAUNCH_CHECK();
   }
   return EAS_OK;
 }
 
-template <typename IN_T>
-int dispatch(const eas_sampler_cfg* c, const StepArgs& a, uint8_t* s0, uint8_t* s1, cudaStream_t st) {
+template <typename IN_T, bool VEC>
+int dispatch(const eas_sampler_cfg* c, const StepArgs& a, float* s0, float* s1, cudaStream_t st) {
   if (c->depth == 2) {
-    if (c->ksize == 3) return launch_steps<3, 2, IN_T>(c, a, s0, s1, st);
-    if (c->ksize == 5) return launch_steps<5, 2, IN_T>(c, a, s0, s1, st);
-    if (c->ksize == 7) return launch_steps<7, 2, IN_T>(c, a, s0, s1, st);
+    if (c->ksize == 3) return launch_steps<3, 2, IN_T, VEC>(c, a, s0, s1, st);
+    if (c->ksize == 5) return launch_steps<5, 2, IN_T, VEC>(c, a, s0, s1, st);
+    if (c->ksize == 7) return launch_steps<7, 2, IN_T, VEC>(c, a, s0, s1, st);
   } else {
-    if (c->ksize == 3) return launch_steps<3, 1, IN_T>(c, a, s0, s1, st);
-    if (c->ksize == 5) return launch_steps<5, 1, IN_T>(c, a, s0, s1, st);
-    if (c->ksize == 7) return launch_steps<7, 1, IN_T>(c, a, s0, s1, st);
+    if (c->ksize == 3) return launch_steps<3, 1, IN_T, VEC>(c, a, s0, s1, st);
+    if (c->ksize == 5) return launch_steps<5, 1, IN_T, VEC>(c, a, s0, s1, st);
+    if (c->ksize == 7) return launch_steps<7, 1, IN_T, VEC>(c, a, s0, s1, st);
   }
   return EAS_E_UNSUPPORTED;
 }
@@ -353,8 +511,8 @@ int check(const eas_sampler_cfg* c) {
 extern "C" size_t eas_sampler_fwd_ws_bytes(const eas_sampler_cfg* c) {
   if (check(c) != EAS_OK) return 0;
   const size_t n = (size_t)c->B * 2 * c->H * c->W;
-  // vm, acc (f32) + seg, tl, s0, s1 (u8), each segment 256 B aligned
-  return 2 * eas_align_up(n * 4, 256) + 4 * eas_align_up(n, 256) + 256;
+  // vm, acc, s0, s1 (f32) + meta (u16), each segment 256 B aligned
+  return 4 * eas_align_up(n * 4, 256) + eas_align_up(n * 2, 256) + 256;
 }
 
 extern "C" int eas_sampler_fwd(const eas_sampler_cfg* c, const void* events, const eas_sampler_weights* w,
@@ -368,7 +526,7 @@ extern "C" int eas_sampler_fwd(const eas_sampler_cfg* c, const void* events, con
   if (c->depth == 2) EAS_REQUIRE(w->in_w1 && w->in_b1 && w->gate_w1 && w->gate_b1, EAS_E_NULL);
   EAS_REQUIRE((v_seq == nullptr) == (gate_seq == nullptr), EAS_E_NULL);
   EAS_REQUIRE(ws_bytes >= eas_sampler_fwd_ws_bytes(c), EAS_E_WORKSPACE);
-  EAS_REQUIRE((uintptr_t)ws % 16 == 0, EAS_E_ALIGN);
+  EAS_REQUIRE((uintptr_t)ws % 16 == 0 && (uintptr_t)events % 4 == 0, EAS_E_ALIGN);
   const size_t n = (size_t)c->B * 2 * c->H * c->W;
   char* p = (char*)ws;
   StepArgs a{};
@@ -377,13 +535,11 @@ extern "C" int eas_sampler_fwd(const eas_sampler_cfg* c, const void* events, con
   p += eas_align_up(n * 4, 256);
   a.acc = (float*)p;
   p += eas_align_up(n * 4, 256);
-  a.seg = (uint8_t*)p;
-  p += eas_align_up(n, 256);
-  a.tl = (uint8_t*)p;
-  p += eas_align_up(n, 256);
-  uint8_t* s0 = (uint8_t*)p;
-  p += eas_align_up(n, 256);
-  uint8_t* s1 = (uint8_t*)p;
+  float* s0 = (float*)p;
+  p += eas_align_up(n * 4, 256);
+  float* s1 = (float*)p;
+  p += eas_align_up(n * 4, 256);
+  a.meta = (uint16_t*)p;
   a.out = out;
   a.v_seq = v_seq;
   a.gate_seq = gate_seq;
@@ -392,6 +548,10 @@ extern "C" int eas_sampler_fwd(const eas_sampler_cfg* c, const void* events, con
   a.readout = c->readout, a.hard_reset = c->hard_reset, a.write_zero = c->write_zero, a.use_abs = c->use_abs;
   a.vreset = c->vreset, a.thresh = c->thresh;
   cudaStream_t st = (cudaStream_t)stream;
-  if (c->in_dtype == EAS_F32) return dispatch<float>(c, a, s0, s1, st);
-  return dispatch<int32_t>(c, a, s0, s1, st);
+  // 16-byte vector path: rows must keep 16 B alignment (W % 4 == 0) and so must every base pointer
+  const bool vec = (c->W % 4 == 0) && ((uintptr_t)events % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+                   (!v_seq || ((uintptr_t)v_seq % 16 == 0 && (uintptr_t)gate_seq % 16 == 0));
+  if (c->in_dtype == EAS_F32)
+    return vec ? dispatch<float, true>(c, a, s0, s1, st) : dispatch<float, false>(c, a, s0, s1, st);
+  return vec ? dispatch<int32_t, true>(c, a, s0, s1, st) : dispatch<int32_t, false>(c, a, s0, s1, st);
 }

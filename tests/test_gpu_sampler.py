@@ -1,0 +1,102 @@
+"""GPU parity: the fused sampler kernels (through the C ABI / module surface) against the golden
+vectors from the reference and against the dense oracle on seeded inputs.
+
+Tolerance (hard part 3): |a-b| <= 1e-5*max(1,|b|) on outputs, compared where the
+spike histories agree; spike-history mismatch budget 1e-4 (near-threshold float ties)."""
+import numpy as np
+import pytest
+import torch
+
+import eas_snn_b200 as eas
+from eas_snn_b200 import synth
+from oracle import sampler as osamp
+from helpers import load_golden, sampler_case, sampler_kwargs, close_report
+
+pytestmark = pytest.mark.gpu
+
+NAMES = list(load_golden("sampler")["names"])
+
+
+def _compare(out_gpu, out_ref, budget=1e-4):
+    a, b = out_gpu.detach().cpu(), out_ref.detach().cpu()
+    err = (a - b).abs()
+    tol = 1e-5 * torch.clamp(b.abs(), min=1.0)
+    bad = err > tol
+    frac = bad.float().mean().item()
+    msg = "max|d|=%.3e bad=%d/%d (%.2e)" % (err.max().item(), int(bad.sum()), bad.numel(), frac)
+    if bad.any():
+        idx = torch.nonzero(bad)[:6].tolist()
+        msg += " first %s got %s want %s" % (idx, [a[tuple(i)].item() for i in idx], [b[tuple(i)].item() for i in idx])
+    return frac <= budget, frac, msg
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_forward_golden(cuda, name):
+    z = load_golden("sampler")
+    cfg, params, grads, x, y = sampler_case(z, name)
+    m = eas.AdaptiveRSNNEmbedding(**sampler_kwargs(cfg)).to(cuda)
+    m.load_state_dict(params)
+    with torch.no_grad():
+        out = m(x.to(cuda))
+    assert out.shape == y.shape and out.dtype == torch.float32
+    ok, frac, msg = _compare(out, y, budget=2e-3 if y.numel() < 10000 else 1e-3)
+    assert ok, name + ": " + msg
+    # the int32 front door gives the same result as the fp32 one
+    with torch.no_grad():
+        out_i = m(x.to(cuda).int())
+    assert torch.equal(out, out_i)
+
+
+def test_forward_vs_oracle_gen1_shape(cuda):
+    """BASELINE config-1 shape: B=2, Tm=4, 240x304, published flags, Poisson counts."""
+    torch.manual_seed(80)
+    kw = dict(kernel_size=5, in_channel=2, out_channel=2, readout="sum", split=False, write_zero=True, abs=False,
+              depth=2, nb_steps=4, vreset=0, thresh=1, embedding="arsnn", Ts=1, spike_attach=True)
+    ref = osamp.OracleSampler(**kw)
+    g = torch.Generator().manual_seed(99)
+    x = torch.poisson(torch.full((2, 4, 2, 240, 304), 1.2), generator=g)
+    with torch.no_grad():
+        want, st = osamp.sampler_forward(x, *_wb(ref), Ts=1, thresh=1, vreset=0, readout="sum",
+                                         spike_attach=True, write_zero=True, return_state=True)
+    fired = (st["seg"] > 0).float().mean().item()
+    assert 0.05 < fired < 0.95, fired
+    m = eas.AdaptiveRSNNEmbedding(**kw).to(cuda)
+    m.load_state_dict(ref.state_dict())
+    with torch.no_grad():
+        out = m(x.to(cuda))
+    ok, frac, msg = _compare(out, want, budget=1e-4)
+    assert ok, msg
+
+
+def _wb(ref):
+    iw, ib = ref._wb(ref.input_conv)
+    gw, gb = ref._wb(ref.gate_conv)
+    return iw, ib, gw, gb
+
+
+def test_6d_input_and_batch_independence(cuda):
+    torch.manual_seed(1)
+    m = eas.AdaptiveRSNNEmbedding(kernel_size=5, depth=2, nb_steps=4, thresh=1, vreset=0, Ts=1,
+                                  write_zero=True, spike_attach=True).to(cuda)
+    x = torch.poisson(torch.full((3, 2, 4, 2, 32, 72), 1.3)).to(cuda)       # [B, Tl, Tm, 2, H, W]
+    with torch.no_grad():
+        full = m(x)
+        assert full.shape == (1, 6, 2, 32, 72)
+        one = m(x[1:2, 1])                                                   # window (b=1, l=1) alone
+    assert torch.equal(full[:, 3], one[:, 0])
+
+
+def test_forward_events_equals_bin_then_sample(cuda):
+    H, W = 64, 80
+    arrs = synth.make_batch(9, 3, H, W, 2e4, 6e4)
+    d = [torch.from_numpy(a).to(cuda) for a in arrs]
+    torch.manual_seed(2)
+    m = eas.AdaptiveRSNNEmbedding(kernel_size=5, depth=2, nb_steps=4, thresh=1, vreset=0, Ts=1,
+                                  write_zero=True, spike_attach=True).to(cuda)
+    with torch.no_grad():
+        a = m.forward_events(*d, H, W)
+        hist = eas.bin_events(*d, H, W, 4)
+        b = m(hist.float())
+    assert a.shape == (1, 3, 2, H, W)
+    assert torch.equal(a, b)
+    assert (a != 0).float().mean().item() > 0.01
