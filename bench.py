@@ -194,7 +194,7 @@ def run_ours(args):
     model = eas.AdaptiveRSNNEmbedding(**SAMPLER_KW).to(dev).eval()
     host = [HostEventBatch(*b) for b in host_batches(rank, BATCH)]
     devb = [hb.to_device(dev) for hb in host]
-    hist_buf = torch.empty((BATCH, TM, 2, H, W), dtype=torch.int32, device=dev)
+    hist_buf = torch.empty((BATCH, TM, 2, H, W), dtype=torch.float32, device=dev)
     torch.cuda.synchronize()
 
     def step(db):
@@ -237,7 +237,7 @@ def run_ours(args):
                           t=torch.empty(nmax, dtype=torch.int64, device=dev),
                           p=torch.empty(nmax, dtype=torch.uint8, device=dev),
                           off=torch.empty(BATCH + 1, dtype=torch.int64, device=dev),
-                          hist=torch.empty((BATCH, TM, 2, H, W), dtype=torch.int32, device=dev),
+                          hist=torch.empty((BATCH, TM, 2, H, W), dtype=torch.float32, device=dev),
                           host_out=torch.empty((TS, BATCH, 2, H, W), dtype=torch.float32).pin_memory(),
                           in_ready=torch.cuda.Event(), cmp_done=torch.cuda.Event(), out_done=torch.cuda.Event()))
     h2d_bytes = int(np.mean([h.nbytes for h in host]))

@@ -16,12 +16,14 @@ STRATEGY = {"auto": 0, "reds": 1, "tiles": 2}
 
 
 def bin_events(x: torch.Tensor, y: torch.Tensor, t: torch.Tensor, p: torch.Tensor, offsets: torch.Tensor,
-               H: int, W: int, Tm: int, strategy: str = "auto", out: torch.Tensor | None = None) -> torch.Tensor:
+               H: int, W: int, Tm: int, strategy: str = "auto", out: torch.Tensor | None = None,
+               dtype: torch.dtype = torch.int32) -> torch.Tensor:
     """Histogram B time-sorted windows.
 
     x, y : int16 ``[N]``; t : int64 ``[N]`` (sorted inside each window); p : uint8/bool ``[N]``;
     offsets : int64 ``[B+1]`` with ``offsets[0] == 0`` and ``offsets[B] == N``.  All CUDA tensors.
-    Returns int32 ``[B, Tm, 2, H, W]`` (counts; cast with ``.float()`` for the reference's dtype).
+    Returns ``[B, Tm, 2, H, W]`` counts, int32 (default) or float32 (``dtype=torch.float32``: exact
+    below 2^24, the dtype the reference casts to on the device and the sampler consumes).
     """
     _lib.require_cuda(x, y, t, p, offsets)
     if p.dtype == torch.bool:
@@ -36,16 +38,20 @@ def bin_events(x: torch.Tensor, y: torch.Tensor, t: torch.Tensor, p: torch.Tenso
     x, y, t, p, offsets = (a.contiguous() for a in (x, y, t, p, offsets))
     B = offsets.numel() - 1
     if out is None:
-        out = torch.empty((B, Tm, 2, H, W), dtype=torch.int32, device=x.device)
-    elif out.shape != (B, Tm, 2, H, W) or out.dtype != torch.int32 or not out.is_contiguous():
-        raise ValueError("out must be a contiguous int32 [B, Tm, 2, H, W] tensor")
+        if dtype not in (torch.int32, torch.float32):
+            raise TypeError("histogram dtype must be int32 or float32")
+        out = torch.empty((B, Tm, 2, H, W), dtype=dtype, device=x.device)
+    elif (out.shape != (B, Tm, 2, H, W) or out.dtype not in (torch.int32, torch.float32)
+          or not out.is_contiguous()):
+        raise ValueError("out must be a contiguous int32/float32 [B, Tm, 2, H, W] tensor")
     L = _lib.lib()
     ws_bytes = L.eas_bin_events_ws_bytes(B, Tm)
     ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
         rc = L.eas_bin_events_ex(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), _lib.ptr(offsets),
                                  B, n, H, W, Tm, _lib.ptr(out), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(),
-                                 STRATEGY[strategy])
+                                 STRATEGY[strategy],
+                                 _lib.EAS_F32 if out.dtype == torch.float32 else _lib.EAS_I32)
     _lib.check(rc, "eas_bin_events")
     return out
 

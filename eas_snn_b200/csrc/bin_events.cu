@@ -65,10 +65,23 @@ bin_bounds_kernel(const int64_t* __restrict__ t, const int64_t* __restrict__ off
 // ---- strategy "tiles" ---------------------------------------------------------------------
 // work item = (window b, micro-bin k, polarity c, row slab): counted in shared memory as packed
 // 16-bit lanes, written once.  Items are handed out through an atomic counter.
+template <typename OUT_T> struct Cvt;
+template <> struct Cvt<int32_t> {
+  static __device__ __forceinline__ uint32_t enc(uint32_t c) { return c; }
+  static __device__ __forceinline__ uint32_t add(uint32_t old, uint32_t c) { return old + c; }
+};
+template <> struct Cvt<float> {  // counts < 2^24 are exact in fp32
+  static __device__ __forceinline__ uint32_t enc(uint32_t c) { return __float_as_uint((float)c); }
+  static __device__ __forceinline__ uint32_t add(uint32_t old, uint32_t c) {
+    return __float_as_uint(__uint_as_float(old) + (float)c);
+  }
+};
+
+template <typename OUT_T>
 __global__ void __launch_bounds__(kSmemThreads)
 bin_hist_smem_kernel(const int16_t* __restrict__ x, const int16_t* __restrict__ y,
                      const uint8_t* __restrict__ p, const int64_t* __restrict__ bounds, int64_t n_items,
-                     int H, int W, int Tm, int n_slabs, int slab_rows, int32_t* __restrict__ hist,
+                     int H, int W, int Tm, int n_slabs, int slab_rows, uint32_t* __restrict__ hist,
                      unsigned int* __restrict__ work_counter) {
   extern __shared__ __align__(16) uint32_t cnt[];  // ceil(slab_rows*W/2) words, two 16-bit counters per word
   __shared__ unsigned int sh_item;
@@ -91,7 +104,7 @@ bin_hist_smem_kernel(const int16_t* __restrict__ x, const int16_t* __restrict__ 
     const int npix = rows * W;
     const int nwords = (npix + 1) >> 1;
     const int nwords4 = (nwords + 3) & ~3;
-    int32_t* __restrict__ out = hist + bkc * HW + (int64_t)y_lo * W;
+    uint32_t* __restrict__ out = hist + bkc * HW + (int64_t)y_lo * W;
     const bool vec_ok = (npix & 3) == 0 && ((((int64_t)y_lo * W) & 3) == 0) && ((HW & 3) == 0);
     bool first = true;
     for (int64_t cs = s; first || cs < e; cs += kChunk) {
@@ -114,18 +127,22 @@ bin_hist_smem_kernel(const int16_t* __restrict__ x, const int16_t* __restrict__ 
         // 2 words = 4 counters -> one 16 B store
         for (int w = threadIdx.x * 2; w < nwords; w += kSmemThreads * 2) {
           const uint2 v = *reinterpret_cast<const uint2*>(cnt + w);
-          uint4 o = make_uint4(v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16);
+          const uint32_t c0 = v.x & 0xffffu, c1 = v.x >> 16, c2 = v.y & 0xffffu, c3 = v.y >> 16;
           uint4* dst = reinterpret_cast<uint4*>(out + 2 * w);
-          if (!first) {
+          uint4 o;
+          if (first) {
+            o = make_uint4(Cvt<OUT_T>::enc(c0), Cvt<OUT_T>::enc(c1), Cvt<OUT_T>::enc(c2), Cvt<OUT_T>::enc(c3));
+          } else {
             const uint4 old = *dst;
-            o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
+            o = make_uint4(Cvt<OUT_T>::add(old.x, c0), Cvt<OUT_T>::add(old.y, c1), Cvt<OUT_T>::add(old.z, c2),
+                           Cvt<OUT_T>::add(old.w, c3));
           }
           st_stream_u4(dst, o);
         }
       } else {
         for (int q = threadIdx.x; q < npix; q += kSmemThreads) {
           const uint32_t v = (cnt[q >> 1] >> ((q & 1) << 4)) & 0xffffu;
-          out[q] = first ? (int32_t)v : out[q] + (int32_t)v;
+          out[q] = first ? Cvt<OUT_T>::enc(v) : Cvt<OUT_T>::add(out[q], v);
         }
       }
       first = false;
@@ -137,11 +154,12 @@ bin_hist_smem_kernel(const int16_t* __restrict__ x, const int16_t* __restrict__ 
 // ---- strategy "reds" ----------------------------------------------------------------------
 constexpr int kEpt = 8;  // events per thread per iteration (one 16 B load of x and of y)
 
+template <typename OUT_T>
 __global__ void __launch_bounds__(256)
 bin_hist_global_kernel(const int16_t* __restrict__ x, const int16_t* __restrict__ y,
                        const uint8_t* __restrict__ p, const int64_t* __restrict__ offsets,
                        const int64_t* __restrict__ bounds, int64_t B, int64_t n, int H, int W, int Tm,
-                       int32_t* __restrict__ hist) {
+                       OUT_T* __restrict__ hist) {
   const int64_t HW = (int64_t)H * W;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * kEpt;
   for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kEpt; i0 < n; i0 += stride) {
@@ -184,7 +202,7 @@ bin_hist_global_kernel(const int16_t* __restrict__ x, const int16_t* __restrict_
       const int xi = xs[j], yi = ys[j];
       if (k < Tm && i >= bnd[0] && (unsigned)xi < (unsigned)W && (unsigned)yi < (unsigned)H) {
         const int c = ps[j] != 0;
-        atomicAdd(hist + ((b * Tm + k) * 2 + c) * HW + (int64_t)yi * W + xi, 1);
+        atomicAdd(hist + ((b * Tm + k) * 2 + c) * HW + (int64_t)yi * W + xi, (OUT_T)1);
       }
     }
   }
@@ -200,12 +218,14 @@ extern "C" size_t eas_bin_events_ws_bytes(int64_t B, int Tm) {
 
 extern "C" int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64_t* t, const uint8_t* p,
                                  const int64_t* offsets, int64_t B, int64_t n_events, int H, int W, int Tm,
-                                 int32_t* hist, void* ws, size_t ws_bytes, void* stream_, int strategy) {
+                                 void* hist, void* ws, size_t ws_bytes, void* stream_, int strategy,
+                                 int out_dtype) {
   cudaStream_t stream = (cudaStream_t)stream_;
   EAS_REQUIRE(B >= 0 && n_events >= 0, EAS_E_SHAPE);
   EAS_REQUIRE(H > 0 && W > 0 && Tm > 0 && Tm <= 1024, EAS_E_SHAPE);
   EAS_REQUIRE((int64_t)H * W < (1ll << 30), EAS_E_SHAPE);
   EAS_REQUIRE(strategy >= 0 && strategy <= 2, EAS_E_UNSUPPORTED);
+  EAS_REQUIRE(out_dtype == EAS_I32 || out_dtype == EAS_F32, EAS_E_UNSUPPORTED);
   if (B == 0) return EAS_OK;
   EAS_REQUIRE(offsets && hist && ws, EAS_E_NULL);
   EAS_REQUIRE(n_events == 0 || (x && y && t && p), EAS_E_NULL);
@@ -237,14 +257,14 @@ extern "C" int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64
   }
   if (strategy == 2) {
     EAS_REQUIRE(fits, EAS_E_UNSUPPORTED);
-    cudaError_t e = cudaFuncSetAttribute(bin_hist_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+    auto kern = out_dtype == EAS_F32 ? bin_hist_smem_kernel<float> : bin_hist_smem_kernel<int32_t>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int per_sm = (int)((220 * 1024) / (smem + 1024));
     int64_t grid = (int64_t)EAS_NUM_SMS * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
     if (grid > n_items) grid = n_items;
-    bin_hist_smem_kernel<<<(unsigned)grid, kSmemThreads, smem, stream>>>(x, y, p, bounds, n_items, H, W, Tm,
-                                                                        n_slabs, slab_rows, hist, counter);
+    kern<<<(unsigned)grid, kSmemThreads, smem, stream>>>(x, y, p, bounds, n_items, H, W, Tm, n_slabs, slab_rows,
+                                                         (uint32_t*)hist, counter);
     EAS_LAUNCH_CHECK();
   } else {
     cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)B * Tm * 2 * HW * sizeof(int32_t), stream);
@@ -254,8 +274,12 @@ extern "C" int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64
       int64_t blocks = eas_ceil_div(threads, 256);
       const int64_t cap = (int64_t)EAS_NUM_SMS * 8 * 4;  // 8 resident CTAs/SM, a few waves
       if (blocks > cap) blocks = cap;
-      bin_hist_global_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, y, p, offsets, bounds, B, n_events, H, W,
-                                                                   Tm, hist);
+      if (out_dtype == EAS_F32)
+        bin_hist_global_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>(x, y, p, offsets, bounds, B, n_events,
+                                                                            H, W, Tm, (float*)hist);
+      else
+        bin_hist_global_kernel<int32_t><<<(unsigned)blocks, 256, 0, stream>>>(x, y, p, offsets, bounds, B, n_events,
+                                                                              H, W, Tm, (int32_t*)hist);
       EAS_LAUNCH_CHECK();
     }
   }
@@ -265,5 +289,5 @@ extern "C" int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64
 extern "C" int eas_bin_events(const int16_t* x, const int16_t* y, const int64_t* t, const uint8_t* p,
                               const int64_t* offsets, int64_t B, int64_t n_events, int H, int W, int Tm,
                               int32_t* hist, void* ws, size_t ws_bytes, void* stream) {
-  return eas_bin_events_ex(x, y, t, p, offsets, B, n_events, H, W, Tm, hist, ws, ws_bytes, stream, 0);
+  return eas_bin_events_ex(x, y, t, p, offsets, B, n_events, H, W, Tm, hist, ws, ws_bytes, stream, 0, EAS_I32);
 }

@@ -61,31 +61,54 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// acc[co][px] += sum_{ci,ky,kx} src[ci][ky][px+kx] * w[ci][ky][kx][co]
+// Packed fp32 FMA (Blackwell FFMA2): {d.lo, d.hi} += a * {b.lo, b.hi}; `a` is a scalar that the
+// assembler encodes as a broadcast operand, so one issue slot does two IEEE fmas.
+__device__ __forceinline__ void ffma2_bcast(unsigned long long& d, float a, float b0, float b1) {
+  unsigned long long av, bv;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(bv) : "f"(b0), "f"(b1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(av), "l"(bv));
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+// acc[co][px] += sum_{ci,ky,kx} src[ci][ky][px+kx] * w[ci][ky][kx][co]      (CO == 4)
+// The (ci, ky) loop is rolled (small code: the whole kernel must stay inside the instruction cache)
+// and software pipelined: the next input row is fetched from shared memory while the current one
+// feeds K*CO*PX fmas, issued as FFMA2 over output-channel pairs (accp[co/2][px] = {co, co+1}).
 template <int CI, int CO, int K, int PX>
 __device__ __forceinline__ void conv_acc(const float* __restrict__ src, int ch_stride, int row_stride,
-                                         const float* __restrict__ wsm, float (&acc)[CO][PX]) {
+                                         const float* __restrict__ wsm, unsigned long long (&accp)[CO / 2][PX]) {
+  static_assert(CO == 4, "weights are fetched as float4");
   constexpr int NIN = PX + K - 1;
   constexpr int NV = (NIN + 3) / 4;
-#pragma unroll 1
-  for (int ci = 0; ci < CI; ++ci) {
+  float4 nxt[NV];
+  {
+    const float4* rowp = reinterpret_cast<const float4*>(src);
 #pragma unroll
-    for (int ky = 0; ky < K; ++ky) {
-      float in[NV * 4];
+    for (int v = 0; v < NV; ++v) nxt[v] = rowp[v];
+  }
+#pragma unroll 1
+  for (int it = 0; it < CI * K; ++it) {
+    float in[NV * 4];
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      in[4 * v + 0] = nxt[v].x, in[4 * v + 1] = nxt[v].y, in[4 * v + 2] = nxt[v].z, in[4 * v + 3] = nxt[v].w;
+    if (it + 1 < CI * K) {
+      const int ci = (it + 1) / K, ky = (it + 1) - ci * K;
       const float4* rowp = reinterpret_cast<const float4*>(src + ci * ch_stride + ky * row_stride);
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const float4 q = rowp[v];
-        in[4 * v + 0] = q.x, in[4 * v + 1] = q.y, in[4 * v + 2] = q.z, in[4 * v + 3] = q.w;
-      }
+      for (int v = 0; v < NV; ++v) nxt[v] = rowp[v];
+    }
+    const float4* wp = reinterpret_cast<const float4*>(wsm + it * K * CO);
 #pragma unroll
-      for (int kx = 0; kx < K; ++kx) {
-        const float4 wq = *reinterpret_cast<const float4*>(wsm + ((ci * K + ky) * K + kx) * CO);
-        const float wv[4] = {wq.x, wq.y, wq.z, wq.w};
+    for (int kx = 0; kx < K; ++kx) {
+      const float4 wq = wp[kx];
 #pragma unroll
-        for (int co = 0; co < CO; ++co)
-#pragma unroll
-          for (int px = 0; px < PX; ++px) acc[co][px] = fmaf(in[px + kx], wv[co], acc[co][px]);
+      for (int px = 0; px < PX; ++px) {
+        ffma2_bcast(accp[0][px], in[px + kx], wq.x, wq.y);
+        ffma2_bcast(accp[1][px], in[px + kx], wq.z, wq.w);
       }
     }
   }
@@ -95,7 +118,7 @@ template <int K, int DEPTH, int TH, int TW>
 struct Geo {
   static constexpr int R = K / 2;
   static constexpr int HALO = R * DEPTH;
-  static constexpr int PX = 8;
+  static constexpr int PX = 4;
   static constexpr int NT = TH * TW / PX;
   // second-layer input (h1 for depth 2, the raw tile for depth 1)
   static constexpr int HR = TH + 2 * R;
@@ -120,7 +143,7 @@ struct Geo {
 };
 
 template <int K, int DEPTH, int TH, int TW, typename IN_T, bool VEC>
-__global__ void __launch_bounds__(TH* TW / 8, 2)
+__global__ void __launch_bounds__(TH* TW / 4, 2)
 sampler_step_kernel(const StepArgs a) {
   using G = Geo<K, DEPTH, TH, TW>;
   constexpr int R = G::R;
@@ -295,22 +318,40 @@ sampler_step_kernel(const StepArgs a) {
     // ---- layer 1 (depth 2): 2->4 per stack, bias, ReLU, zero outside the image ----------------
     if (DEPTH == 2) {
       constexpr int PX1 = 4;
-      constexpr int NSTRIP = G::HR * (G::HC / PX1);
-      for (int idx = tid; idx < NSTRIP; idx += G::NT) {
-        const int r = idx / (G::HC / PX1);
-        const int c0 = (idx - r * (G::HC / PX1)) * PX1;
+      constexpr int SPR = G::HC / PX1;            // strips per row
+      constexpr int NITEM = 2 * G::HR * SPR;      // (stack, row, strip)
+      for (int idx = tid; idx < NITEM; idx += G::NT) {
+        const int stack = idx / (G::HR * SPR);
+        const int rem = idx - stack * (G::HR * SPR);
+        const int r = rem / SPR;
+        const int c0 = (rem - r * SPR) * PX1;
         const int gy = y0 - R + r;
         const bool row_in = (unsigned)gy < (unsigned)a.H;
+        unsigned long long accp[2][PX1];
 #pragma unroll
-        for (int stack = 0; stack < 2; ++stack) {
-          float acc[4][PX1];
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int co = 0; co < 4; ++co)
+          for (int px = 0; px < PX1; ++px) accp[h][px] = 0ull;
+        if (row_in && !(stack == 1 && first))
+          conv_acc<2, 4, K, PX1>(sh_i + (stack * 2 * G::IR + r) * G::IS + c0, G::IR * G::IS, G::IS,
+                                 sh_w1 + stack * G::W1, accp);
+        float acc[4][PX1];
 #pragma unroll
-            for (int px = 0; px < PX1; ++px) acc[co][px] = 0.0f;
-          if (row_in && !(stack == 1 && first))
-            conv_acc<2, 4, K, PX1>(sh_i + (stack * 2 * G::IR + r) * G::IS + c0, G::IR * G::IS, G::IS,
-                                   sh_w1 + stack * G::W1, acc);
+        for (int px = 0; px < PX1; ++px) {
+          unpack2(accp[0][px], acc[0][px], acc[1][px]);
+          unpack2(accp[1][px], acc[2][px], acc[3][px]);
+        }
+        const int gxs = x0 - R + c0;
+        float* hp = sh_h + (stack * 4 * G::HR + r) * G::HS + c0;
+        if (row_in && gxs >= 0 && gxs + PX1 <= a.W) {  // strip fully inside the image (the common case)
+#pragma unroll
+          for (int co = 0; co < 4; ++co) {
+            const float bias = sh_b[4 + stack * 4 + co];
+            *reinterpret_cast<float4*>(hp + co * G::HR * G::HS) =
+                make_float4(fmaxf(acc[co][0] + bias, 0.0f), fmaxf(acc[co][1] + bias, 0.0f),
+                            fmaxf(acc[co][2] + bias, 0.0f), fmaxf(acc[co][3] + bias, 0.0f));
+          }
+        } else {
 #pragma unroll
           for (int co = 0; co < 4; ++co) {
             const float bias = sh_b[4 + stack * 4 + co];
@@ -318,11 +359,10 @@ sampler_step_kernel(const StepArgs a) {
             float* op = reinterpret_cast<float*>(&o);
 #pragma unroll
             for (int px = 0; px < PX1; ++px) {
-              const int gx = x0 - R + c0 + px;
-              const bool in_img = row_in && (unsigned)gx < (unsigned)a.W;
+              const bool in_img = row_in && (unsigned)(gxs + px) < (unsigned)a.W;
               op[px] = in_img ? fmaxf(acc[co][px] + bias, 0.0f) : 0.0f;
             }
-            *reinterpret_cast<float4*>(sh_h + ((stack * 4 + co) * G::HR + r) * G::HS + c0) = o;
+            *reinterpret_cast<float4*>(hp + co * G::HR * G::HS) = o;
           }
         }
       }
@@ -336,11 +376,19 @@ sampler_step_kernel(const StepArgs a) {
     const int r = tid / (TW / PX);
     const int c0 = (tid - r * (TW / PX)) * PX;
     float acc2[4][PX];
+    {
+      unsigned long long accp[2][PX];
 #pragma unroll
-    for (int co = 0; co < 4; ++co)
+      for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int px = 0; px < PX; ++px) acc2[co][px] = 0.0f;
-    conv_acc<(DEPTH == 2 ? 8 : 4), 4, K, PX>(sh_h + r * G::HS + c0, G::HR * G::HS, G::HS, sh_w2, acc2);
+        for (int px = 0; px < PX; ++px) accp[h][px] = 0ull;
+      conv_acc<(DEPTH == 2 ? 8 : 4), 4, K, PX>(sh_h + r * G::HS + c0, G::HR * G::HS, G::HS, sh_w2, accp);
+#pragma unroll
+      for (int px = 0; px < PX; ++px) {
+        unpack2(accp[0][px], acc2[0][px], acc2[1][px]);
+        unpack2(accp[1][px], acc2[2][px], acc2[3][px]);
+      }
+    }
 
     if (DEPTH == 1) {
       __syncthreads();  // everyone is done reading the raw tile
@@ -351,6 +399,9 @@ sampler_step_kernel(const StepArgs a) {
     __syncthreads();
 
     // ---- membrane update + spike-triggered aggregation (embedding.py:132-139, 177-217) --------
+    // Every agg[k] element is written exactly once: by the k-th valid spike of its pixel or by the
+    // residual write at the end (the reference's "+=" always lands on a still-zero element), so
+    // the read-out is a plain store and ReLU (abs) can be applied at write time.
     const int gy = y0 + r;
     const int nv = min(PX, a.W - (x0 + c0));  // valid pixels of this strip (<= 0: none)
     if (gy < a.H && nv > 0) {
@@ -359,96 +410,80 @@ sampler_step_kernel(const StepArgs a) {
         const float bg = sh_b[c], bc = sh_b[2 + c];
         const int64_t base = ((int64_t)b * 2 + c) * HW + (int64_t)gy * a.W + x0 + c0;
         const int so = (c * TH + r) * TW + c0;
-        __align__(16) float vm8[PX], ac8[PX], v8[PX], g8[PX], s8[PX];
-        __align__(16) uint16_t m8[PX];
+        __align__(16) float vm4[PX], ac4[PX], v4[PX], g4[PX], s4[PX], o4[PX];
+        __align__(8) uint16_t m4[PX];
         if (first) {
 #pragma unroll
-          for (int px = 0; px < PX; ++px) vm8[px] = 0.0f, ac8[px] = 0.0f, m8[px] = 0;
+          for (int px = 0; px < PX; ++px) vm4[px] = 0.0f, ac4[px] = 0.0f, m4[px] = 0;
         } else {
-          *reinterpret_cast<float4*>(vm8) = *reinterpret_cast<const float4*>(sh_vm + so);
-          *reinterpret_cast<float4*>(vm8 + 4) = *reinterpret_cast<const float4*>(sh_vm + so + 4);
-          *reinterpret_cast<float4*>(ac8) = *reinterpret_cast<const float4*>(sh_acc + so);
-          *reinterpret_cast<float4*>(ac8 + 4) = *reinterpret_cast<const float4*>(sh_acc + so + 4);
-          *reinterpret_cast<uint4*>(m8) = *reinterpret_cast<const uint4*>(sh_meta + so);
+          *reinterpret_cast<float4*>(vm4) = *reinterpret_cast<const float4*>(sh_vm + so);
+          *reinterpret_cast<float4*>(ac4) = *reinterpret_cast<const float4*>(sh_acc + so);
+          *reinterpret_cast<uint2*>(m4) = *reinterpret_cast<const uint2*>(sh_meta + so);
         }
         float* outp = a.out + base;  // plane k at outp + k*BHW2
 #pragma unroll
         for (int px = 0; px < PX; ++px) {
-          const float gate = eas_sigmoid(acc2[c][px] + bg);
+          const float gate = __fdividef(1.0f, 1.0f + __expf(-(acc2[c][px] + bg)));
           const float cur = acc2[2 + c][px] + bc;
-          int seg = m8[px] & 0xff;
-          int tl = (int)(m8[px] >> 8) - 1;
-          float vm = vm8[px], ac = ac8[px];
-          const float v = __fadd_rn(__fmul_rn(gate, vm), cur);
+          int seg = m4[px] & 0xff;
+          int tl = (int)(m4[px] >> 8) - 1;
+          const float v = __fadd_rn(__fmul_rn(gate, vm4[px]), cur);
           const bool s = __fsub_rn(v, a.thresh) > 0.0f;
-          if (a.hard_reset) vm = s ? a.vreset : v;
-          else vm = s ? __fsub_rn(v, a.thresh) : v;
-          ac = __fadd_rn(ac, v);
+          const float vm = s ? (a.hard_reset ? a.vreset : __fsub_rn(v, a.thresh)) : v;
+          float ac = __fadd_rn(ac4[px], v);
           const bool valid = s && seg < a.Ts;
-          float val = 0.0f;
-          if (valid) {
-            if (a.readout == EAS_READOUT_SUM) val = ac;
-            else if (a.readout == EAS_READOUT_LAST) val = vm;
-            else val = ac / (float)(a.t - tl);
+          float val = a.readout == EAS_READOUT_SUM ? ac : vm;
+          if (a.readout == EAS_READOUT_AVG) val = ac / (float)(a.t - tl);
+          if (a.use_abs) val = fmaxf(val, 0.0f);
+          o4[px] = valid ? val : 0.0f;        // plane 0 on the first step
+          if (!first && valid && px < nv) outp[(int64_t)seg * BHW2 + px] = val;
+          seg += valid ? 1 : 0;
+          tl = valid ? a.t : tl;
+          ac = s ? 0.0f : ac;
+          if (last && !s && seg < a.Ts && !a.write_zero && px < nv) {
+            float tv = a.readout == EAS_READOUT_SUM ? ac : vm;
+            if (a.readout == EAS_READOUT_AVG) tv = ac / (float)(a.Tm - 1 - tl);
+            if (a.use_abs) tv = fmaxf(tv, 0.0f);
+            if (first && seg == 0) o4[px] = tv;   // Tm == 1: still inside the zero-initialising store
+            else outp[(int64_t)seg * BHW2 + px] = tv;
           }
-          if (px < nv) {
-            if (first) {
-              for (int k = 0; k < a.Ts; ++k) outp[k * BHW2 + px] = (valid && k == 0) ? val : 0.0f;
-            } else if (valid) {
-              outp[seg * BHW2 + px] += val;
-            }
-          }
-          if (valid) {
-            ++seg;
-            tl = a.t;
-          }
-          if (s) ac = 0.0f;
-          if (last && px < nv) {
-            if (!s && seg < a.Ts && !a.write_zero) {
-              float tv;
-              if (a.readout == EAS_READOUT_SUM) tv = ac;
-              else if (a.readout == EAS_READOUT_LAST) tv = vm;
-              else tv = ac / (float)(a.Tm - 1 - tl);
-              outp[seg * BHW2 + px] += tv;
-            }
-            if (a.use_abs)
-              for (int k = 0; k < a.Ts; ++k) outp[k * BHW2 + px] = fmaxf(outp[k * BHW2 + px], 0.0f);
-          }
-          vm8[px] = vm, ac8[px] = ac, v8[px] = v, g8[px] = gate, s8[px] = s ? 1.0f : 0.0f;
-          m8[px] = (uint16_t)(seg | ((tl + 1) << 8));
+          vm4[px] = vm, ac4[px] = ac, v4[px] = v, g4[px] = gate, s4[px] = s ? 1.0f : 0.0f;
+          m4[px] = (uint16_t)(seg | ((tl + 1) << 8));
         }
-        // ---- state / training stores ----
-        if (VEC) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (nv >= 4 * (h + 1)) {
-              if (!last) {
-                *reinterpret_cast<float4*>(a.vm + base + 4 * h) = *reinterpret_cast<const float4*>(vm8 + 4 * h);
-                *reinterpret_cast<float4*>(a.acc + base + 4 * h) = *reinterpret_cast<const float4*>(ac8 + 4 * h);
-                *reinterpret_cast<uint2*>(a.meta + base + 4 * h) = *reinterpret_cast<const uint2*>(m8 + 4 * h);
-                *reinterpret_cast<float4*>(a.s_next + base + 4 * h) = *reinterpret_cast<const float4*>(s8 + 4 * h);
-              }
-              if (a.v_seq) {
-                const int64_t se = (int64_t)a.t * BHW2 + base + 4 * h;
-                *reinterpret_cast<float4*>(a.v_seq + se) = *reinterpret_cast<const float4*>(v8 + 4 * h);
-                *reinterpret_cast<float4*>(a.gate_seq + se) = *reinterpret_cast<const float4*>(g8 + 4 * h);
-              }
-            }
+        if (VEC) {  // nv is 4 here (W % 4 == 0)
+          if (first) {
+            *reinterpret_cast<float4*>(outp) = *reinterpret_cast<const float4*>(o4);
+            for (int k = 1; k < a.Ts; ++k) *reinterpret_cast<float4*>(outp + k * BHW2) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (!last) {
+            *reinterpret_cast<float4*>(a.vm + base) = *reinterpret_cast<const float4*>(vm4);
+            *reinterpret_cast<float4*>(a.acc + base) = *reinterpret_cast<const float4*>(ac4);
+            *reinterpret_cast<uint2*>(a.meta + base) = *reinterpret_cast<const uint2*>(m4);
+            *reinterpret_cast<float4*>(a.s_next + base) = *reinterpret_cast<const float4*>(s4);
+          }
+          if (a.v_seq) {
+            const int64_t se = (int64_t)a.t * BHW2 + base;
+            *reinterpret_cast<float4*>(a.v_seq + se) = *reinterpret_cast<const float4*>(v4);
+            *reinterpret_cast<float4*>(a.gate_seq + se) = *reinterpret_cast<const float4*>(g4);
           }
         } else {
 #pragma unroll
           for (int px = 0; px < PX; ++px) {
             if (px < nv) {
+              if (first) {
+                outp[px] = o4[px];
+                for (int k = 1; k < a.Ts; ++k) outp[k * BHW2 + px] = 0.0f;
+              }
               if (!last) {
-                a.vm[base + px] = vm8[px];
-                a.acc[base + px] = ac8[px];
-                a.meta[base + px] = m8[px];
-                a.s_next[base + px] = s8[px];
+                a.vm[base + px] = vm4[px];
+                a.acc[base + px] = ac4[px];
+                a.meta[base + px] = m4[px];
+                a.s_next[base + px] = s4[px];
               }
               if (a.v_seq) {
                 const int64_t se = (int64_t)a.t * BHW2 + base + px;
-                a.v_seq[se] = v8[px];
-                a.gate_seq[se] = g8[px];
+                a.v_seq[se] = v4[px];
+                a.gate_seq[se] = g4[px];
               }
             }
           }

@@ -183,7 +183,7 @@ class AdaptiveRSNNEmbedding(nn.Module):
         """Raw time-sorted event windows -> adaptive frames ``[Ts, B, 2, H, W]``.
 
         Binning (gen1.py:313-360) and sampling (embedding.py:141-226) back to back on the GPU;
-        the int32 histogram is consumed directly by the sampler kernel.
+        the histogram is written as fp32 counts and consumed directly by the sampler kernel.
         """
-        hist = bin_events(x, y, t, p, offsets, H, W, self.nb_steps, strategy=strategy)
+        hist = bin_events(x, y, t, p, offsets, H, W, self.nb_steps, strategy=strategy, dtype=torch.float32)
         return self.forward(hist)

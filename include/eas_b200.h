@@ -60,10 +60,12 @@ size_t eas_bin_events_ws_bytes(int64_t B, int Tm);
 int eas_bin_events(const int16_t* x, const int16_t* y, const int64_t* t, const uint8_t* p,
                    const int64_t* offsets, int64_t B, int64_t n_events, int H, int W, int Tm,
                    int32_t* hist, void* ws, size_t ws_bytes, void* stream);
-/* Same, forcing one strategy: 0 = auto, 1 = global reductions, 2 = shared-memory tiles. */
+/* Same with options: strategy 0 = auto, 1 = global reductions, 2 = shared-memory tiles;
+ * out_dtype EAS_I32, or EAS_F32 (the counts as fp32, exact below 2^24: what the sampler's first
+ * convolution consumes, and the dtype the reference casts its histogram to on the device). */
 int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64_t* t, const uint8_t* p,
                       const int64_t* offsets, int64_t B, int64_t n_events, int H, int W, int Tm,
-                      int32_t* hist, void* ws, size_t ws_bytes, void* stream, int strategy);
+                      void* hist, void* ws, size_t ws_bytes, void* stream, int strategy, int out_dtype);
 
 /* ------------------------------------------------------------------------------------------
  * (a-2) Adaptive event sampler.  Replaces AdaptiveRSNNEmbedding.forward / update,

@@ -60,7 +60,7 @@ torch.manual_seed(80)
 m = eas.AdaptiveRSNNEmbedding(kernel_size=5, depth=2, nb_steps=4, thresh=1, vreset=0, Ts=1, write_zero=True,
                               spike_attach=True).to(dev)
 for B in (1, 8, 64):
-    hist = eas.bin_events(*[torch.from_numpy(a).to(dev) for a in synth.gen1_batch(B)], H, W, 4)
+    hist = eas.bin_events(*[torch.from_numpy(a).to(dev) for a in synth.gen1_batch(B)], H, W, 4, dtype=torch.float32)
     with torch.no_grad():
         med, mn = timeit(lambda: m(hist))
     flop = 2400.0 * H * W * 4 * B * 1.0

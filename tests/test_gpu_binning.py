@@ -67,6 +67,10 @@ def test_gen1_batch_vs_oracle_and_properties(cuda):
     assert int(a[:, :, 1].sum()) <= int(p.sum())
     # idempotence / determinism
     assert torch.equal(a, eas.bin_events(*d, H, W, 4, strategy="tiles"))
+    # fp32 counts (what the sampler consumes) are the same numbers
+    for s in ("tiles", "reds"):
+        f = eas.bin_events(*d, H, W, 4, strategy=s, dtype=torch.float32)
+        assert f.dtype == torch.float32 and torch.equal(f, a.float())
 
 
 def test_mpx_window_properties(cuda):
