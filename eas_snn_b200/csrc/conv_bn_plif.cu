@@ -1,0 +1,462 @@
+// (a-5) conv -> folded BatchNorm -> multi-step PLIF on the 5th-gen tensor cores (inference).
+// Replaces BaseConv.forward after convert_to_spiking: SeqToANNContainer(Conv2d) -> BatchNorm2d('m')
+// -> ParametricLIFNode (yolox/models/network_blocks.py:52-53, yolox/utils/utils_snn.py:25-53), BN
+// folded as in yolox/utils/model_utils.py:61-75.
+//
+// Implicit GEMM, one CTA per (128-pixel, BLOCK_N-channel) output tile:
+//   M = 128 output pixels = NB images x TH rows x TW cols of ONE time step,
+//   N = BLOCK_N output channels, K = taps x Cin walked in 64-channel blocks (one 128 B swizzle row).
+//   A (activations, channels-last bf16) arrives by TMA as a 5-D box [1 plane][NB][TH][TW][64 ch]: the
+//     box origin is shifted per filter tap, out-of-image rows/cols/channels are zero filled by the
+//     TMA unit (= conv padding), stride-2 convs use the tensor map's element strides.  The box lands
+//     in shared memory exactly in the K-major SWIZZLE_128B layout tcgen05 wants.
+//   B (weights [split][Cout][tap][Cin] bf16) arrives by TMA as [BLOCK_N][1][64].
+//   D: one fp32 accumulator per time step in TMEM (T x BLOCK_N columns), tcgen05.mma issued by one
+//     thread.  fp32 accuracy on bf16 tensor cores comes from splitting the folded fp32 weight into
+//     up to three bf16 planes (hi + mid + lo); spikes / SEW sums are small integers, exact in bf16,
+//     so A needs no split except for real-valued inputs (n_xsplit planes).
+//   Epilogue (4 warps, one TMEM lane = one pixel each): tcgen05.ld the T accumulators of a 16-channel
+//     chunk, add the folded BN shift, run the LIF recurrence over t with v in registers, store bf16
+//     spikes channels-last.  The conv output and the membrane potential never touch HBM.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// Two mbarrier rings: B tiles are loaded once per K block and reused by all T time steps / input
+// planes, A tiles stream through a deeper ring.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include "lif.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;               // bf16 elements = 128 B
+constexpr int A_BYTES = BLOCK_M * 128;    // 16 KB
+constexpr int SA = 3;                     // A ring depth (2 CTAs per SM: 2 x ~98 KB)
+constexpr int SB = 2;                     // B ring depth
+constexpr int MAX_WSPLIT = 3;
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t SPIN_LIMIT = 1u << 27;  // watchdog: trap instead of hanging the GPU
+
+struct ConvArgs {
+  int T, Tx, B, Ho, Wo, Cin, Cout, ksize, stride, pad;
+  int n_wsplit, n_xsplit;
+  int NB, TH, TW;
+  int tiles_w, tiles_h, tiles_b, tiles_n;
+  int out_ld, out_mode;
+  float vth, vreset;
+  int hard_reset, decay_input;
+  const float* bias;
+  const float* plif_w;
+  void* out;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by ONE thread for the whole CTA.
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory operand descriptor (8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address
+  d |= (uint64_t)(1024u >> 4) << 32;          // stride byte offset
+  d |= (uint64_t)1 << 46;                     // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                     // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+template <int BLOCK_N, int TMAX>
+struct SmemLayout {
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_B = OFF_A + SA * A_BYTES;
+  static constexpr int OFF_BAR = OFF_B + SB * MAX_WSPLIT * B_BYTES;
+  static constexpr int OFF_BIAS = OFF_BAR + 128;
+  static constexpr int TOTAL = OFF_BIAS + BLOCK_N * 4 + 1024;  // + slack for the 1024 B alignment
+};
+
+template <int BLOCK_N, int TMAX>
+__global__ void __launch_bounds__(NUM_THREADS)
+conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
+                    const ConvArgs a) {
+  using L = SmemLayout<BLOCK_N, TMAX>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem + L::OFF_A;
+  uint8_t* sB = smem + L::OFF_B;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* fullA = bars;               // [SA]
+  uint64_t* emptyA = bars + SA;         // [SA]
+  uint64_t* fullB = bars + 2 * SA;      // [SB]
+  uint64_t* emptyB = bars + 2 * SA + SB;
+  uint64_t* accum_full = bars + 2 * SA + 2 * SB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 1);
+  float* sBias = reinterpret_cast<float*>(smem + L::OFF_BIAS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Tacc = a.Tx;  // accumulators: one per distinct input time step
+  constexpr uint32_t kCols = TMAX * BLOCK_N <= 32 ? 32 : TMAX * BLOCK_N <= 64 ? 64 : TMAX * BLOCK_N <= 128 ? 128
+                             : TMAX * BLOCK_N <= 256 ? 256 : 512;
+
+  // tile coordinates
+  int tile = blockIdx.x;
+  const int tn = tile % a.tiles_n;
+  tile /= a.tiles_n;
+  const int tw = tile % a.tiles_w;
+  tile /= a.tiles_w;
+  const int th = tile % a.tiles_h;
+  const int tb = tile / a.tiles_h;
+  const int n0 = tn * BLOCK_N, wo0 = tw * a.TW, ho0 = th * a.TH, b0 = tb * a.NB;
+  const int ncb = (a.Cin + BLOCK_K - 1) / BLOCK_K;
+  const int taps = a.ksize * a.ksize;
+  const int nkb = taps * ncb;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+    for (int i = 0; i < SA; ++i) mbar_init(fullA + i, 1), mbar_init(emptyA + i, 1);
+    for (int i = 0; i < SB; ++i) mbar_init(fullB + i, 1), mbar_init(emptyB + i, 1);
+    mbar_init(accum_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) sBias[i] = (n0 + i < a.Cout) ? a.bias[n0 + i] : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int tap = kb / ncb, cb = kb - tap * ncb;
+      const int ky = tap / a.ksize, kx = tap - ky * a.ksize;
+      mbar_wait(emptyB + sb, pb ^ 1);
+      mbar_expect_tx(fullB + sb, (uint32_t)(a.n_wsplit * L::B_BYTES));
+      for (int j = 0; j < a.n_wsplit; ++j)
+        tma_load_3d(sB + (sb * MAX_WSPLIT + j) * L::B_BYTES, &wmap, fullB + sb, cb * BLOCK_K, tap, j * a.Cout + n0);
+      if (++sb == SB) sb = 0, pb ^= 1;
+      for (int t = 0; t < Tacc; ++t) {
+        for (int i = 0; i < a.n_xsplit; ++i) {
+          mbar_wait(emptyA + sa, pa ^ 1);
+          mbar_expect_tx(fullA + sa, (uint32_t)A_BYTES);
+          tma_load_5d(sA + sa * A_BYTES, &xmap, fullA + sa, cb * BLOCK_K, wo0 * a.stride + kx - a.pad,
+                      ho0 * a.stride + ky - a.pad, b0, i * a.Tx + t);
+          if (++sa == SA) sa = 0, pa ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                               ((uint32_t)(BLOCK_M >> 4) << 24);
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(fullB + sb, pb);
+      for (int t = 0; t < Tacc; ++t) {
+        for (int i = 0; i < a.n_xsplit; ++i) {
+          mbar_wait(fullA + sa, pa);
+          tc_fence_after();
+          const uint64_t adesc = make_sw128_desc(smem_u32(sA + sa * A_BYTES));
+          // product terms a_i * w_j with i + j < n_wsplit (the dropped ones are below fp32 rounding)
+          for (int j = 0; j + i < a.n_wsplit; ++j) {
+            const uint64_t bdesc = make_sw128_desc(smem_u32(sB + (sb * MAX_WSPLIT + j) * L::B_BYTES));
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              const uint32_t acc = (kb > 0 || i > 0 || j > 0 || k > 0) ? 1u : 0u;
+              tc_mma_bf16(tmem_base + (uint32_t)(t * BLOCK_N), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2),
+                          idesc, acc);
+            }
+          }
+          tc_commit(emptyA + sa);  // frees the A slot once the MMAs above have read it
+          if (++sa == SA) sa = 0, pa ^= 1;
+        }
+      }
+      tc_commit(emptyB + sb);
+      if (++sb == SB) sb = 0, pb ^= 1;
+    }
+    tc_commit(accum_full);
+  } else if (warp >= 2) {
+    // ===================== epilogue: bias + LIF over t + store =====================
+    const int lg = warp & 3;                 // TMEM lane group this warp may read
+    const int m = lg * 32 + lane;            // pixel of the tile
+    const int nb = m / (a.TH * a.TW);
+    const int rem = m - nb * (a.TH * a.TW);
+    const int ph = rem / a.TW, pw = rem - ph * a.TW;
+    const int b = b0 + nb, ho = ho0 + ph, wo = wo0 + pw;
+    const bool valid = b < a.B && ho < a.Ho && wo < a.Wo;
+    const LifDyn d = make_lif(a.plif_w ? *a.plif_w : 0.0f, a.vth, a.hard_reset, a.vreset, a.decay_input);
+    const int64_t pix = ((int64_t)b * a.Ho + ho) * a.Wo + wo;          // within one time step
+    const int64_t step = (int64_t)a.B * a.Ho * a.Wo;                   // pixels per time step
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    for (int c16 = 0; c16 < BLOCK_N / 16; ++c16) {
+      const int ch0 = n0 + c16 * 16;
+      if (ch0 >= a.Cout) break;  // warp-uniform
+      uint32_t acc[TMAX][16];
+#pragma unroll
+      for (int t = 0; t < TMAX; ++t)
+        if (t < Tacc) tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(t * BLOCK_N + c16 * 16), acc[t]);
+      tmem_ld_wait();
+      if (!valid) continue;
+      const int nch = min(16, a.Cout - ch0);
+      if (a.out_mode == EAS_CONV_OUT_SPIKES) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = lif_v_init(d);
+        __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
+        for (int t = 0; t < a.T; ++t) {
+          float s[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float xin = 0.0f;
+#pragma unroll
+            for (int tt = 0; tt < TMAX; ++tt)
+              if (tt == (Tacc == 1 ? 0 : t)) xin = __uint_as_float(acc[tt][j]);
+            const float h = lif_charge(d, v[j], __fadd_rn(xin, sBias[c16 * 16 + j]));
+            s[j] = lif_fire(d, h);
+            v[j] = lif_reset(d, h, s[j]);
+          }
+          __nv_bfloat16* dst = outp + ((int64_t)t * step + pix) * a.out_ld + ch0;
+          if (nch == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            uint4 q0 = make_uint4(pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]), pack_bf16(s[4], s[5]),
+                                  pack_bf16(s[6], s[7]));
+            uint4 q1 = make_uint4(pack_bf16(s[8], s[9]), pack_bf16(s[10], s[11]), pack_bf16(s[12], s[13]),
+                                  pack_bf16(s[14], s[15]));
+            reinterpret_cast<uint4*>(dst)[0] = q0;
+            reinterpret_cast<uint4*>(dst)[1] = q1;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < nch) dst[j] = __float2bfloat16(s[j]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < TMAX; ++t) {
+          if (t < Tacc) {
+            if (a.out_mode == EAS_CONV_OUT_PREACT) {
+              float* dst = reinterpret_cast<float*>(a.out) + ((int64_t)t * step + pix) * a.out_ld + ch0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < nch) dst[j] = __fadd_rn(__uint_as_float(acc[t][j]), sBias[c16 * 16 + j]);
+            } else {  // SiLU, written as three bf16 planes whose sum is the fp32 value
+              __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
+              const int64_t plane = (int64_t)Tacc * step * a.out_ld;
+              __nv_bfloat16* dst = outp + ((int64_t)t * step + pix) * a.out_ld + ch0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (j < nch) {
+                  const float xv = __fadd_rn(__uint_as_float(acc[t][j]), sBias[c16 * 16 + j]);
+                  const float y = xv * eas_sigmoid(xv);
+                  const __nv_bfloat16 hi = __float2bfloat16(y);
+                  const float r1 = y - __bfloat162float(hi);
+                  const __nv_bfloat16 mid = __float2bfloat16(r1);
+                  const __nv_bfloat16 lo = __float2bfloat16(r1 - __bfloat162float(mid));
+                  dst[j] = hi, dst[plane + j] = mid, dst[2 * plane + j] = lo;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kCols) : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = []() -> PFN_cuTensorMapEncodeTiled_v12000 {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }();
+  return fn;
+}
+
+int check_conv(const eas_conv_cfg* c) {
+  EAS_REQUIRE(c, EAS_E_NULL);
+  EAS_REQUIRE(c->T >= 1 && c->T <= 8 && (c->Tx == c->T || c->Tx == 1), EAS_E_SHAPE);
+  EAS_REQUIRE(c->B >= 1 && c->H >= 1 && c->W >= 1 && c->Cin >= 8 && c->Cout >= 1, EAS_E_SHAPE);
+  EAS_REQUIRE(c->Cin % 8 == 0, EAS_E_SHAPE);  // TMA global strides are multiples of 16 B
+  EAS_REQUIRE((c->ksize == 1 || c->ksize == 3) && (c->stride == 1 || c->stride == 2), EAS_E_UNSUPPORTED);
+  EAS_REQUIRE(c->n_wsplit >= 1 && c->n_wsplit <= MAX_WSPLIT && c->n_xsplit >= 1 && c->n_xsplit <= 3, EAS_E_UNSUPPORTED);
+  EAS_REQUIRE(c->out_mode >= EAS_CONV_OUT_SPIKES && c->out_mode <= EAS_CONV_OUT_SILU3, EAS_E_UNSUPPORTED);
+  EAS_REQUIRE(c->x_ld == 0 || (c->x_ld >= c->Cin && c->x_ld % 8 == 0), EAS_E_SHAPE);
+  EAS_REQUIRE(c->out_ld == 0 || c->out_ld >= c->Cout, EAS_E_SHAPE);
+  return EAS_OK;
+}
+
+// M-tile decomposition: NB x TH x TW = 128 (powers of two) covering B x Ho x Wo with the least padding.
+void pick_tile(int B, int Ho, int Wo, int stride, int* NB, int* TH, int* TW) {
+  int64_t best = -1;
+  for (int tw = 1; tw <= 128; tw *= 2) {
+    if (tw * stride > 256) break;
+    for (int th = 1; th * tw <= 128; th *= 2) {
+      if (th * stride > 256) break;
+      const int nb = 128 / (tw * th);
+      const int64_t cost = eas_ceil_div(Wo, tw) * eas_ceil_div(Ho, th) * eas_ceil_div(B, nb);
+      // prefer wide rows on ties (longer contiguous TMA rows)
+      if (best < 0 || cost < best || (cost == best && tw > *TW)) best = cost, *NB = nb, *TH = th, *TW = tw;
+    }
+  }
+}
+
+template <int BLOCK_N, int TMAX>
+int launch_conv(const CUtensorMap& xmap, const CUtensorMap& wmap, const ConvArgs& a, int64_t grid, cudaStream_t st) {
+  using L = SmemLayout<BLOCK_N, TMAX>;
+  auto kern = conv_bn_plif_kernel<BLOCK_N, TMAX>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<(unsigned)grid, NUM_THREADS, L::TOTAL, st>>>(xmap, wmap, a);
+  EAS_LAUNCH_CHECK();
+  return EAS_OK;
+}
+
+}  // namespace
+
+extern "C" size_t eas_conv_bn_plif_ws_bytes(const eas_conv_cfg*) { return 0; }
+
+extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const void* w_planes, const float* bias,
+                                    const float* plif_w, void* out, void* /*ws*/, size_t /*ws_bytes*/, void* stream) {
+  int rc = check_conv(c);
+  if (rc) return rc;
+  EAS_REQUIRE(x && w_planes && bias && out, EAS_E_NULL);
+  EAS_REQUIRE(c->out_mode != EAS_CONV_OUT_SPIKES || plif_w, EAS_E_NULL);
+  EAS_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)w_planes % 16 == 0, EAS_E_ALIGN);
+  auto encode = get_encode_fn();
+  EAS_REQUIRE(encode != nullptr, EAS_E_UNSUPPORTED);
+
+  const int pad = (c->ksize - 1) / 2;
+  const int Ho = (c->H + 2 * pad - c->ksize) / c->stride + 1;
+  const int Wo = (c->W + 2 * pad - c->ksize) / c->stride + 1;
+  const int x_ld = c->x_ld ? c->x_ld : c->Cin;
+  const int out_ld = c->out_ld ? c->out_ld : c->Cout;
+  ConvArgs a{};
+  a.T = c->T, a.Tx = c->Tx, a.B = c->B, a.Ho = Ho, a.Wo = Wo, a.Cin = c->Cin, a.Cout = c->Cout;
+  a.ksize = c->ksize, a.stride = c->stride, a.pad = pad, a.n_wsplit = c->n_wsplit, a.n_xsplit = c->n_xsplit;
+  pick_tile(c->B, Ho, Wo, c->stride, &a.NB, &a.TH, &a.TW);
+  const int BLOCK_N = c->Cout <= 32 ? 32 : 64;
+  a.tiles_w = (int)eas_ceil_div(Wo, a.TW), a.tiles_h = (int)eas_ceil_div(Ho, a.TH);
+  a.tiles_b = (int)eas_ceil_div(c->B, a.NB), a.tiles_n = (int)eas_ceil_div(c->Cout, BLOCK_N);
+  a.out_ld = out_ld, a.out_mode = c->out_mode;
+  a.vth = c->v_threshold, a.vreset = c->v_reset, a.hard_reset = c->hard_reset, a.decay_input = c->decay_input;
+  a.bias = bias, a.plif_w = plif_w, a.out = out;
+  const int64_t grid = (int64_t)a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
+  EAS_REQUIRE(grid > 0 && grid < (1ll << 31), EAS_E_SHAPE);
+
+  // activations: [plane*Tx][B][H][W][x_ld] bf16, innermost first for the tensor map
+  CUtensorMap xmap, wmap;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)c->Cin, (cuuint64_t)c->W, (cuuint64_t)c->H, (cuuint64_t)c->B,
+                          (cuuint64_t)(c->n_xsplit * c->Tx)};
+    cuuint64_t strides[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)c->W * x_ld * 2, (cuuint64_t)c->H * c->W * x_ld * 2,
+                             (cuuint64_t)c->B * c->H * c->W * x_ld * 2};
+    cuuint32_t box[5] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(a.TW * c->stride), (cuuint32_t)(a.TH * c->stride),
+                         (cuuint32_t)a.NB, 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)c->stride, (cuuint32_t)c->stride, 1, 1};
+    CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return EAS_E_SHAPE;
+  }
+  {
+    const int taps = c->ksize * c->ksize;
+    cuuint64_t dims[3] = {(cuuint64_t)c->Cin, (cuuint64_t)taps, (cuuint64_t)(c->n_wsplit * c->Cout)};
+    cuuint64_t strides[2] = {(cuuint64_t)c->Cin * 2, (cuuint64_t)taps * c->Cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, 1, (cuuint32_t)BLOCK_N};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_planes), dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return EAS_E_SHAPE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Tacc = c->Tx;
+  if (BLOCK_N == 32) {
+    if (Tacc <= 1) return launch_conv<32, 1>(xmap, wmap, a, grid, st);
+    if (Tacc <= 4) return launch_conv<32, 4>(xmap, wmap, a, grid, st);
+    return launch_conv<32, 8>(xmap, wmap, a, grid, st);
+  }
+  if (Tacc <= 1) return launch_conv<64, 1>(xmap, wmap, a, grid, st);
+  if (Tacc <= 4) return launch_conv<64, 4>(xmap, wmap, a, grid, st);
+  return launch_conv<64, 8>(xmap, wmap, a, grid, st);
+}

@@ -8,7 +8,7 @@
 //   backward : read x, read g, write dx  (12 B per element-step in fp32); v is recomputed.
 // The charge step uses separate IEEE mul and add (__fmul_rn/__fadd_rn), like eager PyTorch, so the
 // potentials -- and therefore the spikes -- are bit-identical to the reference given identical x.
-#include "common.cuh"
+#include "lif.cuh"
 
 namespace {
 
@@ -42,35 +42,12 @@ __device__ __forceinline__ void store_vec(T* p, const float (&in)[V]) {
   }
 }
 
-struct Dyn {
-  float sw, k, vth, vr, vr_eff;
-  bool hard, decay_in;
-};
-
-__device__ __forceinline__ float charge(const Dyn& d, float v, float x) {
-  if (!d.decay_in) {
-    if (d.vr_eff == 0.0f) return __fadd_rn(__fmul_rn(v, d.k), x);
-    return __fadd_rn(__fsub_rn(v, __fmul_rn(__fsub_rn(v, d.vr_eff), d.sw)), x);
-  }
-  if (d.vr_eff == 0.0f) return __fadd_rn(v, __fmul_rn(__fsub_rn(x, v), d.sw));
-  return __fadd_rn(v, __fmul_rn(__fsub_rn(x, __fsub_rn(v, d.vr_eff)), d.sw));
-}
-__device__ __forceinline__ float fire(const Dyn& d, float h) { return __fsub_rn(h, d.vth) >= 0.0f ? 1.0f : 0.0f; }
-__device__ __forceinline__ float reset(const Dyn& d, float h, float s) {
-  if (d.hard) return s != 0.0f ? d.vr : h;
-  return __fsub_rn(h, __fmul_rn(s, d.vth));
-}
-
+using Dyn = LifDyn;
+__device__ __forceinline__ float charge(const Dyn& d, float v, float x) { return lif_charge(d, v, x); }
+__device__ __forceinline__ float fire(const Dyn& d, float h) { return lif_fire(d, h); }
+__device__ __forceinline__ float reset(const Dyn& d, float h, float s) { return lif_reset(d, h, s); }
 __device__ __forceinline__ Dyn make_dyn(const eas_plif_cfg& c, const float* w) {
-  Dyn d;
-  d.sw = eas_sigmoid(*w);
-  d.k = 1.0f - d.sw;
-  d.vth = c.v_threshold;
-  d.hard = c.hard_reset != 0;
-  d.vr = c.v_reset;
-  d.vr_eff = d.hard ? c.v_reset : 0.0f;
-  d.decay_in = c.decay_input != 0;
-  return d;
+  return make_lif(*w, c.v_threshold, c.hard_reset, c.v_reset, c.decay_input);
 }
 
 template <typename T, int V>

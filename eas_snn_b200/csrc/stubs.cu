@@ -6,8 +6,3 @@ extern "C" int eas_sampler_bwd(const eas_sampler_cfg*, const void*, const eas_sa
                                const float*, const float*, const eas_sampler_grads*, float*, void*, size_t, void*) {
   return EAS_E_UNSUPPORTED;
 }
-extern "C" size_t eas_conv_bn_plif_ws_bytes(const eas_conv_cfg*) { return 0; }
-extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg*, const void*, const void*, const float*, const float*, void*,
-                                    void*, size_t, void*) {
-  return EAS_E_UNSUPPORTED;
-}

@@ -1,0 +1,385 @@
+"""conv -> BatchNorm -> multi-step PLIF fused on the tensor cores, and the spiking CSPDarknet built
+from it.
+
+Drop-in seam: the reference turns every ``BaseConv`` into
+``SeqToANNContainer(Conv2d) -> layer.BatchNorm2d('m') -> ParametricLIFNode``
+(``yolox/utils/utils_snn.py:16-58``, ``yolox/models/network_blocks.py:31-56``).  :class:`FusedConvBNPLIF`
+keeps those three children and their state-dict keys (``conv.0.weight``, ``bn.*``, ``act.w``) but in
+eval mode runs ONE kernel (``eas_conv_bn_plif_fwd``): implicit-GEMM conv on tcgen05 with the BN
+folded into bf16-split weights (``yolox/utils/model_utils.py:61-75``) and the LIF recurrence over T in
+the epilogue, so neither the conv output nor the membrane potential reaches HBM.
+
+Activations between fused layers are channels-last bf16 ``[T, B, H, W, C]`` (spikes and SEW sums
+are small integers, exact in bf16).  :class:`SpikingCSPDarknet` is the reference topology
+(``yolox/models/darknet.py:97-180``) executed on that layout, with concatenations realised by
+writing conv outputs straight into channel slices of the concat buffer.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from .neuron import ATan, ParametricLIFNode
+
+OUT_SPIKES, OUT_PREACT, OUT_SILU3 = 0, 1, 2
+
+
+# ------------------------------------------------------------------------------------------------
+# functional layer
+# ------------------------------------------------------------------------------------------------
+def split_bf16(x: torch.Tensor, n: int) -> torch.Tensor:
+    """fp32 tensor -> ``[n, ...]`` bf16 planes whose (fp32) sum reproduces x to ~2^-(8n)."""
+    planes, r = [], x.float()
+    for _ in range(n):
+        p = r.to(torch.bfloat16)
+        planes.append(p)
+        r = r - p.float()
+    return torch.stack(planes)
+
+
+def fold_bn(conv_w: torch.Tensor, bn_w, bn_b, mean, var, eps: float):
+    """``fuse_conv_and_bn`` (yolox/utils/model_utils.py:61-75) in fp32: (w', shift)."""
+    scale = bn_w.float() / torch.sqrt(var.float() + eps)
+    return conv_w.float() * scale.view(-1, 1, 1, 1), bn_b.float() - mean.float() * scale
+
+
+def pack_weight(w_folded: torch.Tensor, n_wsplit: int) -> torch.Tensor:
+    """``[Cout, Cin, kh, kw]`` fp32 -> ``[n_wsplit, Cout, kh, kw, Cin]`` bf16 planes (K-major for TMA)."""
+    return split_bf16(w_folded.permute(0, 2, 3, 1).contiguous(), n_wsplit).contiguous()
+
+
+def conv_bn_plif(x: torch.Tensor, w_planes: torch.Tensor, bias: torch.Tensor, plif_w: torch.Tensor | None,
+                 T: int, ksize: int, stride: int, n_xsplit: int = 1, out: torch.Tensor | None = None,
+                 out_mode: int = OUT_SPIKES, v_threshold: float = 1.0, v_reset: float | None = None,
+                 decay_input: bool = False) -> torch.Tensor:
+    """One fused layer.
+
+    x        : channels-last bf16 ``[Tx, B, H, W, Cin]`` (``[n_xsplit, Tx, B, H, W, Cin]`` for split
+               real-valued input); may be a channel slice of a wider buffer (pixel stride ``x_ld``).
+    w_planes : ``[n_wsplit, Cout, k, k, Cin]`` bf16 (:func:`pack_weight`), bias ``[Cout]`` fp32.
+    out      : optional destination view ``[T, B, Ho, Wo, Cout]`` (channel slice of a concat buffer).
+    Returns spikes ``[T, B, Ho, Wo, Cout]`` bf16 (or the fp32 pre-activation / 3 SiLU planes).
+    """
+    _lib.require_cuda(x, w_planes, bias)
+    if x.dtype != torch.bfloat16 or w_planes.dtype != torch.bfloat16:
+        raise TypeError("conv_bn_plif expects bf16 activations and weight planes")
+    xs = x if n_xsplit > 1 or x.dim() == 6 else x.unsqueeze(0)
+    if xs.dim() != 6 or xs.shape[0] != n_xsplit:
+        raise ValueError("x must be [Tx,B,H,W,C] or [n_xsplit,Tx,B,H,W,C]")
+    _, Tx, B, H, W, Cin = xs.shape
+    x_ld = xs.stride(-2) if W > 1 else Cin
+    if W == 1 and H > 1:
+        x_ld = xs.stride(-3)
+    want = (Tx * B * H * W * x_ld, B * H * W * x_ld, H * W * x_ld, W * x_ld, x_ld, 1)
+    if x_ld < Cin or any(d > 1 and s_ != w_ for s_, w_, d in zip(xs.stride(), want, xs.shape)):
+        raise ValueError("x must be a dense channels-last tensor or a channel slice of one "
+                         "(shape %s, strides %s)" % (tuple(xs.shape), tuple(xs.stride())))
+    n_wsplit, Cout, kh, kw, Cin_w = w_planes.shape
+    if Cin_w != Cin or kh != ksize or kw != ksize:
+        raise ValueError("weight planes do not match the input")
+    pad = (ksize - 1) // 2
+    Ho = (H + 2 * pad - ksize) // stride + 1
+    Wo = (W + 2 * pad - ksize) // stride + 1
+    dev = x.device
+    To = T if out_mode == OUT_SPIKES else Tx
+    if out is None:
+        if out_mode == OUT_SPIKES:
+            out = torch.empty((To, B, Ho, Wo, Cout), dtype=torch.bfloat16, device=dev)
+        elif out_mode == OUT_PREACT:
+            out = torch.empty((To, B, Ho, Wo, Cout), dtype=torch.float32, device=dev)
+        else:
+            out = torch.empty((3, To, B, Ho, Wo, Cout), dtype=torch.bfloat16, device=dev)
+    oshape = tuple(out.shape[-5:])
+    if oshape != (To, B, Ho, Wo, Cout) or (Cout > 1 and out.stride(-1) != 1):
+        raise ValueError("out has the wrong shape %s, expected %s" % (oshape, (To, B, Ho, Wo, Cout)))
+    out_ld = out.stride(-2) if Wo > 1 else (out.stride(-3) if Ho > 1 else max(Cout, out.stride(-4) // max(1, Ho * Wo)))
+    owant = (B * Ho * Wo * out_ld, Ho * Wo * out_ld, Wo * out_ld, out_ld, 1)
+    if out_ld < Cout or any(d > 1 and s_ != w_ for s_, w_, d in zip(out.stride()[-5:], owant, oshape)):
+        raise ValueError("out must be a dense channels-last tensor or a channel slice of one")
+    cfg = _lib.ConvCfg(T=T, Tx=Tx, B=B, H=H, W=W, Cin=Cin, Cout=Cout, ksize=ksize, stride=stride,
+                       n_wsplit=n_wsplit, n_xsplit=n_xsplit, v_threshold=float(v_threshold),
+                       hard_reset=0 if v_reset is None else 1, v_reset=0.0 if v_reset is None else float(v_reset),
+                       decay_input=int(bool(decay_input)), out_mode=out_mode, x_ld=x_ld, out_ld=out_ld)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        rc = L.eas_conv_bn_plif_fwd(C.byref(cfg), _lib.ptr(xs), _lib.ptr(w_planes), _lib.ptr(bias),
+                                    _lib.ptr(plif_w), _lib.ptr(out), None, 0, _lib.stream_ptr())
+    _lib.check(rc, "eas_conv_bn_plif_fwd")
+    return out
+
+
+def to_channels_last_bf16(x_seq: torch.Tensor) -> torch.Tensor:
+    """``[T, B, C, H, W]`` (any strides / float dtype) -> ``[T, B, H, W, C]`` bf16 contiguous.
+    Free when x_seq is already a permuted view of such a buffer (what the fused layers return)."""
+    y = x_seq.permute(0, 1, 3, 4, 2)
+    if y.dtype != torch.bfloat16:
+        y = y.to(torch.bfloat16)
+    return y.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# module with the reference's children / state-dict keys
+# ------------------------------------------------------------------------------------------------
+class SeqToANNContainer(nn.Sequential):
+    """``spikingjelly.activation_based.layer.SeqToANNContainer``: flatten [T, B] -> apply -> restore."""
+
+    def forward(self, x_seq):
+        y = super().forward(x_seq.flatten(0, 1))
+        return y.view([x_seq.shape[0], x_seq.shape[1]] + list(y.shape[1:]))
+
+
+class MultiStepBatchNorm2d(nn.BatchNorm2d):
+    """``layer.BatchNorm2d(..., step_mode='m')``: statistics over the flattened T*B batch."""
+    step_mode = "m"
+
+    def forward(self, x):
+        if x.dim() != 5:
+            raise ValueError("expected [T, N, C, H, W]")
+        y = super().forward(x.flatten(0, 1))
+        return y.view([x.shape[0], x.shape[1]] + list(y.shape[1:]))
+
+
+class FusedConvBNPLIF(nn.Module):
+    """``BaseConv`` after ``convert_to_spiking`` (network_blocks.py:31-56, utils_snn.py:25-53)."""
+
+    def __init__(self, in_channels, out_channels, ksize, stride, spike_fn=None, n_wsplit: int = 3,
+                 eps: float = 1e-3, momentum: float = 0.03):
+        super().__init__()
+        self.conv = SeqToANNContainer(nn.Conv2d(in_channels, out_channels, ksize, stride, (ksize - 1) // 2,
+                                                bias=False))
+        self.bn = MultiStepBatchNorm2d(out_channels, eps=eps, momentum=momentum)
+        self.act = ParametricLIFNode(init_tau=2.0, decay_input=False, v_threshold=1.0, v_reset=None,
+                                     surrogate_function=copy.deepcopy(spike_fn) if spike_fn is not None else ATan(2.0),
+                                     detach_reset=False, step_mode="m", backend="torch")
+        self.ksize, self.stride, self.n_wsplit = ksize, stride, n_wsplit
+        self.assume_integer_input = False   # set True when the input is known to be spikes / SEW sums
+        self._cache = None
+
+    @classmethod
+    def from_modules(cls, conv: nn.Conv2d, bn: nn.BatchNorm2d, act=None, spike_fn=None, n_wsplit: int = 3):
+        if conv.groups != 1 or conv.bias is not None or conv.kernel_size[0] != conv.kernel_size[1]:
+            raise NotImplementedError("fused layer covers the reference's BaseConv: square, groups=1, no bias")
+        m = cls(conv.in_channels, conv.out_channels, conv.kernel_size[0], conv.stride[0], spike_fn=spike_fn,
+                n_wsplit=n_wsplit, eps=bn.eps, momentum=bn.momentum)
+        m.conv[0].load_state_dict(conv.state_dict())
+        m.bn.load_state_dict(bn.state_dict())
+        if isinstance(act, ParametricLIFNode):
+            m.act = act
+        return m.to(conv.weight.device)
+
+    # -- folded / split weights, rebuilt when any source tensor changes --------------------------
+    def _sources(self):
+        return (self.conv[0].weight, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var)
+
+    def packed(self):
+        key = tuple((t.data_ptr(), t._version) for t in self._sources()) + (self.n_wsplit,)
+        if self._cache is None or self._cache[0] != key:
+            with torch.no_grad():
+                w, shift = fold_bn(self.conv[0].weight, self.bn.weight, self.bn.bias, self.bn.running_mean,
+                                   self.bn.running_var, self.bn.eps)
+                self._cache = (key, pack_weight(w, self.n_wsplit), shift.contiguous())
+        return self._cache[1], self._cache[2]
+
+    # -- channels-last fast path (used by SpikingCSPDarknet) -------------------------------------
+    def run(self, x_cl: torch.Tensor, T: int, out: torch.Tensor | None = None, n_xsplit: int = 1) -> torch.Tensor:
+        wp, shift = self.packed()
+        a = self.act
+        return conv_bn_plif(x_cl, wp, shift, a.w.detach().float(), T, self.ksize, self.stride, n_xsplit=n_xsplit,
+                            out=out, out_mode=OUT_SPIKES, v_threshold=a.v_threshold, v_reset=a.v_reset,
+                            decay_input=a.decay_input)
+
+    # -- reference-shaped forward: [T, B, C, H, W] in, [T, B, C', H', W'] out -----------------------
+    def forward(self, x_seq: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            # training keeps batch statistics and autograd: conv and BN through PyTorch, the neuron
+            # (forward and surrogate backward) through the fused PLIF kernels
+            return self.act(self.bn(self.conv(x_seq)))
+        T = x_seq.shape[0]
+        x_cl = x_seq.permute(0, 1, 3, 4, 2)
+        if x_seq.dtype == torch.bfloat16 or self.assume_integer_input:
+            y = self.run(x_cl.to(torch.bfloat16).contiguous(), T)
+        else:  # real-valued input (e.g. the SiLU stem output): split it so the product stays fp32-accurate
+            y = self.run(split_bf16(x_cl.contiguous(), 3), T, n_xsplit=3)
+        self.act.reset()                                   # stateless: the reference resets per batch
+        return y.permute(0, 1, 4, 2, 3).to(x_seq.dtype)    # logical [T, B, C, H, W], channels-last memory
+
+
+# ------------------------------------------------------------------------------------------------
+# the spiking CSPDarknet on channels-last buffers
+# ------------------------------------------------------------------------------------------------
+class _AnnStemConv(nn.Module):
+    """The stem's inner ``BaseConv`` (conv -> BN -> SiLU); the reference keeps it ANN (utils_snn.py:23-24)."""
+
+    def __init__(self, cin, cout, k):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, 1, (k - 1) // 2, bias=False)
+        self.bn = nn.BatchNorm2d(cout, eps=1e-3, momentum=0.03)
+        self.act = nn.SiLU()
+        self._cache = None
+
+    def packed(self):
+        src = (self.conv.weight, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var)
+        key = tuple((t.data_ptr(), t._version) for t in src)
+        if self._cache is None or self._cache[0] != key:
+            with torch.no_grad():
+                w, shift = fold_bn(self.conv.weight, self.bn.weight, self.bn.bias, self.bn.running_mean,
+                                   self.bn.running_var, self.bn.eps)
+                self._cache = (key, pack_weight(w, 3), shift.contiguous())
+        return self._cache[1], self._cache[2]
+
+
+class _Focus(nn.Module):
+    def __init__(self, cin, cout, k):
+        super().__init__()
+        self.conv = _AnnStemConv(cin * 4, cout, k)
+
+    def run(self, frames: torch.Tensor) -> torch.Tensor:
+        """frames ``[Tx, B, C, H, W]`` fp32 -> SiLU(BN(conv(space_to_depth))) as 3 bf16 planes
+        ``[3, Tx, B, H/2, W/2, cout]`` (network_blocks.py:191-213)."""
+        a, b = frames[..., ::2, ::2], frames[..., 1::2, ::2]
+        c, d = frames[..., ::2, 1::2], frames[..., 1::2, 1::2]
+        x = torch.cat((a, b, c, d), dim=2).permute(0, 1, 3, 4, 2).contiguous()      # channels-last fp32
+        wp, shift = self.conv.packed()
+        return conv_bn_plif(split_bf16(x, 3), wp, shift, None, x.shape[0], 3, 1, n_xsplit=3, out_mode=OUT_SILU3)
+
+
+class _Bottleneck(nn.Module):
+    def __init__(self, cin, cout, shortcut, expansion, spike_fn):
+        super().__init__()
+        hid = int(cout * expansion)
+        self.conv1 = FusedConvBNPLIF(cin, hid, 1, 1, spike_fn)
+        self.conv2 = FusedConvBNPLIF(hid, cout, 3, 1, spike_fn)
+        self.use_add = shortcut and cin == cout
+
+    def run(self, x, T, out=None):
+        if not self.use_add:
+            return self.conv2.run(self.conv1.run(x, T), T, out=out)
+        y = self.conv2.run(self.conv1.run(x, T), T)
+        if out is None:
+            return y + x                              # SEW add (network_blocks.py:99-103): values {0,1,2,..}
+        torch.add(y, x, out=out)
+        return out
+
+
+class _SPP(nn.Module):
+    def __init__(self, cin, cout, spike_fn, ks=(5, 9, 13)):
+        super().__init__()
+        hid = cin // 2
+        self.ks = ks
+        self.conv1 = FusedConvBNPLIF(cin, hid, 1, 1, spike_fn)
+        self.m = nn.ModuleList([SeqToANNContainer(nn.MaxPool2d(k, 1, k // 2)) for k in ks])
+        self.conv2 = FusedConvBNPLIF(hid * (len(ks) + 1), cout, 1, 1, spike_fn)
+
+    def run(self, x, T):
+        Tn, B, H, W, _ = x.shape
+        hid = self.conv1.conv[0].out_channels
+        cat = torch.empty((T, B, H, W, hid * (len(self.ks) + 1)), dtype=torch.bfloat16, device=x.device)
+        y = self.conv1.run(x, T, out=cat[..., :hid])
+        y4 = y.flatten(0, 1).permute(0, 3, 1, 2)       # [T*B, C, H, W] view, channels-last memory
+        for i, k in enumerate(self.ks):
+            p = F.max_pool2d(y4, k, 1, k // 2)
+            cat[..., (i + 1) * hid:(i + 2) * hid].copy_(p.permute(0, 2, 3, 1).reshape(T, B, H, W, hid))
+        return self.conv2.run(cat, T)
+
+
+class _CSPLayer(nn.Module):
+    def __init__(self, cin, cout, n, shortcut, spike_fn):
+        super().__init__()
+        hid = int(cout * 0.5)
+        self.conv1 = FusedConvBNPLIF(cin, hid, 1, 1, spike_fn)
+        self.conv2 = FusedConvBNPLIF(cin, hid, 1, 1, spike_fn)
+        self.conv3 = FusedConvBNPLIF(2 * hid, cout, 1, 1, spike_fn)
+        self.m = nn.Sequential(*[_Bottleneck(hid, hid, shortcut, 1.0, spike_fn) for _ in range(n)])
+
+    def run(self, x, T):
+        Tn, B, H, W, _ = x.shape
+        hid = self.conv1.conv[0].out_channels
+        cat = torch.empty((T, B, H, W, 2 * hid), dtype=torch.bfloat16, device=x.device)
+        self.conv2.run(x, T, out=cat[..., hid:])
+        y = self.conv1.run(x, T)
+        blocks = list(self.m)
+        for i, blk in enumerate(blocks):
+            y = blk.run(y, T, out=cat[..., :hid] if i == len(blocks) - 1 else None)
+        return self.conv3.run(cat, T)
+
+
+class SpikingCSPDarknet(nn.Module):
+    """Spiking CSPDarknet (darknet.py:97-180 after convert_to_spiking), inference, channels-last.
+
+    ``forward(frames)``: ``frames`` is the sampler output ``[Ts or T, B, 2, H, W]`` fp32; a single
+    frame (Ts == 1) is broadcast over the T SNN steps as ``SpikingYOLOX.forward`` does
+    (spiking_yolox.py:54-55) -- here without materialising the copies: the stem and the first
+    spiking conv are computed once and only the neuron runs T times.
+    Returns ``{dark3, dark4, dark5}`` spike tensors as logical ``[T, B, C, H, W]`` views.
+    """
+
+    def __init__(self, dep_mul, wid_mul, in_dim=2, spike_fn=None, T=3, out_features=("dark3", "dark4", "dark5")):
+        super().__init__()
+        spike_fn = spike_fn if spike_fn is not None else ATan(2.0)
+        c = int(wid_mul * 64)
+        d = max(round(dep_mul * 3), 1)
+        self.T = T
+        self.out_features = out_features
+        self.stem = SeqToANNContainer(_Focus(in_dim, c, 3))
+        self.dark2 = nn.Sequential(FusedConvBNPLIF(c, c * 2, 3, 2, spike_fn), _CSPLayer(c * 2, c * 2, d, True, spike_fn))
+        self.dark3 = nn.Sequential(FusedConvBNPLIF(c * 2, c * 4, 3, 2, spike_fn),
+                                   _CSPLayer(c * 4, c * 4, d * 3, True, spike_fn))
+        self.dark4 = nn.Sequential(FusedConvBNPLIF(c * 4, c * 8, 3, 2, spike_fn),
+                                   _CSPLayer(c * 8, c * 8, d * 3, True, spike_fn))
+        self.dark5 = nn.Sequential(FusedConvBNPLIF(c * 8, c * 16, 3, 2, spike_fn), _SPP(c * 16, c * 16, spike_fn),
+                                   _CSPLayer(c * 16, c * 16, d, False, spike_fn))
+
+    @torch.no_grad()
+    def forward(self, frames: torch.Tensor, return_all: bool = False):
+        if self.training:
+            raise RuntimeError("SpikingCSPDarknet (fused) is the inference path; call .eval()")
+        _lib.require_cuda(frames)
+        T = self.T
+        if frames.shape[0] not in (1, T):
+            raise ValueError("the timestep of SNN is not matched with that of input")   # spiking_yolox.py:57
+        stem3 = self.stem[0].run(frames.float())                     # [3, Tx, B, H/2, W/2, c] bf16 planes
+        x = self.dark2[0].run(stem3, T, n_xsplit=3)                   # first spiking conv: real-valued input
+        outs = {}
+        x = self.dark2[1].run(x, T)
+        outs["dark2"] = x
+        for name in ("dark3", "dark4", "dark5"):
+            seq = getattr(self, name)
+            x = seq[0].run(x, T)
+            for blk in list(seq)[1:]:
+                x = blk.run(x, T)
+            outs[name] = x
+        keys = outs.keys() if return_all else self.out_features
+        return {k: outs[k].permute(0, 1, 4, 2, 3) for k in keys}
+
+
+def convert_to_spiking(model: nn.Module, spike_fn, fuse: bool = True, n_wsplit: int = 3) -> nn.Module:
+    """``yolox/utils/utils_snn.py:16-58`` with the fused layer: every child that looks like the
+    reference's ``BaseConv`` (``.conv`` Conv2d, ``.bn`` BatchNorm2d, ``.act``) becomes a
+    :class:`FusedConvBNPLIF` (same keys); ``Focus`` is wrapped whole and stays ANN; lone Conv2d /
+    Upsample / MaxPool2d are wrapped; remaining activations become :class:`ParametricLIFNode`."""
+    for name, module in model.named_children():
+        cname = type(module).__name__
+        if cname == "Focus":
+            setattr(model, name, SeqToANNContainer(module))
+        elif fuse and isinstance(getattr(module, "conv", None), nn.Conv2d) and \
+                isinstance(getattr(module, "bn", None), nn.BatchNorm2d) and hasattr(module, "act") and \
+                module.conv.groups == 1:
+            setattr(model, name, FusedConvBNPLIF.from_modules(module.conv, module.bn, spike_fn=spike_fn,
+                                                              n_wsplit=n_wsplit))
+        elif isinstance(module, (nn.Conv2d, nn.Upsample, nn.MaxPool2d)):
+            setattr(model, name, SeqToANNContainer(module))
+        elif isinstance(module, nn.BatchNorm2d):
+            bn = MultiStepBatchNorm2d(module.num_features, module.eps, module.momentum)
+            setattr(model, name, bn)
+        elif name.endswith("act") or isinstance(module, (nn.ReLU, nn.SiLU, nn.LeakyReLU)):
+            setattr(model, name, ParametricLIFNode(init_tau=2.0, decay_input=False, v_threshold=1.0, v_reset=None,
+                                                   surrogate_function=copy.deepcopy(spike_fn), detach_reset=False,
+                                                   step_mode="m", backend="torch"))
+        else:
+            convert_to_spiking(module, spike_fn, fuse=fuse, n_wsplit=n_wsplit)
+    return model

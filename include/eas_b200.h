@@ -166,8 +166,19 @@ typedef struct {
   int32_t hard_reset;
   float v_reset;
   int32_t decay_input;
-  int32_t out_mode;     /* 0: spikes bf16; 1: pre-activation f32 (debug / non-spiking) */
+  int32_t out_mode;     /* EAS_CONV_OUT_* */
+  int32_t x_ld;         /* channels per pixel of the input buffer (>= Cin; 0 = Cin): lets the input be
+                           a channel slice of a wider concat buffer */
+  int32_t out_ld;       /* channels per pixel of the output buffer (>= Cout; 0 = Cout): lets the
+                           output land in a channel slice of a concat buffer (CSPLayer / SPP cat) */
 } eas_conv_cfg;
+
+enum {
+  EAS_CONV_OUT_SPIKES = 0, /* bf16 spikes [T][B][Ho][Wo][out_ld]                                  */
+  EAS_CONV_OUT_PREACT = 1, /* f32 conv + bias [Tx][B][Ho][Wo][out_ld] (no neuron)                 */
+  EAS_CONV_OUT_SILU3 = 2   /* SiLU(conv + bias) as 3 bf16 planes hi/mid/lo [3][Tx][B][Ho][Wo][out_ld]
+                              (the ANN stem, network_blocks.py:191-213, feeding a spiking conv)   */
+};
 
 size_t eas_conv_bn_plif_ws_bytes(const eas_conv_cfg* cfg);
 int eas_conv_bn_plif_fwd(const eas_conv_cfg* cfg, const void* x, const void* w_planes,

@@ -1,0 +1,150 @@
+"""GPU parity: the tcgen05 conv -> folded BN -> PLIF kernel (through the C ABI) against fp32 PyTorch
+convolution (pre-activation mode) and against the oracle's conv -> BN -> PLIF (spike mode), and the
+whole fused spiking CSPDarknet against the golden vector produced by the reference model."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import eas_snn_b200 as eas
+from eas_snn_b200 import fused
+from oracle import backbone as ob, plif as op
+from helpers import load_golden, close_report
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_conv(x_cl, w, stride):
+    """x_cl [Tx,B,H,W,C] fp32 (exact values), w [Cout,Cin,k,k] fp32 -> [Tx,B,Ho,Wo,Cout] fp64-accumulated."""
+    Tx, B, H, W, C = x_cl.shape
+    k = w.shape[-1]
+    y = F.conv2d(x_cl.flatten(0, 1).permute(0, 3, 1, 2).double(), w.double(), None, stride, (k - 1) // 2)
+    return y.permute(0, 2, 3, 1).reshape(Tx, B, y.shape[2], y.shape[3], -1)
+
+
+SHAPES = [
+    # Tx, B, H,  W,  Cin, Cout, k, stride
+    (1, 1, 8, 16, 64, 64, 1, 1),       # exactly one 128 x 64 x 64 tile
+    (1, 2, 16, 24, 64, 64, 1, 1),      # several M tiles
+    (3, 2, 16, 24, 128, 96, 1, 1),     # 2 K blocks, N tail
+    (1, 1, 16, 16, 64, 64, 3, 1),      # 3x3 taps + zero padding by TMA
+    (3, 2, 20, 28, 48, 80, 3, 1),      # Cin < 64 (channel OOB fill), ragged tiles
+    (3, 2, 32, 40, 32, 64, 3, 2),      # stride 2 through tensor-map element strides
+    (3, 4, 8, 10, 192, 192, 3, 1),     # small map: several images per tile
+    (2, 3, 5, 7, 16, 24, 1, 1),        # tiny, everything ragged
+    (3, 2, 16, 20, 8, 16, 3, 2),       # Cin = 8 (the golden backbone's first layers)
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_preact_matches_fp32_conv(cuda, shape):
+    Tx, B, H, W, Cin, Cout, k, stride = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randint(0, 3, (Tx, B, H, W, Cin), generator=g).float()           # spikes / SEW sums
+    w = torch.randn((Cout, Cin, k, k), generator=g) / (Cin * k * k) ** 0.5
+    bias = torch.randn(Cout, generator=g)
+    want = _ref_conv(x, w, stride) + bias.double()
+    wp = fused.pack_weight(w.to(cuda), 3)
+    got = fused.conv_bn_plif(x.to(cuda).bfloat16(), wp, bias.to(cuda), None, Tx, k, stride, out_mode=fused.OUT_PREACT)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    # tcgen05 accumulates in fp32 with truncation: the error grows ~1.6e-8 * K (K = taps * Cin); the bf16x3
+    # weight split itself is exact to 2^-24.  (cuDNN's default TF32 path is ~1e-3 on the same data.)
+    K = Cin * k * k
+    ok, msg = close_report(got, want, rtol=1e-6, atol=2e-6 + 2.5e-8 * K)
+    print("preact %s: %s" % (shape, msg))
+    assert ok, "%s: %s" % (shape, msg)
+
+
+def test_single_plane_is_bf16_accurate(cuda):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randint(0, 2, (1, 1, 16, 16, 64), generator=g).float()
+    w = torch.randn((64, 64, 3, 3), generator=g) / 24.0
+    bias = torch.zeros(64)
+    got = fused.conv_bn_plif(x.to(cuda).bfloat16(), fused.pack_weight(w.to(cuda), 1), bias.to(cuda), None, 1, 3, 1,
+                             out_mode=fused.OUT_PREACT)
+    want = _ref_conv(x, w.bfloat16().float(), 1)
+    ok, msg = close_report(got, want, rtol=1e-5, atol=1e-5)
+    assert ok, msg
+
+
+def test_real_valued_input_split(cuda):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn((1, 2, 12, 20, 8), generator=g)
+    w = torch.randn((32, 8, 3, 3), generator=g) / 8.0
+    bias = torch.randn(32, generator=g) * 0.1
+    want = _ref_conv(x, w, 1) + bias.double()
+    got = fused.conv_bn_plif(fused.split_bf16(x.to(cuda), 3), fused.pack_weight(w.to(cuda), 3), bias.to(cuda), None,
+                             1, 3, 1, n_xsplit=3, out_mode=fused.OUT_PREACT)
+    ok, msg = close_report(got, want, rtol=3e-6, atol=3e-6)
+    assert ok, msg
+    # SiLU planes sum back to the fp32 activation
+    planes = fused.conv_bn_plif(fused.split_bf16(x.to(cuda), 3), fused.pack_weight(w.to(cuda), 3), bias.to(cuda),
+                                None, 1, 3, 1, n_xsplit=3, out_mode=fused.OUT_SILU3)
+    silu = F.silu(want).float()
+    ok, msg = close_report(planes.float().sum(0), silu, rtol=1e-5, atol=1e-5)
+    assert ok, msg
+
+
+@pytest.mark.parametrize("cfg", [(64, 64, 1, 1, 3), (32, 64, 3, 2, 3), (96, 48, 3, 1, 3), (64, 64, 1, 1, 1)])
+def test_layer_vs_oracle_conv_bn_plif(cuda, cfg):
+    """Teacher-forced single layer: identical spike input, conv -> BN(eval) -> PLIF oracle vs the fused kernel."""
+    Cin, Cout, k, stride, T = cfg
+    torch.manual_seed(Cin + Cout + k)
+    ref = ob.SpikingBaseConv(Cin, Cout, k, stride, op.ATan(2.0))
+    x = (torch.rand(3, 2, Cin, 24, 32) < 0.2).float()
+    x = x + (torch.rand_like(x) < 0.05).float()                       # a few 2s (SEW sums)
+    ob.calibrate_bn(ref, x)
+    ref.act.w.data.fill_(0.3)
+    with torch.no_grad():
+        want = ref(x)
+    rate = want.mean().item()
+    assert 0.02 < rate < 0.9, rate
+    m = fused.FusedConvBNPLIF(Cin, Cout, k, stride, eas.ATan(2.0)).to(cuda)
+    m.load_state_dict(ref.state_dict())
+    m.eval()
+    with torch.no_grad():
+        got_cl = m.run(x.to(cuda).permute(0, 1, 3, 4, 2).contiguous().bfloat16(), 3)
+        got = got_cl.permute(0, 1, 4, 2, 3).float().cpu()
+        got_mod = m(x.to(cuda))                                        # drop-in [T,B,C,H,W] fp32 path
+    mism = (got != want).float().mean().item()
+    print("layer %s: spike mismatch %.3e (rate %.3f)" % (cfg, mism, rate))
+    assert mism <= 1e-4, "spike mismatch %.3e (rate %.3f)" % (mism, rate)
+    assert got_mod.dtype == torch.float32 and got_mod.shape == want.shape
+    assert (got_mod.cpu() != want).float().mean().item() <= 1e-4
+
+
+def test_output_into_concat_slice(cuda):
+    g = torch.Generator().manual_seed(4)
+    x = torch.randint(0, 2, (2, 1, 8, 16, 64), generator=g).float().to(cuda).bfloat16()
+    w = fused.pack_weight((torch.randn((32, 64, 1, 1), generator=g) / 8).to(cuda), 3)
+    bias = torch.randn(32, generator=g).to(cuda)
+    pw = torch.tensor(0.0, device=cuda)
+    cat = torch.full((2, 1, 8, 16, 96), 7.0, dtype=torch.bfloat16, device=cuda)
+    alone = fused.conv_bn_plif(x, w, bias, pw, 2, 1, 1)
+    fused.conv_bn_plif(x, w, bias, pw, 2, 1, 1, out=cat[..., 32:64])
+    assert torch.equal(cat[..., 32:64], alone)
+    assert bool((cat[..., :32] == 7).all()) and bool((cat[..., 64:] == 7).all())
+    # and a channel slice as INPUT
+    wide = torch.zeros((2, 1, 8, 16, 160), dtype=torch.bfloat16, device=cuda)
+    wide[..., 64:128] = x
+    assert torch.equal(fused.conv_bn_plif(wide[..., 64:128], w, bias, pw, 2, 1, 1), alone)
+
+
+def test_backbone_golden(cuda):
+    """Whole spiking CSPDarknet (tiny width) vs the golden spikes of the REFERENCE model."""
+    z = load_golden("backbone")
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    net = fused.SpikingCSPDarknet(0.33, 0.125, in_dim=2, spike_fn=eas.ATan(2.0), T=3).to(cuda)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    x = torch.from_numpy(z["x"]).to(cuda)
+    outs = net(x[:1])                                      # Ts == 1 frame, broadcast inside
+    outs_T = net(x)                                        # explicit T frames
+    for k in ("dark3", "dark4", "dark5"):
+        want = torch.from_numpy(z["out/" + k]).float()
+        got = outs[k].float().cpu()
+        mism = (got != want).float().mean().item()
+        print("backbone %s: spike mismatch %.3e (rate %.3f)" % (k, mism, want.mean().item()))
+        assert got.shape == want.shape
+        assert mism <= 2e-3, "%s mismatch %.3e (rate %.3f)" % (k, mism, want.mean().item())
+        assert torch.equal(outs_T[k].float().cpu(), got), k + ": broadcast path differs from explicit T frames"
