@@ -51,8 +51,7 @@ class _SamplerFn(torch.autograd.Function):
         plist = [iw0, ib0, iw1, ib1, gw0, gb0, gw1, gb1]
         plist = [None if q is None else q.detach().contiguous().float() for q in plist]
         wstruct = _pack_ptrs(plist)
-        need_grad = torch.is_grad_enabled() and any(q is not None and q.requires_grad for q in params)
-        need_grad = need_grad or (torch.is_grad_enabled() and events.requires_grad)
+        need_grad = any(ctx.needs_input_grad)   # grad mode is off inside Function.forward: ask the ctx
         dev = events.device
         out = torch.empty((mod.Ts, B, 2, H, W), dtype=torch.float32, device=dev)
         v_seq = gate_seq = None
