@@ -151,7 +151,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     model = make_cpu_model()
-    windows = 16   # bounded sample of the 64-window batch so K steps end within minutes
+    # bounded sample of the 64-window batch, sized so that K steps end within a couple of minutes
+    windows = max(2, min(16, 480 // max(1, args.steps)))
     sets = [synth.gen1_batch(windows, cfg=2, first_sample=s * BATCH) for s in range(NSETS)]
     for w in range(args.warmup):
         cpu_step(model, sets[w % NSETS])

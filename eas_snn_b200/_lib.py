@@ -40,7 +40,8 @@ class ConvCfg(C.Structure):
                 ("Cin", C.c_int32), ("Cout", C.c_int32), ("ksize", C.c_int32), ("stride", C.c_int32),
                 ("n_wsplit", C.c_int32), ("n_xsplit", C.c_int32), ("v_threshold", C.c_float),
                 ("hard_reset", C.c_int32), ("v_reset", C.c_float), ("decay_input", C.c_int32),
-                ("out_mode", C.c_int32), ("x_ld", C.c_int32), ("out_ld", C.c_int32)]
+                ("out_mode", C.c_int32), ("x_ld", C.c_int32), ("out_ld", C.c_int32), ("res_ld", C.c_int32),
+                ("residual", C.c_void_p)]
 
 
 # name -> (restype, argtypes); the single source the "exports every symbol" test walks.

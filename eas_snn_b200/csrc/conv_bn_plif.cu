@@ -28,10 +28,6 @@
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;               // bf16 elements = 128 B
-constexpr int A_BYTES = BLOCK_M * 128;    // 16 KB
-constexpr int SA = 3;                     // A ring depth (2 CTAs per SM: 2 x ~98 KB)
-constexpr int SB = 2;                     // B ring depth
 constexpr int MAX_WSPLIT = 3;
 constexpr int NUM_THREADS = 192;
 constexpr uint32_t SPIN_LIMIT = 1u << 27;  // watchdog: trap instead of hanging the GPU
@@ -41,7 +37,8 @@ struct ConvArgs {
   int n_wsplit, n_xsplit;
   int NB, TH, TW;
   int tiles_w, tiles_h, tiles_b, tiles_n;
-  int out_ld, out_mode;
+  int out_ld, out_mode, res_ld;
+  const __nv_bfloat16* residual;   // SEW shortcut added to the spikes (network_blocks.py:99-103) or null
   float vth, vreset;
   int hard_reset, decay_input;
   const float* bias;
@@ -101,13 +98,16 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// K-major, SWIZZLE_128B shared-memory operand descriptor (8-row groups 1024 B apart).
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+// K-major swizzled shared-memory operand descriptor.  One K block is one swizzle row of BK bf16
+// (128 / 64 / 32 B), 8-row groups are 8 rows apart (1024 / 512 / 256 B).
+template <int BK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
+  constexpr uint64_t layout = BK == 64 ? 2 : BK == 32 ? 4 : 6;  // SWIZZLE_128B / 64B / 32B
   uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address
-  d |= (uint64_t)(1024u >> 4) << 32;          // stride byte offset
-  d |= (uint64_t)1 << 46;                     // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                     // SWIZZLE_128B
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);       // start address
+  d |= (uint64_t)((8u * BK * 2u) >> 4) << 32;     // stride byte offset
+  d |= (uint64_t)1 << 46;                         // descriptor version (sm_100)
+  d |= layout << 61;
   return d;
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -124,21 +124,25 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-template <int BLOCK_N, int TMAX>
+template <int BLOCK_N, int BK>
 struct SmemLayout {
-  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int A_BYTES = BLOCK_M * BK * 2;
+  static constexpr int B_BYTES = BLOCK_N * BK * 2;
+  static constexpr int SA = (48 * 1024 / A_BYTES) > 8 ? 8 : (48 * 1024 / A_BYTES);  // A ring depth (<= 48 KB)
+  static constexpr int SB = BK == 64 ? 2 : 4;                                       // B ring depth
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + SA * A_BYTES;
   static constexpr int OFF_BAR = OFF_B + SB * MAX_WSPLIT * B_BYTES;
-  static constexpr int OFF_BIAS = OFF_BAR + 128;
+  static constexpr int OFF_BIAS = OFF_BAR + 256;
   static constexpr int TOTAL = OFF_BIAS + BLOCK_N * 4 + 1024;  // + slack for the 1024 B alignment
 };
 
-template <int BLOCK_N, int TMAX>
+template <int BLOCK_N, int TMAX, int BK>
 __global__ void __launch_bounds__(NUM_THREADS)
 conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
                     const ConvArgs a) {
-  using L = SmemLayout<BLOCK_N, TMAX>;
+  using L = SmemLayout<BLOCK_N, BK>;
+  constexpr int SA = L::SA, SB = L::SB, A_BYTES = L::A_BYTES, BLOCK_K = BK;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem + L::OFF_A;
@@ -226,10 +230,10 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         for (int i = 0; i < a.n_xsplit; ++i) {
           mbar_wait(fullA + sa, pa);
           tc_fence_after();
-          const uint64_t adesc = make_sw128_desc(smem_u32(sA + sa * A_BYTES));
+          const uint64_t adesc = make_kmajor_desc<BK>(smem_u32(sA + sa * A_BYTES));
           // product terms a_i * w_j with i + j < n_wsplit (the dropped ones are below fp32 rounding)
           for (int j = 0; j + i < a.n_wsplit; ++j) {
-            const uint64_t bdesc = make_sw128_desc(smem_u32(sB + (sb * MAX_WSPLIT + j) * L::B_BYTES));
+            const uint64_t bdesc = make_kmajor_desc<BK>(smem_u32(sB + (sb * MAX_WSPLIT + j) * L::B_BYTES));
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k) {
               const uint32_t acc = (kb > 0 || i > 0 || j > 0 || k > 0) ? 1u : 0u;
@@ -287,6 +291,20 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
             v[j] = lif_reset(d, h, s[j]);
           }
           __nv_bfloat16* dst = outp + ((int64_t)t * step + pix) * a.out_ld + ch0;
+          if (a.residual) {  // SEW add: y = spikes + x (small integers, exact in bf16)
+            const __nv_bfloat16* rp = a.residual + ((int64_t)t * step + pix) * a.res_ld + ch0;
+            if (nch == 16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+              const uint4 r0 = reinterpret_cast<const uint4*>(rp)[0], r1 = reinterpret_cast<const uint4*>(rp)[1];
+              const __nv_bfloat16* rb0 = reinterpret_cast<const __nv_bfloat16*>(&r0);
+              const __nv_bfloat16* rb1 = reinterpret_cast<const __nv_bfloat16*>(&r1);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) s[j] += __bfloat162float(rb0[j]), s[8 + j] += __bfloat162float(rb1[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < nch) s[j] += __bfloat162float(rp[j]);
+            }
+          }
           if (nch == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
             uint4 q0 = make_uint4(pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]), pack_bf16(s[4], s[5]),
                                   pack_bf16(s[6], s[7]));
@@ -362,6 +380,8 @@ int check_conv(const eas_conv_cfg* c) {
   EAS_REQUIRE(c->out_mode >= EAS_CONV_OUT_SPIKES && c->out_mode <= EAS_CONV_OUT_SILU3, EAS_E_UNSUPPORTED);
   EAS_REQUIRE(c->x_ld == 0 || (c->x_ld >= c->Cin && c->x_ld % 8 == 0), EAS_E_SHAPE);
   EAS_REQUIRE(c->out_ld == 0 || c->out_ld >= c->Cout, EAS_E_SHAPE);
+  EAS_REQUIRE(c->res_ld == 0 || c->res_ld >= c->Cout, EAS_E_SHAPE);
+  EAS_REQUIRE(!c->residual || c->out_mode == EAS_CONV_OUT_SPIKES, EAS_E_UNSUPPORTED);
   return EAS_OK;
 }
 
@@ -380,15 +400,35 @@ void pick_tile(int B, int Ho, int Wo, int stride, int* NB, int* TH, int* TW) {
   }
 }
 
-template <int BLOCK_N, int TMAX>
+template <int BLOCK_N, int TMAX, int BK>
 int launch_conv(const CUtensorMap& xmap, const CUtensorMap& wmap, const ConvArgs& a, int64_t grid, cudaStream_t st) {
-  using L = SmemLayout<BLOCK_N, TMAX>;
-  auto kern = conv_bn_plif_kernel<BLOCK_N, TMAX>;
+  using L = SmemLayout<BLOCK_N, BK>;
+  auto kern = conv_bn_plif_kernel<BLOCK_N, TMAX, BK>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
   if (e != cudaSuccess) return (int)e;
   kern<<<(unsigned)grid, NUM_THREADS, L::TOTAL, st>>>(xmap, wmap, a);
   EAS_LAUNCH_CHECK();
   return EAS_OK;
+}
+
+template <int BLOCK_N, int BK>
+int launch_conv_t(int Tacc, const CUtensorMap& xmap, const CUtensorMap& wmap, const ConvArgs& a, int64_t grid,
+                  cudaStream_t st) {
+  if (Tacc <= 1) return launch_conv<BLOCK_N, 1, BK>(xmap, wmap, a, grid, st);
+  if (Tacc <= 4 || BLOCK_N == 128) return launch_conv<BLOCK_N, 4, BK>(xmap, wmap, a, grid, st);
+  if constexpr (BLOCK_N <= 64) return launch_conv<BLOCK_N, 8, BK>(xmap, wmap, a, grid, st);
+  return EAS_E_UNSUPPORTED;
+}
+
+// K block = one swizzle row of 64 / 32 / 16 channels: least padded K plus a per-block overhead.
+int pick_bk(int Cin) {
+  int best = 64, best_cost = 1 << 30;
+  for (int bk : {64, 32, 16}) {
+    const int nb = (Cin + bk - 1) / bk;
+    const int cost = nb * bk + 8 * nb;
+    if (cost < best_cost) best_cost = cost, best = bk;
+  }
+  return best;
 }
 
 }  // namespace
@@ -414,10 +454,17 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
   a.T = c->T, a.Tx = c->Tx, a.B = c->B, a.Ho = Ho, a.Wo = Wo, a.Cin = c->Cin, a.Cout = c->Cout;
   a.ksize = c->ksize, a.stride = c->stride, a.pad = pad, a.n_wsplit = c->n_wsplit, a.n_xsplit = c->n_xsplit;
   pick_tile(c->B, Ho, Wo, c->stride, &a.NB, &a.TH, &a.TW);
-  const int BLOCK_N = c->Cout <= 32 ? 32 : 64;
+  const int BK = pick_bk(c->Cin);
+  const int taps_ = c->ksize * c->ksize;
+  const int nkb_ = taps_ * (int)eas_ceil_div(c->Cin, BK);
+  // wide N tile (A re-read from L2 half as often) only where the K loop is long enough to hide the
+  // single-CTA-per-SM epilogue, and the T accumulators still fit 512 TMEM columns
+  const bool wide = BK == 64 && c->Cout >= 128 && nkb_ >= 16 && c->Tx <= 4;
+  const int BLOCK_N = c->Cout <= 32 ? 32 : (wide ? 128 : 64);
   a.tiles_w = (int)eas_ceil_div(Wo, a.TW), a.tiles_h = (int)eas_ceil_div(Ho, a.TH);
   a.tiles_b = (int)eas_ceil_div(c->B, a.NB), a.tiles_n = (int)eas_ceil_div(c->Cout, BLOCK_N);
   a.out_ld = out_ld, a.out_mode = c->out_mode;
+  a.residual = (const __nv_bfloat16*)c->residual, a.res_ld = c->res_ld ? c->res_ld : c->Cout;
   a.vth = c->v_threshold, a.vreset = c->v_reset, a.hard_reset = c->hard_reset, a.decay_input = c->decay_input;
   a.bias = bias, a.plif_w = plif_w, a.out = out;
   const int64_t grid = (int64_t)a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
@@ -425,16 +472,18 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
 
   // activations: [plane*Tx][B][H][W][x_ld] bf16, innermost first for the tensor map
   CUtensorMap xmap, wmap;
+  const CUtensorMapSwizzle swz = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   {
     cuuint64_t dims[5] = {(cuuint64_t)c->Cin, (cuuint64_t)c->W, (cuuint64_t)c->H, (cuuint64_t)c->B,
                           (cuuint64_t)(c->n_xsplit * c->Tx)};
     cuuint64_t strides[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)c->W * x_ld * 2, (cuuint64_t)c->H * c->W * x_ld * 2,
                              (cuuint64_t)c->B * c->H * c->W * x_ld * 2};
-    cuuint32_t box[5] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(a.TW * c->stride), (cuuint32_t)(a.TH * c->stride),
+    cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)(a.TW * c->stride), (cuuint32_t)(a.TH * c->stride),
                          (cuuint32_t)a.NB, 1};
     cuuint32_t estr[5] = {1, (cuuint32_t)c->stride, (cuuint32_t)c->stride, 1, 1};
     CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return EAS_E_SHAPE;
   }
@@ -442,21 +491,21 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
     const int taps = c->ksize * c->ksize;
     cuuint64_t dims[3] = {(cuuint64_t)c->Cin, (cuuint64_t)taps, (cuuint64_t)(c->n_wsplit * c->Cout)};
     cuuint64_t strides[2] = {(cuuint64_t)c->Cin * 2, (cuuint64_t)taps * c->Cin * 2};
-    cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, 1, (cuuint32_t)BLOCK_N};
+    cuuint32_t box[3] = {(cuuint32_t)BK, 1, (cuuint32_t)BLOCK_N};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_planes), dims, strides, box,
-                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return EAS_E_SHAPE;
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int Tacc = c->Tx;
-  if (BLOCK_N == 32) {
-    if (Tacc <= 1) return launch_conv<32, 1>(xmap, wmap, a, grid, st);
-    if (Tacc <= 4) return launch_conv<32, 4>(xmap, wmap, a, grid, st);
-    return launch_conv<32, 8>(xmap, wmap, a, grid, st);
-  }
-  if (Tacc <= 1) return launch_conv<64, 1>(xmap, wmap, a, grid, st);
-  if (Tacc <= 4) return launch_conv<64, 4>(xmap, wmap, a, grid, st);
-  return launch_conv<64, 8>(xmap, wmap, a, grid, st);
+#define EAS_CONV_BK(BN_)                                                              \
+  (BK == 64 ? launch_conv_t<BN_, 64>(Tacc, xmap, wmap, a, grid, st)                   \
+   : BK == 32 ? launch_conv_t<BN_, 32>(Tacc, xmap, wmap, a, grid, st)                 \
+              : launch_conv_t<BN_, 16>(Tacc, xmap, wmap, a, grid, st))
+  if (BLOCK_N == 32) return EAS_CONV_BK(32);
+  if (BLOCK_N == 128) return launch_conv_t<128, 64>(Tacc, xmap, wmap, a, grid, st);
+  return EAS_CONV_BK(64);
+#undef EAS_CONV_BK
 }

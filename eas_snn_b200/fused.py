@@ -56,13 +56,14 @@ def pack_weight(w_folded: torch.Tensor, n_wsplit: int) -> torch.Tensor:
 def conv_bn_plif(x: torch.Tensor, w_planes: torch.Tensor, bias: torch.Tensor, plif_w: torch.Tensor | None,
                  T: int, ksize: int, stride: int, n_xsplit: int = 1, out: torch.Tensor | None = None,
                  out_mode: int = OUT_SPIKES, v_threshold: float = 1.0, v_reset: float | None = None,
-                 decay_input: bool = False) -> torch.Tensor:
+                 decay_input: bool = False, residual: torch.Tensor | None = None) -> torch.Tensor:
     """One fused layer.
 
     x        : channels-last bf16 ``[Tx, B, H, W, Cin]`` (``[n_xsplit, Tx, B, H, W, Cin]`` for split
                real-valued input); may be a channel slice of a wider buffer (pixel stride ``x_ld``).
     w_planes : ``[n_wsplit, Cout, k, k, Cin]`` bf16 (:func:`pack_weight`), bias ``[Cout]`` fp32.
     out      : optional destination view ``[T, B, Ho, Wo, Cout]`` (channel slice of a concat buffer).
+    residual : optional bf16 ``[T, B, Ho, Wo, Cout]`` added to the spikes in the epilogue (SEW shortcut).
     Returns spikes ``[T, B, Ho, Wo, Cout]`` bf16 (or the fp32 pre-activation / 3 SiLU planes).
     """
     _lib.require_cuda(x, w_planes, bias)
@@ -101,10 +102,19 @@ def conv_bn_plif(x: torch.Tensor, w_planes: torch.Tensor, bias: torch.Tensor, pl
     owant = (B * Ho * Wo * out_ld, Ho * Wo * out_ld, Wo * out_ld, out_ld, 1)
     if out_ld < Cout or any(d > 1 and s_ != w_ for s_, w_, d in zip(out.stride()[-5:], owant, oshape)):
         raise ValueError("out must be a dense channels-last tensor or a channel slice of one")
+    res_ld = 0
+    if residual is not None:
+        if residual.dtype != torch.bfloat16 or tuple(residual.shape) != (T, B, Ho, Wo, Cout):
+            raise ValueError("residual must be bf16 [T, B, Ho, Wo, Cout]")
+        res_ld = residual.stride(-2) if Wo > 1 else (residual.stride(-3) if Ho > 1 else Cout)
+        rwant = (B * Ho * Wo * res_ld, Ho * Wo * res_ld, Wo * res_ld, res_ld, 1)
+        if any(d > 1 and s_ != w_ for s_, w_, d in zip(residual.stride(), rwant, residual.shape)):
+            raise ValueError("residual must be channels-last (or a channel slice)")
     cfg = _lib.ConvCfg(T=T, Tx=Tx, B=B, H=H, W=W, Cin=Cin, Cout=Cout, ksize=ksize, stride=stride,
                        n_wsplit=n_wsplit, n_xsplit=n_xsplit, v_threshold=float(v_threshold),
                        hard_reset=0 if v_reset is None else 1, v_reset=0.0 if v_reset is None else float(v_reset),
-                       decay_input=int(bool(decay_input)), out_mode=out_mode, x_ld=x_ld, out_ld=out_ld)
+                       decay_input=int(bool(decay_input)), out_mode=out_mode, x_ld=x_ld, out_ld=out_ld,
+                       res_ld=res_ld, residual=None if residual is None else residual.data_ptr())
     L = _lib.lib()
     with torch.cuda.device(dev):
         rc = L.eas_conv_bn_plif_fwd(C.byref(cfg), _lib.ptr(xs), _lib.ptr(w_planes), _lib.ptr(bias),
@@ -186,12 +196,13 @@ class FusedConvBNPLIF(nn.Module):
         return self._cache[1], self._cache[2]
 
     # -- channels-last fast path (used by SpikingCSPDarknet) -------------------------------------
-    def run(self, x_cl: torch.Tensor, T: int, out: torch.Tensor | None = None, n_xsplit: int = 1) -> torch.Tensor:
+    def run(self, x_cl: torch.Tensor, T: int, out: torch.Tensor | None = None, n_xsplit: int = 1,
+            residual: torch.Tensor | None = None) -> torch.Tensor:
         wp, shift = self.packed()
         a = self.act
         return conv_bn_plif(x_cl, wp, shift, a.w.detach().float(), T, self.ksize, self.stride, n_xsplit=n_xsplit,
                             out=out, out_mode=OUT_SPIKES, v_threshold=a.v_threshold, v_reset=a.v_reset,
-                            decay_input=a.decay_input)
+                            decay_input=a.decay_input, residual=residual)
 
     # -- reference-shaped forward: [T, B, C, H, W] in, [T, B, C', H', W'] out -----------------------
     def forward(self, x_seq: torch.Tensor) -> torch.Tensor:
@@ -257,13 +268,8 @@ class _Bottleneck(nn.Module):
         self.use_add = shortcut and cin == cout
 
     def run(self, x, T, out=None):
-        if not self.use_add:
-            return self.conv2.run(self.conv1.run(x, T), T, out=out)
-        y = self.conv2.run(self.conv1.run(x, T), T)
-        if out is None:
-            return y + x                              # SEW add (network_blocks.py:99-103): values {0,1,2,..}
-        torch.add(y, x, out=out)
-        return out
+        # SEW add y + x (network_blocks.py:99-103) happens in the conv epilogue: values {0,1,2,..}
+        return self.conv2.run(self.conv1.run(x, T), T, out=out, residual=x if self.use_add else None)
 
 
 class _SPP(nn.Module):

@@ -171,6 +171,9 @@ typedef struct {
                            a channel slice of a wider concat buffer */
   int32_t out_ld;       /* channels per pixel of the output buffer (>= Cout; 0 = Cout): lets the
                            output land in a channel slice of a concat buffer (CSPLayer / SPP cat) */
+  int32_t res_ld;       /* channels per pixel of the residual buffer (0 = Cout) */
+  const void* residual; /* optional bf16 [T][B][Ho][Wo][res_ld]: SEW shortcut added to the spikes
+                           (Bottleneck, network_blocks.py:99-103); NULL = none */
 } eas_conv_cfg;
 
 enum {

@@ -130,6 +130,27 @@ def test_output_into_concat_slice(cuda):
     assert torch.equal(fused.conv_bn_plif(wide[..., 64:128], w, bias, pw, 2, 1, 1), alone)
 
 
+def test_residual_and_wide_tiles(cuda):
+    """SEW shortcut fused in the epilogue; a layer large enough for the 128-wide N tile; K blocks of 32."""
+    g = torch.Generator().manual_seed(9)
+    for (Cin, Cout, k, H, W) in [(192, 192, 3, 16, 20), (96, 96, 3, 16, 24), (128, 256, 3, 8, 12)]:
+        x = (torch.rand((3, 2, H, W, Cin), generator=g) < 0.3).float()
+        w = torch.randn((Cout, Cin, k, k), generator=g) / (Cin * k * k) ** 0.5 * 2.0
+        bias = torch.randn(Cout, generator=g) * 0.3 + 0.3
+        pre = (_ref_conv(x, w, 1) + bias.double()).float()
+        want = op.plif_forward(pre, torch.tensor(0.2), op.ATan(2.0), 1.0, None, False, False)
+        res = torch.randint(0, 3, want.shape, generator=g).float()
+        xg, wp = x.to(cuda).bfloat16(), fused.pack_weight(w.to(cuda), 3)
+        pw = torch.tensor(0.2, device=cuda)
+        got = fused.conv_bn_plif(xg, wp, bias.to(cuda), pw, 3, k, 1).float().cpu()
+        got_r = fused.conv_bn_plif(xg, wp, bias.to(cuda), pw, 3, k, 1, residual=res.to(cuda).bfloat16()).float().cpu()
+        mism = (got != want).float().mean().item()
+        print("wide/residual (%d,%d,%d): mismatch %.3e rate %.3f" % (Cin, Cout, k, mism, want.mean().item()))
+        assert 0.02 < want.mean().item() < 0.95
+        assert mism <= 1e-4
+        assert torch.equal(got_r, got + res)
+
+
 def test_backbone_golden(cuda):
     """Whole spiking CSPDarknet (tiny width) vs the golden spikes of the REFERENCE model."""
     z = load_golden("backbone")
