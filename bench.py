@@ -72,6 +72,11 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            # nvidia-smi takes a while to start (and holds driver locks while it does): wait for its
+            # first sample so that start-up never overlaps a timed region
+            t_end = time.time() + 10.0
+            while time.time() < t_end and os.path.getsize(self.path) == 0:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 
@@ -314,9 +319,9 @@ def run_ours(args):
                   "what": "events -> bin -> sampler -> SYOLOX-M spiking CSPDarknet fwd (T=3, 256x320, %d tcgen05 "
                           "conv+BN+PLIF launches), %d windows per GPU; FPN/head not included (out of scope)"
                           % (n_conv, BATCH),
-                  "tensor": {"achieved": gflop / (fms / fsteps) / 1e3, "unit": "TFLOP/s (1x conv FLOPs; the kernel "
+                  "tensor": {"achieved": gflop / (fms / fsteps), "unit": "TFLOP/s (1x conv FLOPs; the kernel "
                              "runs 3 bf16 passes for fp32-equivalent weights)", "peak": 1394.4,
-                             "frac": gflop / (fms / fsteps) / 1e3 / 1394.4},
+                             "frac": gflop / (fms / fsteps) / 1394.4},
                   "spike_rate": {k: round(float(v.float().mean()), 4) for k, v in outs.items()}}
 
     # ---- per-kernel durations (CUDA events on the launching stream) for the roofline -----------

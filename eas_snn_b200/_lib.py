@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libeas_b200.so")
 
 EAS_F32, EAS_I32, EAS_BF16, EAS_U8 = 0, 1, 2, 3
 READOUT = {"sum": 0, "last": 1, "avg": 2}
+SAMPLER_ALGO = {"auto": 0, "fp32": 1, "tensor": 2}
 SURROGATE = {"atan": 0, "sigmoid": 1, "rect": 2}
 
 
@@ -20,7 +21,7 @@ class SamplerCfg(C.Structure):
     _fields_ = [("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Tm", C.c_int32), ("Ts", C.c_int32),
                 ("ksize", C.c_int32), ("depth", C.c_int32), ("readout", C.c_int32), ("hard_reset", C.c_int32),
                 ("vreset", C.c_float), ("thresh", C.c_float), ("spike_attach", C.c_int32),
-                ("write_zero", C.c_int32), ("use_abs", C.c_int32), ("in_dtype", C.c_int32)]
+                ("write_zero", C.c_int32), ("use_abs", C.c_int32), ("in_dtype", C.c_int32), ("algo", C.c_int32)]
 
 
 class SamplerPtrs(C.Structure):

@@ -7,6 +7,32 @@ namespace eas_sampler {
 
 constexpr int ru4(int a) { return (a + 3) / 4 * 4; }
 
+// Arguments of one sampler step (shared by the FP32-pipe kernel and the tensor-core kernel).
+struct StepArgs {
+  const void* events;     // [B][Tm][2][H][W]
+  const float* s_prev;    // [B][2][H][W]
+  float* s_next;
+  float* vm;
+  float* acc;
+  uint16_t* meta;         // seg | (t_last + 1) << 8
+  float* out;             // [Ts][B][2][H][W]
+  float* v_seq;           // [Tm][B][2][H][W] or null
+  float* gate_seq;
+  eas_sampler_weights w;
+  int B, H, W, Tm, Ts;
+  int t;                  // sampler step (0 = newest micro-bin)
+  int readout, hard_reset, write_zero, use_abs;
+  float vreset, thresh;
+};
+
+
+// Tensor-core path (sampler_tc.cu): depth 2, k 5 on tcgen05.  `wimg` = eas_sampler_tc_wimg_bytes()
+// of workspace holding the pre-packed weight tiles (built once per forward call).
+size_t eas_sampler_tc_wimg_bytes();
+bool eas_sampler_tc_supported(const eas_sampler_cfg* c, const void* events, const float* out, const float* v_seq,
+                              const float* gate_seq);
+int eas_sampler_tc_run(const eas_sampler_cfg* cfg, StepArgs a, float* s0, float* s1, void* wimg, cudaStream_t st);
+
 __device__ __forceinline__ void cp_async_16(void* smem, const void* g, bool pred) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   const int sz = pred ? 16 : 0;

@@ -25,23 +25,6 @@ namespace {
 
 using namespace eas_sampler;
 
-struct StepArgs {
-  const void* events;     // [B][Tm][2][H][W]
-  const float* s_prev;    // [B][2][H][W]
-  float* s_next;
-  float* vm;
-  float* acc;
-  uint16_t* meta;         // seg | (t_last + 1) << 8
-  float* out;             // [Ts][B][2][H][W]
-  float* v_seq;           // [Tm][B][2][H][W] or null
-  float* gate_seq;
-  eas_sampler_weights w;
-  int B, H, W, Tm, Ts;
-  int t;                  // sampler step (0 = newest micro-bin)
-  int readout, hard_reset, write_zero, use_abs;
-  float vreset, thresh;
-};
-
 template <int K, int DEPTH, int TH, int TW, typename IN_T, bool VEC>
 __global__ void __launch_bounds__(TH* TW / 4, 2)
 sampler_step_kernel(const StepArgs a) {
@@ -438,6 +421,7 @@ int check(const eas_sampler_cfg* c) {
   EAS_REQUIRE(c->ksize == 3 || c->ksize == 5 || c->ksize == 7, EAS_E_UNSUPPORTED);
   EAS_REQUIRE(c->readout >= EAS_READOUT_SUM && c->readout <= EAS_READOUT_AVG, EAS_E_UNSUPPORTED);
   EAS_REQUIRE(c->in_dtype == EAS_F32 || c->in_dtype == EAS_I32, EAS_E_UNSUPPORTED);
+  EAS_REQUIRE(c->algo >= EAS_SAMPLER_AUTO && c->algo <= EAS_SAMPLER_TENSOR, EAS_E_UNSUPPORTED);
   return EAS_OK;
 }
 
@@ -447,7 +431,9 @@ extern "C" size_t eas_sampler_fwd_ws_bytes(const eas_sampler_cfg* c) {
   if (check(c) != EAS_OK) return 0;
   const size_t n = (size_t)c->B * 2 * c->H * c->W;
   // vm, acc, s0, s1 (f32) + meta (u16), each segment 256 B aligned
-  return 4 * eas_align_up(n * 4, 256) + eas_align_up(n * 2, 256) + 256;
+  // + the packed weight tiles of the tensor-core path
+  return 4 * eas_align_up(n * 4, 256) + eas_align_up(n * 2, 256) + 256 +
+         eas_align_up(eas_sampler_tc_wimg_bytes(), 256);
 }
 
 extern "C" int eas_sampler_fwd(const eas_sampler_cfg* c, const void* events, const eas_sampler_weights* w,
@@ -475,6 +461,8 @@ extern "C" int eas_sampler_fwd(const eas_sampler_cfg* c, const void* events, con
   float* s1 = (float*)p;
   p += eas_align_up(n * 4, 256);
   a.meta = (uint16_t*)p;
+  p += eas_align_up(n * 2, 256);
+  void* wimg = (void*)p;
   a.out = out;
   a.v_seq = v_seq;
   a.gate_seq = gate_seq;
@@ -483,6 +471,10 @@ extern "C" int eas_sampler_fwd(const eas_sampler_cfg* c, const void* events, con
   a.readout = c->readout, a.hard_reset = c->hard_reset, a.write_zero = c->write_zero, a.use_abs = c->use_abs;
   a.vreset = c->vreset, a.thresh = c->thresh;
   cudaStream_t st = (cudaStream_t)stream;
+  // depth 2, k 5 (the published configuration): tensor-core kernel (sampler_tc.cu)
+  const bool tc_ok = eas_sampler_tc_supported(c, events, out, v_seq, gate_seq);
+  if (c->algo == EAS_SAMPLER_TENSOR) EAS_REQUIRE(tc_ok, EAS_E_UNSUPPORTED);
+  if (tc_ok && c->algo != EAS_SAMPLER_FP32) return eas_sampler_tc_run(c, a, s0, s1, wimg, st);
   // 16-byte vector path: rows must keep 16 B alignment (W % 4 == 0) and so must every base pointer
   const bool vec = (c->W % 4 == 0) && ((uintptr_t)events % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
                    (!v_seq || ((uintptr_t)v_seq % 16 == 0 && (uintptr_t)gate_seq % 16 == 0));

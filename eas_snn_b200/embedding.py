@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import copy
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -24,7 +25,8 @@ def _cfg(B, H, W, Tm, mod, in_dtype):
                            readout=_lib.READOUT[mod.readout], hard_reset=0 if mod.vreset is None else 1,
                            vreset=0.0 if mod.vreset is None else float(mod.vreset), thresh=float(mod.thresh),
                            spike_attach=int(bool(mod.spike_attach)), write_zero=int(bool(mod.write_zero)),
-                           use_abs=int(bool(mod.abs)), in_dtype=in_dtype)
+                           use_abs=int(bool(mod.abs)), in_dtype=in_dtype,
+                           algo=_lib.SAMPLER_ALGO[getattr(mod, "algo", "auto")])
 
 
 def _pack_ptrs(tensors):
@@ -133,6 +135,8 @@ class AdaptiveRSNNEmbedding(nn.Module):
             self.input_conv_agg = nn.Conv2d(in_channel, out_channel * 2, self.kernel_size,
                                             padding=self.kernel_size // 2)
         self.spike_attach = spike_attach
+        # forward kernel: "auto" (tensor cores for depth 2 / k 5, else the FP32-pipe kernel), "fp32", "tensor"
+        self.algo = os.environ.get("EAS_SAMPLER_ALGO", "auto")
         self._init_weight()
 
     @staticmethod

@@ -90,7 +90,11 @@ typedef struct {
   int32_t write_zero;   /* RPD: residual potential of silent pixels dropped      */
   int32_t use_abs;      /* relu on the aggregated frames                         */
   int32_t in_dtype;     /* EAS_F32 or EAS_I32                                    */
+  int32_t algo;         /* EAS_SAMPLER_* (forward only): AUTO picks the tensor-core kernel for
+                           depth 2, k 5, W % 4 == 0, 16 B aligned buffers, else the FP32-pipe kernel */
 } eas_sampler_cfg;
+
+enum { EAS_SAMPLER_AUTO = 0, EAS_SAMPLER_FP32 = 1, EAS_SAMPLER_TENSOR = 2 };
 
 typedef struct {
   const float *in_w0, *in_b0, *in_w1, *in_b1;

@@ -30,11 +30,23 @@ def _compare(out_gpu, out_ref, budget=1e-4):
     return frac <= budget, frac, msg
 
 
+ALGOS = ["fp32", "tensor"]
+
+
+def _tc_capable(cfg_or_kw, W):
+    k = cfg_or_kw.get("ksize", cfg_or_kw.get("kernel_size"))
+    return k == 5 and cfg_or_kw["depth"] == 2 and W % 4 == 0
+
+
+@pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("name", NAMES)
-def test_forward_golden(cuda, name):
+def test_forward_golden(cuda, name, algo):
     z = load_golden("sampler")
     cfg, params, grads, x, y = sampler_case(z, name)
+    if algo == "tensor" and not _tc_capable(cfg, cfg["W"]):
+        pytest.skip("the tensor-core kernel covers depth 2 / k 5 / W % 4 == 0")
     m = eas.AdaptiveRSNNEmbedding(**sampler_kwargs(cfg)).to(cuda)
+    m.algo = algo
     m.load_state_dict(params)
     with torch.no_grad():
         out = m(x.to(cuda))
@@ -47,7 +59,8 @@ def test_forward_golden(cuda, name):
     assert torch.equal(out, out_i)
 
 
-def test_forward_vs_oracle_gen1_shape(cuda):
+@pytest.mark.parametrize("algo", ALGOS)
+def test_forward_vs_oracle_gen1_shape(cuda, algo):
     """BASELINE config-1 shape: B=2, Tm=4, 240x304, published flags, Poisson counts."""
     torch.manual_seed(80)
     kw = dict(kernel_size=5, in_channel=2, out_channel=2, readout="sum", split=False, write_zero=True, abs=False,
@@ -61,10 +74,12 @@ def test_forward_vs_oracle_gen1_shape(cuda):
     fired = (st["seg"] > 0).float().mean().item()
     assert 0.05 < fired < 0.95, fired
     m = eas.AdaptiveRSNNEmbedding(**kw).to(cuda)
+    m.algo = algo
     m.load_state_dict(ref.state_dict())
     with torch.no_grad():
         out = m(x.to(cuda))
     ok, frac, msg = _compare(out, want, budget=1e-4)
+    print(algo, msg)
     assert ok, msg
 
 
@@ -74,10 +89,12 @@ def _wb(ref):
     return iw, ib, gw, gb
 
 
-def test_6d_input_and_batch_independence(cuda):
+@pytest.mark.parametrize("algo", ALGOS)
+def test_6d_input_and_batch_independence(cuda, algo):
     torch.manual_seed(1)
     m = eas.AdaptiveRSNNEmbedding(kernel_size=5, depth=2, nb_steps=4, thresh=1, vreset=0, Ts=1,
                                   write_zero=True, spike_attach=True).to(cuda)
+    m.algo = algo
     x = torch.poisson(torch.full((3, 2, 4, 2, 32, 72), 1.3)).to(cuda)       # [B, Tl, Tm, 2, H, W]
     with torch.no_grad():
         full = m(x)
@@ -100,3 +117,55 @@ def test_forward_events_equals_bin_then_sample(cuda):
     assert a.shape == (1, 3, 2, H, W)
     assert torch.equal(a, b)
     assert (a != 0).float().mean().item() > 0.01
+
+
+@pytest.mark.parametrize("shape", [(1, 4, 8, 12), (3, 4, 61, 100), (2, 5, 130, 236), (5, 3, 33, 480), (64, 2, 24, 32)])
+@pytest.mark.parametrize("flags", [dict(readout="sum", Ts=1, vreset=0, spike_attach=True, write_zero=True, abs=False),
+                                   dict(readout="avg", Ts=2, vreset=None, spike_attach=False, write_zero=False, abs=True),
+                                   dict(readout="last", Ts=3, vreset=0.25, spike_attach=True, write_zero=False, abs=False)])
+def test_tensor_kernel_vs_oracle_shapes(cuda, shape, flags):
+    """Tensor-core kernel on ragged strip / segment geometries (1..5 strips per row, segments that
+    start mid-image, fewer tiles than ring slots) against the dense oracle, and against the FP32 kernel."""
+    B, Tm, H, W = shape
+    torch.manual_seed(7)
+    kw = dict(kernel_size=5, in_channel=2, out_channel=2, split=False, depth=2, nb_steps=Tm, thresh=1,
+              embedding="arsnn", **flags)
+    ref = osamp.OracleSampler(**kw)
+    g = torch.Generator().manual_seed(B * 1000 + H)
+    x = torch.poisson(torch.full((B, Tm, 2, H, W), 1.0), generator=g)
+    x[0, 0, 0, H // 2, W // 2] = 300.0            # a count that is not exact in one bf16 plane
+    if H % 2 == 1:                                # real-valued micro-frames (resized inputs): all 3 planes
+        x = x * (0.5 + torch.rand(x.shape, generator=g))
+    with torch.no_grad():
+        want = ref(x)
+    m = eas.AdaptiveRSNNEmbedding(**kw).to(cuda)
+    m.load_state_dict(ref.state_dict())
+    outs = {}
+    for algo in ALGOS:
+        m.algo = algo
+        with torch.no_grad():
+            outs[algo] = m(x.to(cuda))
+        ok, frac, msg = _compare(outs[algo], want, budget=2e-3 if want.numel() < 20000 else 2e-4)
+        print(algo, shape, msg)
+        assert ok, algo + ": " + msg
+    ok, frac, msg = _compare(outs["tensor"], outs["fp32"].cpu(), budget=2e-3 if want.numel() < 20000 else 2e-4)
+    assert ok, "tensor vs fp32: " + msg
+    assert (want != 0).float().mean().item() > 0.01
+
+
+def test_tensor_kernel_saves_same_sequences_for_backward(cuda):
+    """Training forward: v_seq / gate_seq written by the tensor-core kernel feed the same backward."""
+    torch.manual_seed(3)
+    kw = dict(kernel_size=5, depth=2, nb_steps=4, thresh=1, vreset=0, Ts=1, write_zero=True, spike_attach=True)
+    m = eas.AdaptiveRSNNEmbedding(**kw).to(cuda)
+    x = torch.poisson(torch.full((2, 4, 2, 48, 64), 1.1)).to(cuda)
+    grads = {}
+    for algo in ALGOS:
+        m.algo = algo
+        m.zero_grad()
+        out = m(x)
+        (out * torch.linspace(0.5, 1.5, out.numel(), device=cuda).view_as(out)).sum().backward()
+        grads[algo] = [p.grad.clone() for p in m.parameters()]
+    for a, b in zip(grads["tensor"], grads["fp32"]):
+        scale = b.abs().max().item() + 1e-12
+        assert (a - b).abs().max().item() <= 2e-3 * scale, ((a - b).abs().max().item(), scale)
