@@ -23,12 +23,15 @@ struct StepArgs {
   int t;                  // sampler step (0 = newest micro-bin)
   int readout, hard_reset, write_zero, use_abs;
   float vreset, thresh;
+  const int* run_if;      // FP32-pipe kernel only: when set, the launch is a no-op unless *run_if != 0
 };
 
 
 // Tensor-core path (sampler_tc.cu): depth 2, k 5 on tcgen05.  `wimg` = eas_sampler_tc_wimg_bytes()
 // of workspace holding the pre-packed weight tiles (built once per forward call).
 size_t eas_sampler_tc_wimg_bytes();
+// device flag raised by the tensor-core kernels when an operand did not fit fp16 (|x| >= 65504)
+const int* eas_sampler_tc_flag(const void* wimg);
 bool eas_sampler_tc_supported(const eas_sampler_cfg* c, const void* events, const float* out, const float* v_seq,
                               const float* gate_seq);
 int eas_sampler_tc_run(const eas_sampler_cfg* cfg, StepArgs a, float* s0, float* s1, void* wimg, cudaStream_t st);

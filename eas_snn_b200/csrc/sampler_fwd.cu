@@ -43,6 +43,7 @@ sampler_step_kernel(const StepArgs a) {
   float* sh_l = DEPTH == 2 ? sh_i : sh_h;  // the tile filled from global memory
   __shared__ float sh_b[16];          // [0..3] layer-2 bias sum, [4..7] in b0, [8..11] gate b0
 
+  if (a.run_if != nullptr && *a.run_if == 0) return;  // fall-back launch that is not needed
   const int tid = threadIdx.x;
   const int tiles_x = (a.W + TW - 1) / TW;
   const int tiles_y = (a.H + TH - 1) / TH;
@@ -474,7 +475,13 @@ extern "C" int eas_sampler_fwd(const eas_sampler_cfg* c, const void* events, con
   // depth 2, k 5 (the published configuration): tensor-core kernel (sampler_tc.cu)
   const bool tc_ok = eas_sampler_tc_supported(c, events, out, v_seq, gate_seq);
   if (c->algo == EAS_SAMPLER_TENSOR) EAS_REQUIRE(tc_ok, EAS_E_UNSUPPORTED);
-  if (tc_ok && c->algo != EAS_SAMPLER_FP32) return eas_sampler_tc_run(c, a, s0, s1, wimg, st);
+  if (tc_ok && c->algo != EAS_SAMPLER_FP32) {
+    rc = eas_sampler_tc_run(c, a, s0, s1, wimg, st);
+    if (rc != EAS_OK || c->algo == EAS_SAMPLER_TENSOR) return rc;
+    // AUTO: operands beyond the fp16 range (never seen on event data) raise a device flag; the
+    // FP32-pipe launches below then recompute the whole step sequence, otherwise they exit at once.
+    a.run_if = eas_sampler_tc_flag(wimg);
+  }
   // 16-byte vector path: rows must keep 16 B alignment (W % 4 == 0) and so must every base pointer
   const bool vec = (c->W % 4 == 0) && ((uintptr_t)events % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
                    (!v_seq || ((uintptr_t)v_seq % 16 == 0 && (uintptr_t)gate_seq % 16 == 0));

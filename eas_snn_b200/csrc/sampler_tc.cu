@@ -17,15 +17,19 @@
 //     scripts/umma_shift_probe.cu);
 //   * B is the block-Toeplitz expansion of the 5 taps of that filter row: [N = 4 px x 4 channels]
 //     x [K = 8 px x channels], built once per forward by sampler_tc_pack_weights;
-//   * fp32 accuracy on bf16 tensor cores: weights are split into 3 bf16 planes (hi+mid+lo), the
-//     real-valued operands (counts, hidden activations) likewise; spikes are exact.  Product terms
-//     below fp32 rounding are skipped and the small terms are accumulated first (the TMEM
-//     accumulator truncates).
+//   * fp32-equivalent accuracy on 16-bit tensor cores: every real operand (counts, hidden
+//     activations, weights x 2^8) is split into TWO fp16 planes hi + lo (22 mantissa bits; spikes are
+//     exact), the three product terms hi*hi, lo*hi, hi*lo are accumulated in fp32 in TMEM, the
+//     hi*lo term in its own accumulator columns (concatenated along N, which is free: a
+//     shared-memory-operand MMA of M=128, K=16 costs 64 cycles for any N <= 128, measured with
+//     scripts/umma_rate_probe.cu) and added in the epilogue.  Magnitudes >= 65504 cannot be held in
+//     fp16: they raise a flag in the workspace and the caller re-runs the step sequence on the
+//     FP32-pipe kernel (never seen on event data; keeps the operator total).
 // One persistent CTA per SM walks vertical strips of <= 116 pixels (QPR <= 31 quads per row incl.
 // halo) top to bottom as a rolling pipeline over 128-quad tiles:
-//   producers (4 warps): counts + previous spikes -> 3 bf16 planes -> X0 ring (zero padded)
+//   producers (4 warps): counts + previous spikes -> fp16 hi/lo planes -> X0 ring (zero padded)
 //   MMA (1 thread)     : layer 1 (X0 -> D1 in TMEM), layer 2 (X1 -> D2 in TMEM)
-//   epilogue 1 (4 warps): D1 + bias, ReLU, image mask, 3-plane split -> X1 ring
+//   epilogue 1 (4 warps): D1 + bias, ReLU, image mask, hi/lo split -> X1 ring
 //   epilogue 2 (4 warps): D2 -> sigmoid gate, membrane update, threshold/reset, spike-triggered
 //                         read-out, state write-back (same arithmetic as sampler_step_kernel)
 // Rings hold S tiles plus a mirrored copy of slot 0 so that a 128-row operand never wraps.
@@ -42,23 +46,31 @@ constexpr int S1 = 3;           // X1 ring slots
 constexpr int RS0 = S0 * TILE, RS1 = S1 * TILE;
 constexpr int X0_BYTES = (S0 + 1) * TILE * ROWB;          // + mirrored slot 0
 constexpr int X1_PLANE = (S1 + 1) * TILE * ROWB;
-constexpr int X1_BYTES = 3 * X1_PLANE;
-constexpr int BT = 1024;        // one B tile: [16 rows (N)][32 bf16 (K)] SWIZZLE_64B
-constexpr int NB_L1 = 5 * 7;    // per ky: in0.h0, in0.h1, in1, in2, gate0, gate1, gate2
-constexpr int NB_L2 = 3 * 5 * 2;
-constexpr int WB_BYTES = (NB_L1 + NB_L2) * BT;            // 66560
+constexpr int X1_BYTES = 2 * X1_PLANE;
+// B tiles (SWIZZLE_64B, 64 B rows = 32 fp16 of K = two MMA K-steps):
+//   layer 1, per ky: IN [32 rows][32] (2 KB), GATE [32 rows][32] (2 KB)
+//   layer 2, per (ky, h): A [32 rows][32] (2 KB: w_hi | w_lo), B [16 rows][32] (1 KB: w_hi)
+constexpr int W1_KY = 4096, W2_KYH = 3072;
+constexpr int OFF_W2 = 5 * W1_KY;
+constexpr int WB_BYTES = OFF_W2 + 10 * W2_KYH;             // 51200
 constexpr int WIMG_BYTES = WB_BYTES + 64;                  // + 12 bias floats
+constexpr float W_SCALE = 256.0f, W_UNSCALE = 1.0f / 256.0f;  // keeps the weight lo plane a normal fp16
+constexpr float F16_MAX = 65504.0f;
 constexpr int OFF_X0 = WB_BYTES;
 constexpr int OFF_X1 = OFF_X0 + X0_BYTES;
 constexpr int OFF_BAR = OFF_X1 + X1_BYTES;
 constexpr int NBAR = 2 * S0 + 2 * S1 + 8;
 constexpr int OFF_MISC = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_MISC + 128 + 1024;          // + slack for the 1024 B alignment
-constexpr int NUM_THREADS = 13 * 32;  // warps 0-3 epilogue 1, 4-7 epilogue 2, 8 MMA, 9-12 producers
+// warps 0-3 epilogue 1, 4-7 / 8-11 epilogue 2 (even / odd tiles), 12 MMA issuer, 13-16 producers
+constexpr int W_E2 = 4, W_MMA = 12, W_PROD = 13;
+constexpr int NUM_THREADS = 17 * 32;
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
-// TMEM columns: D1 (input stack 16 + gate stack 16) x 2 buffers, D2 16 x 2 buffers
-constexpr uint32_t TM_D1 = 0, TM_D2 = 64, TM_COLS = 128;
+// TMEM columns: D1 = [in: x*w_hi (16) | x_hi*w_lo (16)][gate: same] x 2 buffers (64 apart);
+// D2 = [x_hi*w_hi (16) | x_hi*w_lo (16) | x_lo*w_hi (16)] x 2 buffers (64 apart).  The partial sums
+// are added in fp32 by the epilogues.
+constexpr uint32_t TM_D1 = 0, TM_D2 = 128, TM_COLS = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -85,6 +97,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -117,27 +138,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__host__ __device__ __forceinline__ float bf16_round_f(float x) {
-#ifdef __CUDA_ARCH__
-  return __bfloat162float(__float2bfloat16_rn(x));
-#else
-  return __bfloat162float(__float2bfloat16(x));
-#endif
-}
-// x = hi + mid + lo (three bf16 values); returned as packed pairs for two inputs.
-__device__ __forceinline__ void split3_pair(float a, float b, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  const float2 hf = __bfloat1622float2(h);
-  const float ra = a - hf.x, rb = b - hf.y;
-  const __nv_bfloat162 m = __floats2bfloat162_rn(ra, rb);
-  const float2 mf = __bfloat1622float2(m);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(ra - mf.x, rb - mf.y);
+// (a, b) -> packed fp16 pairs hi, lo with a ~= hi.x + lo.x (22 mantissa bits); `ovf` is raised when
+// a magnitude does not fit fp16.
+__device__ __forceinline__ void split2_pair(float a, float b, uint32_t& hi, uint32_t& lo, bool& ovf) {
+  ovf = ovf || !(fabsf(a) < F16_MAX) || !(fabsf(b) < F16_MAX);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
-  mid = *reinterpret_cast<const uint32_t*>(&m);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+__device__ __forceinline__ uint32_t pack2_f16(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -145,56 +157,55 @@ __device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_
 }
 
 // ---- weight image -------------------------------------------------------------------------------
-// B tiles in the order the MMA issuer walks them, each already in its SWIZZLE_64B shared-memory
-// layout (tile base 1024 B aligned), followed by 12 bias floats.
-//   layer 1, per ky (7 tiles):
-//     in0.h : K = [hi|mid|lo|spk] chunks of half h (32)   x w_in0 plane 0 (spk chunk: 0)
-//     in1   : K = [half 0: hi|mid][half 1: hi|mid]        x w_in0 plane 1
-//     in2   : same, mid chunk zero                        x w_in0 plane 2
-//     gate j: K = [half 0: lo|spk][half 1: lo|spk], lo: 0 x w_gate0 plane j
-//   layer 2, per (j, ky, h): K = 4 px x 8 hidden channels of half h, w_in1 | w_gate1 plane j.
-// N index n = 4 * (output pixel of the quad) + output channel.
-__device__ __forceinline__ float bf16_plane(float w, int plane) {
-  const float hi = bf16_round_f(w);
-  if (plane == 0) return hi;
-  const float mid = bf16_round_f(w - hi);
-  if (plane == 1) return mid;
-  return bf16_round_f(w - hi - mid);
+// B tiles in their SWIZZLE_64B shared-memory layout (image base 1024 B aligned), then 12 bias
+// floats.  Row n of a tile = output column n of the MMA; k = position inside the 32-element row.
+//   layer 1, IN(ky):   k = h*16 + c*8 + p*2 + ci, c in {ev_hi, ev_lo}; n = part*16 + jpx*4 + co
+//                      part 0: w_hi for both c;  part 1: w_lo for c = ev_hi, 0 for c = ev_lo
+//            GATE(ky): k = h*16 + c*8 + p*2 + ci, c in {spk, zero pad}; part 0: g_hi, part 1: g_lo
+//   layer 2, A(ky,h):  k = p*8 + ci (8 hidden channels: input stack 0-3, gate stack 4-7);
+//                      n = part*16 + jpx*4 + co, part 0: w_hi, part 1: w_lo;   B(ky,h): w_hi only
+// with tap = 4*h + p - jpx (window pixel minus output pixel), weights pre-scaled by 2^8.
+__device__ __forceinline__ float f16_plane(float w, int plane) {
+  const float ws = w * W_SCALE;
+  const float hi = __half2float(__float2half_rn(ws));
+  return plane == 0 ? hi : __half2float(__float2half_rn(ws - hi));
 }
 
-__global__ void sampler_tc_pack_weights(const eas_sampler_weights w, uint8_t* img) {
+__global__ void sampler_tc_pack_weights(const eas_sampler_weights w, uint8_t* img, int* flag) {
   constexpr int K = 5;
-  const int total = (NB_L1 + NB_L2) * 16 * 32;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int tile = idx / 512, n = (idx >> 5) & 15, k = idx & 31;
-    const int jpx = n >> 2, co = n & 3;
+  const int n1 = 5 * 2 * 32 * 32, n2 = 10 * 48 * 32;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n1 + n2; idx += gridDim.x * blockDim.x) {
     float val = 0.0f;
-    if (tile < NB_L1) {
-      const int ky = tile / 7, kind = tile % 7;
-      if (kind < 2) {  // in0, half h = kind
-        const int c = k >> 3, p = (k & 7) >> 1, ci = k & 1, tap = 4 * kind + p - jpx;
-        if (c < 3 && tap >= 0 && tap < K) val = bf16_plane(w.in_w0[((co * 2 + ci) * K + ky) * K + tap], 0);
-      } else if (kind < 4) {  // in1 / in2: k = h*16 + c*8 + p*2 + ci, c in {hi, mid}
-        const int h = k >> 4, c = (k >> 3) & 1, p = (k & 7) >> 1, ci = k & 1, tap = 4 * h + p - jpx;
-        const int plane = kind - 1;
-        if (tap >= 0 && tap < K && !(plane == 2 && c == 1))
-          val = bf16_plane(w.in_w0[((co * 2 + ci) * K + ky) * K + tap], plane);
-      } else {  // gate j: k = h*16 + c*8 + p*2 + ci, c in {lo (zero), spk}
-        const int h = k >> 4, c = (k >> 3) & 1, p = (k & 7) >> 1, ci = k & 1, tap = 4 * h + p - jpx;
-        if (c == 1 && tap >= 0 && tap < K) val = bf16_plane(w.gate_w0[((co * 2 + ci) * K + ky) * K + tap], kind - 4);
+    int off;
+    if (idx < n1) {
+      const int ky = idx / 2048, r = idx % 2048;
+      const int gate = r / 1024, n = (r / 32) % 32, k = r % 32;
+      const int part = n >> 4, jpx = (n >> 2) & 3, co = n & 3;
+      const int h = k >> 4, c = (k >> 3) & 1, p = (k & 7) >> 1, ci = k & 1, tap = 4 * h + p - jpx;
+      if (tap >= 0 && tap < K) {
+        if (!gate) {
+          if (!(part == 1 && c == 1)) val = f16_plane(w.in_w0[((co * 2 + ci) * K + ky) * K + tap], part);
+        } else if (c == 0) {
+          val = f16_plane(w.gate_w0[((co * 2 + ci) * K + ky) * K + tap], part);
+        }
       }
+      off = ky * W1_KY + gate * 2048 + n * 64 + (((k >> 3) ^ ((n >> 1) & 3)) << 4) + (k & 7) * 2;
     } else {
-      const int t2 = tile - NB_L1;
-      const int h = t2 & 1, ky = (t2 >> 1) % 5, j = t2 / 10;
+      const int i2 = idx - n1;
+      const int kyh = i2 / 1536, r = i2 % 1536;
+      const int ky = kyh >> 1, h = kyh & 1;
+      const int n = r / 32, k = r % 32;          // n 0..31: tile A, 32..47: tile B
+      const int nn = n < 32 ? n : n - 32;
+      const int part = n < 32 ? (nn >> 4) : 0, jpx = (nn >> 2) & 3, co = nn & 3;
       const int p = k >> 3, ci = k & 7, tap = 4 * h + p - jpx;
       if (tap >= 0 && tap < K) {
         const float wv = ci < 4 ? w.in_w1[((co * 4 + ci) * K + ky) * K + tap]
                                 : w.gate_w1[((co * 4 + (ci - 4)) * K + ky) * K + tap];
-        val = bf16_plane(wv, j);
+        val = f16_plane(wv, part);
       }
+      off = OFF_W2 + kyh * W2_KYH + (n < 32 ? 0 : 2048) + nn * 64 + (((k >> 3) ^ ((nn >> 1) & 3)) << 4) + (k & 7) * 2;
     }
-    const int off = tile * BT + n * 64 + (((k >> 3) ^ ((n >> 1) & 3)) << 4) + (k & 7) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16(val);
+    *reinterpret_cast<__half*>(img + off) = __float2half_rn(val);
   }
   if (blockIdx.x == 0 && threadIdx.x < 4) {
     float* b = reinterpret_cast<float*>(img + WB_BYTES);
@@ -202,6 +213,7 @@ __global__ void sampler_tc_pack_weights(const eas_sampler_weights w, uint8_t* im
     b[4 + threadIdx.x] = w.in_b0[threadIdx.x];
     b[8 + threadIdx.x] = w.gate_b0[threadIdx.x];
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *flag = 0;
 }
 
 // ---- the step kernel ----------------------------------------------------------------------------
@@ -244,7 +256,7 @@ struct SegIter {
 
 template <bool kInt>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-sampler_tc_step_kernel(const StepArgs a, const TcGeo g, const uint8_t* __restrict__ wimg) {
+sampler_tc_step_kernel(const StepArgs a, const TcGeo g, const uint8_t* __restrict__ wimg, int* __restrict__ ovf_flag) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -277,7 +289,7 @@ sampler_tc_step_kernel(const StepArgs a, const TcGeo g, const uint8_t* __restric
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(TM_COLS)
                  : "memory");
@@ -295,9 +307,9 @@ sampler_tc_step_kernel(const StepArgs a, const TcGeo g, const uint8_t* __restric
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 9) {
+  if (warp >= W_PROD) {
     // ===================== producers: counts + previous spikes -> X0 ring =====================
-    const int q = (warp - 9) * 32 + lane;  // quad of the tile this thread fills
+    const int q = (warp - W_PROD) * 32 + lane;  // quad of the tile this thread fills
     SegIter it(a, g);
     Seg s;
     int gt = 0;  // global X0 tile counter
@@ -331,14 +343,16 @@ sampler_tc_step_kernel(const StepArgs a, const TcGeo g, const uint8_t* __restric
             cur[c].z = (float)__float_as_int(cur[c].z), cur[c].w = (float)__float_as_int(cur[c].w);
           }
         }
-        // chunk layout: element = px*2 + ch
-        uint32_t hi[4], mid[4], lo[4], sp[4];
-        split3_pair(cur[0].x, cur[1].x, hi[0], mid[0], lo[0]);
-        split3_pair(cur[0].y, cur[1].y, hi[1], mid[1], lo[1]);
-        split3_pair(cur[0].z, cur[1].z, hi[2], mid[2], lo[2]);
-        split3_pair(cur[0].w, cur[1].w, hi[3], mid[3], lo[3]);
-        sp[0] = pack2_bf16(cur[2].x, cur[3].x), sp[1] = pack2_bf16(cur[2].y, cur[3].y);
-        sp[2] = pack2_bf16(cur[2].z, cur[3].z), sp[3] = pack2_bf16(cur[2].w, cur[3].w);
+        // chunk layout: element = px*2 + ch; chunks [ev_hi | ev_lo | spikes | zero]
+        uint32_t hi[4], lo[4], sp[4];
+        bool ovf = false;
+        split2_pair(cur[0].x, cur[1].x, hi[0], lo[0], ovf);
+        split2_pair(cur[0].y, cur[1].y, hi[1], lo[1], ovf);
+        split2_pair(cur[0].z, cur[1].z, hi[2], lo[2], ovf);
+        split2_pair(cur[0].w, cur[1].w, hi[3], lo[3], ovf);
+        if (ovf) *ovf_flag = 1;
+        sp[0] = pack2_f16(cur[2].x, cur[3].x), sp[1] = pack2_f16(cur[2].y, cur[3].y);
+        sp[2] = pack2_f16(cur[2].z, cur[3].z), sp[3] = pack2_f16(cur[2].w, cur[3].w);
         const int slot = gt % S0;
         mbar_wait(x0_empty + slot, ((gt / S0) & 1) ^ 1);
         const int pos = slot * TILE + q;
@@ -348,20 +362,26 @@ sampler_tc_step_kernel(const StepArgs a, const TcGeo g, const uint8_t* __restric
           const uint32_t row = sX0 + (uint32_t)(pos + rep * RS0) * ROWB;
           const uint32_t sw = (row >> 7) & 3;
           st_shared_v4(row + ((0 ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
-          st_shared_v4(row + ((1 ^ sw) << 4), mid[0], mid[1], mid[2], mid[3]);
-          st_shared_v4(row + ((2 ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
-          st_shared_v4(row + ((3 ^ sw) << 4), sp[0], sp[1], sp[2], sp[3]);
+          st_shared_v4(row + ((1 ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
+          st_shared_v4(row + ((2 ^ sw) << 4), sp[0], sp[1], sp[2], sp[3]);
+          st_shared_v4(row + ((3 ^ sw) << 4), 0u, 0u, 0u, 0u);
         }
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(x0_full + slot);
       }
     }
-  } else if (warp == 8) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) |
-                                 ((uint32_t)(TILE >> 4) << 24);
+  } else if (warp == W_MMA) {
+    // ===================== MMA issuer =====================
+    // The whole warp walks the (warp-uniform) schedule so that descriptors live in uniform registers;
+    // only the elected lane issues tcgen05.mma / tcgen05.commit.
+    const bool leader = elect_one();
+    {
+      // fp16 x fp16 -> fp32, M = 128, N = 32 / 16
+      constexpr uint32_t idesc32 = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+      constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+      // descriptor + (byte offset >> 4) moves the start address (all buffers sit below 256 KB)
+      const uint64_t wdesc = sw64_desc(sWB), x0desc = sw64_desc(sX0), x1desc = sw64_desc(sX1);
       SegIter it(a, g);
       Seg s;
       int g0 = 0, g1 = 0, g2 = 0;  // global tile counters at the segment start
@@ -376,44 +396,31 @@ sampler_tc_step_kernel(const StepArgs a, const TcGeo g, const uint8_t* __restric
             while (w0 < need0) mbar_wait(x0_full + (w0 % S0), (w0 / S0) & 1), ++w0;
             mbar_wait(d1_empty + buf, ((gi >> 1) & 1) ^ 1);
             tc_fence_after();
-            const uint32_t d_in = tmem_base + TM_D1 + buf * 32, d_gate = d_in + 16;
-            uint32_t arow[10];
-#pragma unroll
-            for (int ky = 0; ky < 5; ++ky)
-#pragma unroll
-              for (int h = 0; h < 2; ++h)
-                arow[ky * 2 + h] = sX0 + (uint32_t)((base0 + i * TILE + ky * QPR + h) % RS0) * ROWB;
-            uint32_t acc_in = 0, acc_g = 0;
-            // small product terms first: x_hi*w_lo, (x_hi+x_mid)*w_mid, x_lo*w_hi
-#pragma unroll
+            const uint32_t d_in = tmem_base + TM_D1 + buf * 64, d_gate = d_in + 32;
+            // rolled over ky (small code: the issuer must not become instruction-fetch bound); the ring
+            // position advances by QPR rows per filter row and wraps without a division
+            int pos = (base0 + i * TILE) % RS0;
+            uint64_t bd = wdesc;  // IN tile of ky (GATE tile 2048 B further)
+#pragma unroll 1
             for (int ky = 0; ky < 5; ++ky) {
-              const uint32_t bt = sWB + (uint32_t)(ky * 7) * BT;
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const uint64_t a0 = sw64_desc(arow[ky * 2 + h]), a1 = sw64_desc(arow[ky * 2 + h] + 32);
-                tc_mma(d_in, a0, sw64_desc(bt + 3 * BT + h * 32), idesc, acc_in), acc_in = 1;   // in2
-                tc_mma(d_in, a0, sw64_desc(bt + 2 * BT + h * 32), idesc, 1);                    // in1
-                tc_mma(d_in, a1, sw64_desc(bt + h * BT + 32), idesc, 1);                        // in0: lo chunk
-                if (!first) {
-                  tc_mma(d_gate, a1, sw64_desc(bt + 6 * BT + h * 32), idesc, acc_g), acc_g = 1;  // gate lo
-                  tc_mma(d_gate, a1, sw64_desc(bt + 5 * BT + h * 32), idesc, 1);                 // gate mid
-                }
+              const int pos1 = pos + 1 == RS0 ? 0 : pos + 1;
+              const uint64_t a0 = x0desc + (uint64_t)(pos * (ROWB >> 4)), a1 = x0desc + (uint64_t)(pos1 * (ROWB >> 4));
+              const uint32_t acc = ky == 0 ? 0u : 1u;
+              // counts (hi | lo chunks) x IN tile, K-step h; spikes (| zero pad) x GATE tile (zero on step 0)
+              if (leader) tc_mma(d_in, a0, bd, idesc32, acc);
+              if (leader) tc_mma(d_in, a1, bd + 2, idesc32, 1u);
+              if (!first) {
+                if (leader) tc_mma(d_gate, a0 + 2, bd + (2048 >> 4), idesc32, acc);
+                if (leader) tc_mma(d_gate, a1 + 2, bd + ((2048 >> 4) + 2), idesc32, 1u);
               }
+              bd += (uint64_t)(W1_KY >> 4);
+              pos += QPR;
+              if (pos >= RS0) pos -= RS0;
             }
-#pragma unroll
-            for (int ky = 0; ky < 5; ++ky) {
-              const uint32_t bt = sWB + (uint32_t)(ky * 7) * BT;
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const uint64_t a0 = sw64_desc(arow[ky * 2 + h]), a1 = sw64_desc(arow[ky * 2 + h] + 32);
-                tc_mma(d_in, a0, sw64_desc(bt + h * BT), idesc, 1);                              // in0: hi|mid
-                if (!first) tc_mma(d_gate, a1, sw64_desc(bt + 4 * BT + h * 32), idesc, 1);       // gate hi
-              }
-            }
-            tc_commit(d1_full + buf);
-            tc_commit(x0_empty + ((g0 + i) % S0));
+            if (leader) tc_commit(d1_full + buf);
+            if (leader) tc_commit(x0_empty + ((g0 + i) % S0));
             if (i == s.nt1 - 1)
-              for (int k = s.nt1; k < s.nt0; ++k) tc_commit(x0_empty + ((g0 + k) % S0));
+              for (int k = s.nt1; k < s.nt0; ++k) if (leader) tc_commit(x0_empty + ((g0 + k) % S0));
           }
           const int j = itr - 2;
           if (j >= 0 && j < s.nt2) {
@@ -423,34 +430,31 @@ sampler_tc_step_kernel(const StepArgs a, const TcGeo g, const uint8_t* __restric
             while (w1 < need1) mbar_wait(x1_full + (w1 % S1), (w1 / S1) & 1), ++w1;
             mbar_wait(d2_empty + buf, ((gj >> 1) & 1) ^ 1);
             tc_fence_after();
-            const uint32_t d2 = tmem_base + TM_D2 + buf * 16;
-            uint32_t arow[10];
-#pragma unroll
-            for (int ky = 0; ky < 5; ++ky)
-#pragma unroll
-              for (int h = 0; h < 2; ++h)
-                arow[ky * 2 + h] = sX1 + (uint32_t)((base1 + j * TILE + ky * QPR + h) % RS1) * ROWB;
-            uint32_t acc = 0;
-            // (x plane, w plane) terms with xp + wp < 3, smallest first
-            constexpr int XP[6] = {2, 1, 0, 1, 0, 0};
-            constexpr int WP[6] = {0, 1, 2, 0, 1, 0};
-#pragma unroll
-            for (int term = 0; term < 6; ++term) {
-#pragma unroll
-              for (int ky = 0; ky < 5; ++ky) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  const uint32_t ar = arow[ky * 2 + h] + (uint32_t)XP[term] * X1_PLANE;
-                  const uint32_t bt = sWB + (uint32_t)(NB_L1 + (WP[term] * 5 + ky) * 2 + h) * BT;
-                  tc_mma(d2, sw64_desc(ar), sw64_desc(bt), idesc, acc), acc = 1;
-                  tc_mma(d2, sw64_desc(ar + 32), sw64_desc(bt + 32), idesc, 1);
-                }
-              }
+            const uint32_t d2 = tmem_base + TM_D2 + buf * 64;
+            // x_hi * [w_hi | w_lo] -> columns 0..31, x_lo * w_hi -> columns 32..47 (two independent chains)
+            int pos = (base1 + j * TILE) % RS1;
+            uint64_t bd = wdesc + (uint64_t)(OFF_W2 >> 4);  // tiles A, B of (ky, h = 0); h = 1 is W2_KYH further
+#pragma unroll 1
+            for (int ky = 0; ky < 5; ++ky) {
+              const int pos1 = pos + 1 == RS1 ? 0 : pos + 1;
+              const uint64_t a0 = x1desc + (uint64_t)(pos * (ROWB >> 4)), a1 = x1desc + (uint64_t)(pos1 * (ROWB >> 4));
+              const uint32_t acc = ky == 0 ? 0u : 1u;
+              if (leader) tc_mma(d2, a0, bd, idesc32, acc);
+              if (leader) tc_mma(d2 + 32, a0 + (X1_PLANE >> 4), bd + (2048 >> 4), idesc16, acc);
+              if (leader) tc_mma(d2, a0 + 2, bd + 2, idesc32, 1u);
+              if (leader) tc_mma(d2 + 32, a0 + ((X1_PLANE >> 4) + 2), bd + ((2048 >> 4) + 2), idesc16, 1u);
+              if (leader) tc_mma(d2, a1, bd + (W2_KYH >> 4), idesc32, 1u);
+              if (leader) tc_mma(d2 + 32, a1 + (X1_PLANE >> 4), bd + ((W2_KYH + 2048) >> 4), idesc16, 1u);
+              if (leader) tc_mma(d2, a1 + 2, bd + ((W2_KYH >> 4) + 2), idesc32, 1u);
+              if (leader) tc_mma(d2 + 32, a1 + ((X1_PLANE >> 4) + 2), bd + (((W2_KYH + 2048) >> 4) + 2), idesc16, 1u);
+              bd += (uint64_t)((2 * W2_KYH) >> 4);
+              pos += QPR;
+              if (pos >= RS1) pos -= RS1;
             }
-            tc_commit(d2_full + buf);
-            tc_commit(x1_empty + ((g1 + j) % S1));
+            if (leader) tc_commit(d2_full + buf);
+            if (leader) tc_commit(x1_empty + ((g1 + j) % S1));
             if (j == s.nt2 - 1)
-              for (int k = s.nt2; k < s.nt1; ++k) tc_commit(x1_empty + ((g1 + k) % S1));
+              for (int k = s.nt2; k < s.nt1; ++k) if (leader) tc_commit(x1_empty + ((g1 + k) % S1));
           }
         }
         g0 += s.nt0, g1 += s.nt1, g2 += s.nt2;
@@ -471,29 +475,36 @@ sampler_tc_step_kernel(const StepArgs a, const TcGeo g, const uint8_t* __restric
         const bool row_in = (unsigned)y1 < (unsigned)a.H;
         mbar_wait(d1_full + buf, (gt >> 1) & 1);
         tc_fence_after();
-        uint32_t din[16], dg[16];
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + TM_D1 + buf * 32;
+        // D1 columns: [x*w_hi (16) | x_hi*w_lo (16)] for the input stack, then the same for the gate stack
+        uint32_t din[16], dinl[16], dg[16], dgl[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + TM_D1 + buf * 64;
         tmem_ld16(taddr, din);
-        if (!first) tmem_ld16(taddr + 16, dg);
+        tmem_ld16(taddr + 16, dinl);
+        if (!first) tmem_ld16(taddr + 32, dg), tmem_ld16(taddr + 48, dgl);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(d1_empty + buf);
-        uint32_t ph[4][4], pm[4][4], pl[4][4];  // [px][4 x (2 channels)]
+        uint32_t ph[4][4], pl[4][4];  // [px][4 x (2 channels)]
+        bool ovf = false;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           const bool in_img = row_in && (unsigned)(x1 + p) < (unsigned)a.W;
           float hv[8];
 #pragma unroll
           for (int co = 0; co < 4; ++co) {
-            const float vi = fmaxf(__uint_as_float(din[p * 4 + co]) + sh_b[4 + co], 0.0f);
-            const float vg = fmaxf((first ? 0.0f : __uint_as_float(dg[p * 4 + co])) + sh_b[8 + co], 0.0f);
+            const float ci = (__uint_as_float(din[p * 4 + co]) + __uint_as_float(dinl[p * 4 + co])) * W_UNSCALE;
+            const float cg = first ? 0.0f
+                                   : (__uint_as_float(dg[p * 4 + co]) + __uint_as_float(dgl[p * 4 + co])) * W_UNSCALE;
+            const float vi = fmaxf(ci + sh_b[4 + co], 0.0f);
+            const float vg = fmaxf(cg + sh_b[8 + co], 0.0f);
             hv[co] = in_img ? vi : 0.0f;
             hv[4 + co] = in_img ? vg : 0.0f;
           }
 #pragma unroll
-          for (int c2 = 0; c2 < 4; ++c2) split3_pair(hv[2 * c2], hv[2 * c2 + 1], ph[p][c2], pm[p][c2], pl[p][c2]);
+          for (int c2 = 0; c2 < 4; ++c2) split2_pair(hv[2 * c2], hv[2 * c2 + 1], ph[p][c2], pl[p][c2], ovf);
         }
+        if (ovf) *ovf_flag = 1;
         mbar_wait(x1_empty + slot, ((gt / S1) & 1) ^ 1);
         const int pos = slot * TILE + q;
 #pragma unroll
@@ -505,8 +516,7 @@ sampler_tc_step_kernel(const StepArgs a, const TcGeo g, const uint8_t* __restric
           for (int p = 0; p < 4; ++p) {
             const uint32_t ca = row + (((uint32_t)p ^ sw) << 4);
             st_shared_v4(ca, ph[p][0], ph[p][1], ph[p][2], ph[p][3]);
-            st_shared_v4(ca + X1_PLANE, pm[p][0], pm[p][1], pm[p][2], pm[p][3]);
-            st_shared_v4(ca + 2 * X1_PLANE, pl[p][0], pl[p][1], pl[p][2], pl[p][3]);
+            st_shared_v4(ca + X1_PLANE, pl[p][0], pl[p][1], pl[p][2], pl[p][3]);
           }
         }
         fence_async_smem();
@@ -517,7 +527,9 @@ sampler_tc_step_kernel(const StepArgs a, const TcGeo g, const uint8_t* __restric
   } else {
     // ===================== epilogue 2: D2 -> membrane update + spike-triggered read-out =====================
     // Same arithmetic, statement for statement, as sampler_step_kernel (embedding.py:132-139, 177-217).
-    const int wq = warp - 4;
+    // Two groups of four warps take alternate tiles (= alternate D2 buffers): one warp per scheduler
+    // runs this dependent arithmetic at a few cycles per instruction, too slow for one group alone.
+    const int wq = warp & 3, grp = (warp - W_E2) >> 2;
     const int q = wq * 32 + lane;
     SegIter it(a, g);
     Seg s;
@@ -526,6 +538,7 @@ sampler_tc_step_kernel(const StepArgs a, const TcGeo g, const uint8_t* __restric
       const int nq2 = s.nrows * QPR;
       for (int j = 0; j < s.nt2; ++j, ++gt) {
         const int buf = gt & 1;
+        if (buf != grp) continue;
         const int f = j * TILE + q;
         const int r2 = f / QPR, m = f - r2 * QPR;
         const int gy = s.ya + r2, gx = s.xs + 4 * m;
@@ -546,27 +559,35 @@ sampler_tc_step_kernel(const StepArgs a, const TcGeo g, const uint8_t* __restric
         }
         mbar_wait(d2_full + buf, (gt >> 1) & 1);
         tc_fence_after();
-        uint32_t d[16];
-        tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + TM_D2 + buf * 16, d);
+        uint32_t d[16], dl[16], dx[16];  // x_hi*w_hi | x_hi*w_lo | x_lo*w_hi
+        const uint32_t t2 = tmem_base + ((uint32_t)(wq * 32) << 16) + TM_D2 + buf * 64;
+        tmem_ld16(t2, d);
+        tmem_ld16(t2 + 16, dl);
+        tmem_ld16(t2 + 32, dx);
         tmem_ld_wait();
+#pragma unroll
+        for (int n = 0; n < 16; ++n)
+          d[n] = __float_as_uint(__uint_as_float(d[n]) + (__uint_as_float(dl[n]) + __uint_as_float(dx[n])));
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(d2_empty + buf);
         if (!valid) continue;
-#pragma unroll
+#pragma unroll 1   // rolled: halves the code of this role (the four roles share one instruction cache)
         for (int c = 0; c < 2; ++c) {
           const float bg = sh_b[c], bc = sh_b[2 + c];
           const int64_t base = base0 + c * HW;
           __align__(16) float vm4[4], ac4[4], v4[4], g4[4], s4[4], o4[4];
           __align__(8) uint16_t m4[4];
-          *reinterpret_cast<float4*>(vm4) = vmq[c];
-          *reinterpret_cast<float4*>(ac4) = acq[c];
-          *reinterpret_cast<uint2*>(m4) = mtq[c];
+          *reinterpret_cast<float4*>(vm4) = c ? vmq[1] : vmq[0];
+          *reinterpret_cast<float4*>(ac4) = c ? acq[1] : acq[0];
+          *reinterpret_cast<uint2*>(m4) = c ? mtq[1] : mtq[0];
           float* outp = a.out + base;  // plane k at outp + k*BHW2
 #pragma unroll
           for (int px = 0; px < 4; ++px) {
-            const float gate = __fdividef(1.0f, 1.0f + __expf(-(__uint_as_float(d[px * 4 + c]) + bg)));
-            const float cur = __uint_as_float(d[px * 4 + 2 + c]) + bc;
+            const float gpre = __uint_as_float(c ? d[px * 4 + 1] : d[px * 4]) * W_UNSCALE;
+            const float cpre = __uint_as_float(c ? d[px * 4 + 3] : d[px * 4 + 2]) * W_UNSCALE;
+            const float gate = __fdividef(1.0f, 1.0f + __expf(-(gpre + bg)));
+            const float cur = cpre + bc;
             int seg = m4[px] & 0xff;
             int tl = (int)(m4[px] >> 8) - 1;
             const float v = __fadd_rn(__fmul_rn(gate, vm4[px]), cur);
@@ -613,7 +634,7 @@ sampler_tc_step_kernel(const StepArgs a, const TcGeo g, const uint8_t* __restric
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == W_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TM_COLS) : "memory");
   }
@@ -630,7 +651,11 @@ TcGeo pick_geo(int W) {
 
 }  // namespace
 
-size_t eas_sampler_tc_wimg_bytes() { return (size_t)WIMG_BYTES; }
+size_t eas_sampler_tc_wimg_bytes() { return (size_t)WIMG_BYTES + 64; }  // + the fp16-range flag
+
+const int* eas_sampler_tc_flag(const void* wimg) {
+  return reinterpret_cast<const int*>(reinterpret_cast<const uint8_t*>(wimg) + WIMG_BYTES);
+}
 
 bool eas_sampler_tc_supported(const eas_sampler_cfg* c, const void* events, const float* out, const float* v_seq,
                               const float* gate_seq) {
@@ -642,7 +667,8 @@ bool eas_sampler_tc_supported(const eas_sampler_cfg* c, const void* events, cons
 
 int eas_sampler_tc_run(const eas_sampler_cfg* cfg, StepArgs a, float* s0, float* s1, void* wimg, cudaStream_t st) {
   EAS_REQUIRE((uintptr_t)wimg % 16 == 0, EAS_E_ALIGN);
-  sampler_tc_pack_weights<<<32, 256, 0, st>>>(a.w, reinterpret_cast<uint8_t*>(wimg));
+  int* flag = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(wimg) + WIMG_BYTES);
+  sampler_tc_pack_weights<<<32, 256, 0, st>>>(a.w, reinterpret_cast<uint8_t*>(wimg), flag);
   EAS_LAUNCH_CHECK();
   const TcGeo g = pick_geo(cfg->W);
   auto kern = cfg->in_dtype == EAS_I32 ? sampler_tc_step_kernel<true> : sampler_tc_step_kernel<false>;
@@ -657,7 +683,7 @@ int eas_sampler_tc_run(const eas_sampler_cfg* cfg, StepArgs a, float* s0, float*
     a.t = t;
     a.s_prev = (t & 1) ? s0 : s1;  // step t reads what step t-1 wrote
     a.s_next = (t & 1) ? s1 : s0;
-    kern<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, st>>>(a, g, reinterpret_cast<const uint8_t*>(wimg));
+    kern<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, st>>>(a, g, reinterpret_cast<const uint8_t*>(wimg), flag);
     EAS_LAUNCH_CHECK();
   }
   return EAS_OK;

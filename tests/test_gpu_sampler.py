@@ -169,3 +169,25 @@ def test_tensor_kernel_saves_same_sequences_for_backward(cuda):
     for a, b in zip(grads["tensor"], grads["fp32"]):
         scale = b.abs().max().item() + 1e-12
         assert (a - b).abs().max().item() <= 2e-3 * scale, ((a - b).abs().max().item(), scale)
+
+
+def test_auto_falls_back_beyond_fp16_range(cuda):
+    """The tensor-core kernel holds operands as fp16 hi+lo pairs; a magnitude >= 65504 raises its
+    device flag and algo="auto" recomputes on the FP32-pipe kernel: bit-identical to algo="fp32"."""
+    torch.manual_seed(5)
+    kw = dict(kernel_size=5, depth=2, nb_steps=4, thresh=1, vreset=0, Ts=1, write_zero=True, spike_attach=True)
+    m = eas.AdaptiveRSNNEmbedding(**kw).to(cuda)
+    x = torch.poisson(torch.full((2, 4, 2, 40, 64), 1.0)).to(cuda)
+    outs = {}
+    for big in (False, True):
+        if big:
+            x[1, 2, 0, 17, 33] = 70000.0
+        for algo in ("auto", "fp32"):
+            m.algo = algo
+            with torch.no_grad():
+                outs[algo] = m(x)
+        if big:
+            assert torch.equal(outs["auto"], outs["fp32"])
+        else:   # in range: auto is the tensor-core kernel (fp32-equivalent, not bit-identical)
+            ok, frac, msg = _compare(outs["auto"], outs["fp32"].cpu(), budget=2e-3)
+            assert ok, msg
