@@ -325,38 +325,59 @@ def run_ours(args):
                   "spike_rate": {k: round(float(v.float().mean()), 4) for k, v in outs.items()}}
 
     # ---- per-kernel durations (CUDA events on the launching stream) for the roofline -----------
-    def time_call(fn, reps=10):
+    def time_call(fn, reps=10, warm=3):
         ts = []
-        for r in range(reps):
+        for r in range(warm + reps):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn(r)
             b.record()
             torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b))
-        return float(np.mean(ts))
+            if r >= warm:
+                ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
 
     t_bin = time_call(lambda r: eas.bin_events(*devb[r % NSETS], H, W, TM, out=hist_buf))
-    hist_fixed = eas.bin_events(*devb[0], H, W, TM).clone()
+    hist_fixed = eas.bin_events(*devb[0], H, W, TM, dtype=torch.float32).clone()
     with torch.no_grad():
         t_smp = time_call(lambda r: model(hist_fixed))
+        model.algo = "fp32"
+        t_smp_fp32 = time_call(lambda r: model(hist_fixed))
+        model.algo = "auto"
     n_avg = float(np.mean([h.n for h in host]))
     bins = BATCH * TM * 2 * H * W
     bin_bytes = 13.0 * n_avg + 4.0 * bins                 # 13 B/event + 4 B/bin
     bin_bytes_touched = 5.0 * n_avg + 4.0 * bins          # t is only touched by the Tm+1 binary searches
-    smp_launch_ms = t_smp / TM
+    smp_launch_ms = t_smp / TM                                # one of the Tm step launches (+ 1/Tm of the weight pack)
     smp_bytes_launch = 8.0 * H * W * (TM + TS) * BATCH / TM   # SURVEY 8d, per launch (one of Tm steps)
     smp_flop_launch = 2400.0 * H * W * BATCH                  # 2400 FLOP per pixel-step
     fp32_peak = EAS_FP32_PEAK(sm_max_mhz)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    tensor_peak = float(peaks.get("bf16_tflops", 1590.0))     # burst figure: the kernel is timed alone
+    # issue model of the tensor-core sampler: 60 MMAs (M=128, K=16, N<=32) per 128-quad
+    # tile, 64 cycles each (scripts/umma_rate_probe.cu), ~69.5 tiles per SM per launch on this workload
+    tiles_per_sm = BATCH * 4 * (H + 4 * 148.0 / (BATCH * 4) * 2) * 21 / 128.0 / 148.0
+    mma_floor_ms = tiles_per_sm * 60 * 64 / (sm_max_mhz * 1e3)
     roofline = {
-        "kernel": "sampler_step_kernel (dominant: %.0f%% of the step)" % (100.0 * t_smp / (t_smp + t_bin)),
-        "bound": "hbm", "achieved": smp_bytes_launch / smp_launch_ms / 1e6, "peak": peak_gbs, "unit": "GB/s",
-        "frac": smp_bytes_launch / smp_launch_ms / 1e6 / peak_gbs, "traffic": None, "peak_source": peak_src,
+        "kernel": "sampler_tc_step_kernel (dominant: %.0f%% of the step)" % (100.0 * t_smp / (t_smp + t_bin)),
+        "bound": "tensor", "achieved": smp_flop_launch / smp_launch_ms / 1e9, "peak": tensor_peak, "unit": "TFLOP/s",
+        "frac": smp_flop_launch / smp_launch_ms / 1e9 / tensor_peak,
+        "traffic": 372.3e6, "traffic_source": "profiles/r1_ncu_sampler_tc_e.txt (dram read 210.1 MB + write 162.2 MB per launch)",
+        "peak_source": "measured cuBLAS bf16 burst (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
         "launch_ms": smp_launch_ms,
-        "note": "this kernel is FP32-pipe bound (240 FLOP/B), not HBM bound: see fp32",
-        "fp32": {"achieved": smp_flop_launch / smp_launch_ms / 1e9, "peak": fp32_peak, "unit": "TFLOP/s",
-                 "frac": smp_flop_launch / smp_launch_ms / 1e9 / fp32_peak,
-                 "peak_source": "148 SMs x 128 lanes x 2 x %.0f MHz" % sm_max_mhz},
+        "note": "algorithmic FLOPs (2400 per pixel-step, SURVEY 8d) over the dense bf16 GEMM peak; the kernel issues "
+                "fp16 hi/lo split MMAs with N = 32/16 (4-output-channel convolutions), whose cost is a fixed 64 "
+                "cycles per M=128,K=16 instruction whatever N is: see mma_issue_model",
+        "mma_issue_model": {"floor_ms": mma_floor_ms, "frac": mma_floor_ms / smp_launch_ms,
+                            "what": "60 tcgen05.mma per 512-pixel tile x 64 cycles (measured floor for N <= 128)"},
+        "hbm": {"achieved": smp_bytes_launch / smp_launch_ms / 1e6, "peak": peak_gbs, "unit": "GB/s",
+                "frac": smp_bytes_launch / smp_launch_ms / 1e6 / peak_gbs,
+                "note": "compulsory bytes only (240 FLOP/B: not the binding roofline)"},
+        "fp32_pipe_kernel": {"launch_ms": t_smp_fp32 / TM, "achieved": smp_flop_launch / (t_smp_fp32 / TM) / 1e9,
+                             "peak": fp32_peak, "unit": "TFLOP/s", "frac": smp_flop_launch / (t_smp_fp32 / TM) / 1e9 / fp32_peak,
+                             "note": "the FFMA2 kernel (algo='fp32', all other sampler configurations); peak = 148 SMs x 128 "
+                                     "lanes x 2 x %.0f MHz" % sm_max_mhz},
         "others": {"bin_events (bounds + tiles)": {
             "bound": "hbm", "call_ms": t_bin, "achieved": bin_bytes / t_bin / 1e6, "peak": peak_gbs,
             "unit": "GB/s", "frac": bin_bytes / t_bin / 1e6 / peak_gbs,
@@ -373,7 +394,7 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps, "pipeline": "3 streams (H2D / compute / D2H), 2 slots",
                     "checksum": checksum},
-            "gpu_launches": args.steps * (2 + TM),
+            "gpu_launches": args.steps * (2 + 1 + 2 * TM),   # bin (2) + weight pack + Tm steps + Tm (no-op) fall-back launches
             "clocks": clk, "roofline": roofline}
     if frames is not None:
         line["frames"] = frames

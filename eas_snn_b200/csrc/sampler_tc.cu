@@ -62,9 +62,9 @@ constexpr int OFF_BAR = OFF_X1 + X1_BYTES;
 constexpr int NBAR = 2 * S0 + 2 * S1 + 8;
 constexpr int OFF_MISC = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_MISC + 128 + 1024;          // + slack for the 1024 B alignment
-// warps 0-3 epilogue 1, 4-7 / 8-11 epilogue 2 (even / odd tiles), 12 MMA issuer, 13-16 producers
-constexpr int W_E2 = 4, W_MMA = 12, W_PROD = 13;
-constexpr int NUM_THREADS = 17 * 32;
+// warps 0-3 epilogue 1, 4-7 / 8-11 epilogue 2 (even / odd tiles), 12-14 MMA issuers, 15-18 producers
+constexpr int W_E2 = 4, W_MMA = 12, W_PROD = 15;
+constexpr int NUM_THREADS = 19 * 32;
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
 // TMEM columns: D1 = [in: x*w_hi (16) | x_hi*w_lo (16)][gate: same] x 2 buffers (64 apart);
@@ -282,10 +282,10 @@ sampler_tc_step_kernel(const StepArgs a, const TcGeo g, const uint8_t* __restric
   // ---- prologue: barriers, TMEM, weight image -> shared -------------------------------------
   if (threadIdx.x == 0) {
     for (int i = 0; i < S0; ++i) mbar_init(x0_full + i, 4), mbar_init(x0_empty + i, 1);
-    for (int i = 0; i < S1; ++i) mbar_init(x1_full + i, 4), mbar_init(x1_empty + i, 1);
+    for (int i = 0; i < S1; ++i) mbar_init(x1_full + i, 4), mbar_init(x1_empty + i, 2);
     for (int i = 0; i < 2; ++i) {
       mbar_init(d1_full + i, 1), mbar_init(d1_empty + i, 4);
-      mbar_init(d2_full + i, 1), mbar_init(d2_empty + i, 4);
+      mbar_init(d2_full + i, 2), mbar_init(d2_empty + i, 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -371,93 +371,110 @@ sampler_tc_step_kernel(const StepArgs a, const TcGeo g, const uint8_t* __restric
         if (lane == 0) mbar_arrive(x0_full + slot);
       }
     }
-  } else if (warp == W_MMA) {
-    // ===================== MMA issuer =====================
-    // The whole warp walks the (warp-uniform) schedule so that descriptors live in uniform registers;
-    // only the elected lane issues tcgen05.mma / tcgen05.commit.
+  } else if (warp >= W_MMA) {
+    // ===================== MMA issuers =====================
+    // Three issuing warps (layer 1; layer 2 hi plane; layer 2 lo plane): issuing is what bounds the
+    // tensor pipe for such small MMAs, and the three accumulator chains are independent.  Each warp
+    // walks its (warp-uniform) schedule so that descriptors live in uniform registers; only the
+    // elected lane issues tcgen05.mma / tcgen05.commit.
     const bool leader = elect_one();
-    {
-      // fp16 x fp16 -> fp32, M = 128, N = 32 / 16
-      constexpr uint32_t idesc32 = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
-      constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
-      // descriptor + (byte offset >> 4) moves the start address (all buffers sit below 256 KB)
-      const uint64_t wdesc = sw64_desc(sWB), x0desc = sw64_desc(sX0), x1desc = sw64_desc(sX1);
-      SegIter it(a, g);
-      Seg s;
-      int g0 = 0, g1 = 0, g2 = 0;  // global tile counters at the segment start
-      int w0 = 0, w1 = 0;          // X0 / X1 tiles already waited for (global)
+    // fp16 x fp16 -> fp32, M = 128, N = 32 / 16
+    constexpr uint32_t idesc32 = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+    constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+    // descriptor + (byte offset >> 4) moves the start address (all buffers sit below 256 KB)
+    const uint64_t wdesc = sw64_desc(sWB);
+    SegIter it(a, g);
+    Seg s;
+    if (warp == W_MMA) {
+      // ---------- layer 1: X0 -> D1 ----------
+      const uint64_t x0desc = sw64_desc(sX0);
+      int g0 = 0, g1 = 0;  // global tile counters at the segment start
+      int w0 = 0;          // X0 tiles already waited for (global)
       while (it.next(s)) {
-        const int base0 = (g0 % S0) * TILE, base1 = (g1 % S1) * TILE;
-        for (int itr = 0; itr < s.nt1 + 2; ++itr) {
-          if (itr < s.nt1) {
-            // ---------- layer 1, tile i: X0 -> D1 ----------
-            const int i = itr, gi = g1 + i, buf = gi & 1;
-            const int need0 = g0 + min(i + 2, s.nt0);
-            while (w0 < need0) mbar_wait(x0_full + (w0 % S0), (w0 / S0) & 1), ++w0;
-            mbar_wait(d1_empty + buf, ((gi >> 1) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t d_in = tmem_base + TM_D1 + buf * 64, d_gate = d_in + 32;
-            // rolled over ky (small code: the issuer must not become instruction-fetch bound); the ring
-            // position advances by QPR rows per filter row and wraps without a division
-            int pos = (base0 + i * TILE) % RS0;
-            uint64_t bd = wdesc;  // IN tile of ky (GATE tile 2048 B further)
+        int pos = (g0 % S0) * TILE;  // ring row of tile 0, advanced by TILE per tile
+        for (int i = 0; i < s.nt1; ++i) {
+          const int gi = g1 + i, buf = gi & 1;
+          const int need0 = g0 + min(i + 2, s.nt0);
+          while (w0 < need0) mbar_wait(x0_full + (w0 % S0), (w0 / S0) & 1), ++w0;
+          mbar_wait(d1_empty + buf, ((gi >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_in = tmem_base + TM_D1 + buf * 64, d_gate = d_in + 32;
+          // rolled over ky (small code); the ring position advances by QPR rows per filter row and
+          // wraps without a division
+          int pk = pos;
+          uint64_t bd = wdesc;  // IN tile of ky (GATE tile 2048 B further)
 #pragma unroll 1
-            for (int ky = 0; ky < 5; ++ky) {
-              const int pos1 = pos + 1 == RS0 ? 0 : pos + 1;
-              const uint64_t a0 = x0desc + (uint64_t)(pos * (ROWB >> 4)), a1 = x0desc + (uint64_t)(pos1 * (ROWB >> 4));
-              const uint32_t acc = ky == 0 ? 0u : 1u;
+          for (int ky = 0; ky < 5; ++ky) {
+            const int pk1 = pk + 1 == RS0 ? 0 : pk + 1;
+            const uint64_t a0 = x0desc + (uint64_t)(pk * (ROWB >> 4)), a1 = x0desc + (uint64_t)(pk1 * (ROWB >> 4));
+            const uint32_t acc = ky == 0 ? 0u : 1u;
+            if (leader) {
               // counts (hi | lo chunks) x IN tile, K-step h; spikes (| zero pad) x GATE tile (zero on step 0)
-              if (leader) tc_mma(d_in, a0, bd, idesc32, acc);
-              if (leader) tc_mma(d_in, a1, bd + 2, idesc32, 1u);
+              tc_mma(d_in, a0, bd, idesc32, acc);
+              tc_mma(d_in, a1, bd + 2, idesc32, 1u);
               if (!first) {
-                if (leader) tc_mma(d_gate, a0 + 2, bd + (2048 >> 4), idesc32, acc);
-                if (leader) tc_mma(d_gate, a1 + 2, bd + ((2048 >> 4) + 2), idesc32, 1u);
+                tc_mma(d_gate, a0 + 2, bd + (2048 >> 4), idesc32, acc);
+                tc_mma(d_gate, a1 + 2, bd + ((2048 >> 4) + 2), idesc32, 1u);
               }
-              bd += (uint64_t)(W1_KY >> 4);
-              pos += QPR;
-              if (pos >= RS0) pos -= RS0;
             }
-            if (leader) tc_commit(d1_full + buf);
-            if (leader) tc_commit(x0_empty + ((g0 + i) % S0));
+            bd += (uint64_t)(W1_KY >> 4);
+            pk += QPR;
+            if (pk >= RS0) pk -= RS0;
+          }
+          if (leader) {
+            tc_commit(d1_full + buf);
+            tc_commit(x0_empty + ((g0 + i) % S0));
             if (i == s.nt1 - 1)
-              for (int k = s.nt1; k < s.nt0; ++k) if (leader) tc_commit(x0_empty + ((g0 + k) % S0));
+              for (int k = s.nt1; k < s.nt0; ++k) tc_commit(x0_empty + ((g0 + k) % S0));
           }
-          const int j = itr - 2;
-          if (j >= 0 && j < s.nt2) {
-            // ---------- layer 2, tile j: X1 -> D2 ----------
-            const int gj = g2 + j, buf = gj & 1;
-            const int need1 = g1 + min(j + 2, s.nt1);
-            while (w1 < need1) mbar_wait(x1_full + (w1 % S1), (w1 / S1) & 1), ++w1;
-            mbar_wait(d2_empty + buf, ((gj >> 1) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t d2 = tmem_base + TM_D2 + buf * 64;
-            // x_hi * [w_hi | w_lo] -> columns 0..31, x_lo * w_hi -> columns 32..47 (two independent chains)
-            int pos = (base1 + j * TILE) % RS1;
-            uint64_t bd = wdesc + (uint64_t)(OFF_W2 >> 4);  // tiles A, B of (ky, h = 0); h = 1 is W2_KYH further
-#pragma unroll 1
-            for (int ky = 0; ky < 5; ++ky) {
-              const int pos1 = pos + 1 == RS1 ? 0 : pos + 1;
-              const uint64_t a0 = x1desc + (uint64_t)(pos * (ROWB >> 4)), a1 = x1desc + (uint64_t)(pos1 * (ROWB >> 4));
-              const uint32_t acc = ky == 0 ? 0u : 1u;
-              if (leader) tc_mma(d2, a0, bd, idesc32, acc);
-              if (leader) tc_mma(d2 + 32, a0 + (X1_PLANE >> 4), bd + (2048 >> 4), idesc16, acc);
-              if (leader) tc_mma(d2, a0 + 2, bd + 2, idesc32, 1u);
-              if (leader) tc_mma(d2 + 32, a0 + ((X1_PLANE >> 4) + 2), bd + ((2048 >> 4) + 2), idesc16, 1u);
-              if (leader) tc_mma(d2, a1, bd + (W2_KYH >> 4), idesc32, 1u);
-              if (leader) tc_mma(d2 + 32, a1 + (X1_PLANE >> 4), bd + ((W2_KYH + 2048) >> 4), idesc16, 1u);
-              if (leader) tc_mma(d2, a1 + 2, bd + ((W2_KYH >> 4) + 2), idesc32, 1u);
-              if (leader) tc_mma(d2 + 32, a1 + ((X1_PLANE >> 4) + 2), bd + (((W2_KYH + 2048) >> 4) + 2), idesc16, 1u);
-              bd += (uint64_t)((2 * W2_KYH) >> 4);
-              pos += QPR;
-              if (pos >= RS1) pos -= RS1;
-            }
-            if (leader) tc_commit(d2_full + buf);
-            if (leader) tc_commit(x1_empty + ((g1 + j) % S1));
-            if (j == s.nt2 - 1)
-              for (int k = s.nt2; k < s.nt1; ++k) if (leader) tc_commit(x1_empty + ((g1 + k) % S1));
-          }
+          pos += TILE;
+          if (pos >= RS0) pos -= RS0;
         }
-        g0 += s.nt0, g1 += s.nt1, g2 += s.nt2;
+        g0 += s.nt0, g1 += s.nt1;
+      }
+    } else {
+      // ---------- layer 2, plane `pl` of X1 -> D2: x_hi * [w_hi | w_lo] -> columns 0..31 (tile A),
+      //            x_lo * w_hi -> columns 32..47 (tile B) ----------
+      const int pl = warp - W_MMA - 1;
+      const uint64_t x1desc = sw64_desc(sX1) + (uint64_t)(pl * (X1_PLANE >> 4));
+      const uint64_t wd2 = wdesc + (uint64_t)((OFF_W2 + pl * 2048) >> 4);
+      const uint32_t idesc = pl == 0 ? idesc32 : idesc16;
+      int g1 = 0, g2 = 0, w1 = 0;
+      while (it.next(s)) {
+        int pos = (g1 % S1) * TILE;
+        for (int j = 0; j < s.nt2; ++j) {
+          const int gj = g2 + j, buf = gj & 1;
+          const int need1 = g1 + min(j + 2, s.nt1);
+          while (w1 < need1) mbar_wait(x1_full + (w1 % S1), (w1 / S1) & 1), ++w1;
+          mbar_wait(d2_empty + buf, ((gj >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d2 = tmem_base + TM_D2 + buf * 64 + pl * 32;
+          int pk = pos;
+          uint64_t bd = wd2;  // tile of (ky, h = 0); h = 1 is W2_KYH further
+#pragma unroll 1
+          for (int ky = 0; ky < 5; ++ky) {
+            const int pk1 = pk + 1 == RS1 ? 0 : pk + 1;
+            const uint64_t a0 = x1desc + (uint64_t)(pk * (ROWB >> 4)), a1 = x1desc + (uint64_t)(pk1 * (ROWB >> 4));
+            if (leader) {
+              tc_mma(d2, a0, bd, idesc, ky == 0 ? 0u : 1u);
+              tc_mma(d2, a0 + 2, bd + 2, idesc, 1u);
+              tc_mma(d2, a1, bd + (W2_KYH >> 4), idesc, 1u);
+              tc_mma(d2, a1 + 2, bd + ((W2_KYH >> 4) + 2), idesc, 1u);
+            }
+            bd += (uint64_t)((2 * W2_KYH) >> 4);
+            pk += QPR;
+            if (pk >= RS1) pk -= RS1;
+          }
+          if (leader) {
+            tc_commit(d2_full + buf);
+            tc_commit(x1_empty + ((g1 + j) % S1));
+            if (j == s.nt2 - 1)
+              for (int k = s.nt2; k < s.nt1; ++k) tc_commit(x1_empty + ((g1 + k) % S1));
+          }
+          pos += TILE;
+          if (pos >= RS1) pos -= RS1;
+        }
+        g1 += s.nt1, g2 += s.nt2;
       }
     }
   } else if (warp < 4) {
