@@ -357,8 +357,7 @@ def run_ours(args):
     tensor_peak = float(peaks.get("bf16_tflops", 1590.0))     # burst figure: the kernel is timed alone
     # issue model of the tensor-core sampler: 60 MMAs (M=128, K=16, N<=32) per 128-quad
     # tile, 64 cycles each (scripts/umma_rate_probe.cu), ~69.5 tiles per SM per launch on this workload
-    tiles_per_sm = BATCH * 4 * (H + 4 * 148.0 / (BATCH * 4) * 2) * 21 / 128.0 / 148.0
-    mma_floor_ms = tiles_per_sm * 60 * 64 / (sm_max_mhz * 1e3)
+    mma_floor_ms = tc_issue_floor_cycles(BATCH, H, W) / (sm_max_mhz * 1e3)
     roofline = {
         "kernel": "sampler_tc_step_kernel (dominant: %.0f%% of the step)" % (100.0 * t_smp / (t_smp + t_bin)),
         "bound": "tensor", "achieved": smp_flop_launch / smp_launch_ms / 1e9, "peak": tensor_peak, "unit": "TFLOP/s",
@@ -405,6 +404,28 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def tc_issue_floor_cycles(B: int, H: int, W: int, n_sm: int = 148) -> float:
+    """MMA-issue floor of one sampler step launch (the schedule of sampler_tc.cu restated): every SM walks
+    its share of (image, strip, row) space in segments; a segment of n rows costs ceil((n+4)*QPR/128) layer-1
+    tiles x 20 MMAs + ceil(n*QPR/128) layer-2 tiles x 40 MMAs, 64 cycles per MMA; the slowest SM counts."""
+    max_tw = 4 * (31 - 2)
+    ns = -(-W // max_tw)
+    tw = (-(-W // ns) + 3) // 4 * 4
+    qpr = tw // 4 + 2
+    total = B * ns * H
+    grid = min(n_sm, max(1, -(-total // 8)))
+    worst = 0
+    for c in range(grid):
+        r, r_end, cyc = total * c // grid, total * (c + 1) // grid, 0
+        while r < r_end:
+            ya = r % H
+            n = min(H - ya, r_end - r)
+            cyc += (-(-((n + 4) * qpr) // 128) * 20 + -(-(n * qpr) // 128) * 40) * 64
+            r += n
+        worst = max(worst, cyc)
+    return float(worst)
 
 
 def EAS_FP32_PEAK(sm_mhz: float) -> float:

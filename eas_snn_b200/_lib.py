@@ -55,6 +55,10 @@ SIGNATURES = {
                                  _P, _P, C.c_size_t, _P]),
     "eas_bin_events_ex": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
                                     _P, _P, C.c_size_t, _P, C.c_int, C.c_int]),
+    "eas_dat_windows": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _P, _P]),
+    "eas_bin_dat_ws_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
+    "eas_bin_dat": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, _P,
+                              C.c_int, C.c_int]),
     "eas_sampler_fwd_ws_bytes": (C.c_size_t, [C.POINTER(SamplerCfg)]),
     "eas_sampler_fwd": (C.c_int, [C.POINTER(SamplerCfg), _P, C.POINTER(SamplerPtrs), _P, _P, _P, _P,
                                   C.c_size_t, _P]),

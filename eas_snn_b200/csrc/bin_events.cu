@@ -22,35 +22,65 @@
 
 namespace {
 
+// Where the events come from.  SoaSrc: the reference's events_struct de-interleaved (x, y, t, p) with
+// windows back to back (offsets[B+1]).  DatSrc: raw 8-byte PSEE .dat Event2D records
+// {u32 t; u32 x:14 | y:14 << 14 | p << 28} (dat_events_tools.py:24, 46-51) with one [first, last) record
+// range per window (eas_dat_windows).
+struct SoaSrc {
+  const int16_t* __restrict__ x;
+  const int16_t* __restrict__ y;
+  const int64_t* __restrict__ t;
+  const uint8_t* __restrict__ p;
+  const int64_t* __restrict__ offsets;
+  __device__ __forceinline__ int64_t begin(int64_t b) const { return offsets[b]; }
+  __device__ __forceinline__ int64_t end(int64_t b) const { return offsets[b + 1]; }
+  __device__ __forceinline__ int64_t time(int64_t i) const { return t[i]; }
+  __device__ __forceinline__ void xyc(int64_t i, int& xi, int& yi, int& ci) const {
+    xi = x[i], yi = y[i], ci = p[i] != 0;
+  }
+};
+struct DatSrc {
+  const uint2* __restrict__ rec;
+  const int64_t* __restrict__ ranges;
+  __device__ __forceinline__ int64_t begin(int64_t b) const { return ranges[2 * b]; }
+  __device__ __forceinline__ int64_t end(int64_t b) const { return ranges[2 * b + 1]; }
+  __device__ __forceinline__ int64_t time(int64_t i) const { return (int64_t)rec[i].x; }
+  __device__ __forceinline__ void xyc(int64_t i, int& xi, int& yi, int& ci) const {
+    const uint32_t w = rec[i].y;
+    xi = (int)(w & 16383u), yi = (int)((w >> 14) & 16383u), ci = (int)((w >> 28) & 1u);
+  }
+};
+
 constexpr int kSmemThreads = 512;
 constexpr int kSlabMaxBytes = 72 * 1024;   // 3 CTAs/SM: phases of different CTAs overlap
 constexpr int kChunk = 65535;
 
 // One warp per (window, boundary): 32-ary search on the sorted timestamps (4 dependent loads for
 // 1e5 events instead of 17).  Also resets the work counter of the tile kernel.
+template <typename SRC>
 __global__ void __launch_bounds__(128)
-bin_bounds_kernel(const int64_t* __restrict__ t, const int64_t* __restrict__ offsets, int64_t B, int Tm,
-                  int64_t* __restrict__ bounds, unsigned int* __restrict__ work_counter) {
+bin_bounds_kernel(const SRC src, int64_t B, int Tm, int64_t* __restrict__ bounds,
+                  unsigned int* __restrict__ work_counter) {
   const int lane = threadIdx.x & 31;
   const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (gid == 0 && lane == 0) *work_counter = 0u;
   if (gid >= B * (Tm + 1)) return;
   const int64_t b = gid / (Tm + 1);
   const int k = (int)(gid - b * (Tm + 1));
-  const int64_t s = offsets[b], e = offsets[b + 1];
+  const int64_t s = src.begin(b), e = src.end(b);
   if (e <= s) {
     if (lane == 0) bounds[gid] = s;
     return;
   }
-  const int64_t t0 = t[s];
-  const int64_t tw = (t[e - 1] - t0) / Tm;  // sorted => non-negative => trunc == floor
+  const int64_t t0 = src.time(s);
+  const int64_t tw = (src.time(e - 1) - t0) / Tm;  // sorted => non-negative => trunc == floor
   const int64_t key = t0 + (int64_t)k * tw;
   int64_t lo = s, hi = e;  // answer (first index with t[i] >= key) is in [lo, hi]
   while (hi - lo > 0) {
     const int64_t len = hi - lo;
     const int64_t step = (len + 31) / 32;  // probes at lo + (lane+1)*step - 1
     const int64_t pi = lo + (int64_t)(lane + 1) * step - 1;
-    const bool less = pi < hi ? (t[pi] < key) : false;  // out-of-range probes count as ">= key"
+    const bool less = pi < hi ? (src.time(pi) < key) : false;  // out-of-range probes count as ">= key"
     const unsigned m = __ballot_sync(0xffffffffu, less);
     const int nless = __popc(m);  // sorted => the lanes with t < key are a prefix
     const int64_t nlo = lo + (int64_t)nless * step;
@@ -77,10 +107,9 @@ template <> struct Cvt<float> {  // counts < 2^24 are exact in fp32
   }
 };
 
-template <typename OUT_T>
+template <typename OUT_T, typename SRC>
 __global__ void __launch_bounds__(kSmemThreads)
-bin_hist_smem_kernel(const int16_t* __restrict__ x, const int16_t* __restrict__ y,
-                     const uint8_t* __restrict__ p, const int64_t* __restrict__ bounds, int64_t n_items,
+bin_hist_smem_kernel(const SRC src, const int64_t* __restrict__ bounds, int64_t n_items,
                      int H, int W, int Tm, int n_slabs, int slab_rows, uint32_t* __restrict__ hist,
                      unsigned int* __restrict__ work_counter) {
   extern __shared__ __align__(16) uint32_t cnt[];  // ceil(slab_rows*W/2) words, two 16-bit counters per word
@@ -114,9 +143,9 @@ bin_hist_smem_kernel(const int16_t* __restrict__ x, const int16_t* __restrict__ 
       const int64_t ce = (e - cs > kChunk) ? cs + kChunk : e;
 #pragma unroll 4
       for (int64_t i = cs + threadIdx.x; i < ce; i += kSmemThreads) {
-        const int yi = (int)y[i] - y_lo;
-        const int ci = p[i] != 0;
-        const int xi = x[i];
+        int xi, yi, ci;
+        src.xyc(i, xi, yi, ci);
+        yi -= y_lo;
         if (ci == c && (unsigned)xi < (unsigned)W && (unsigned)yi < (unsigned)rows) {
           const int pix = yi * W + xi;
           atomicAdd(cnt + (pix >> 1), 1u << ((pix & 1) << 4));
@@ -208,7 +237,181 @@ bin_hist_global_kernel(const int16_t* __restrict__ x, const int16_t* __restrict_
   }
 }
 
+// Event-parallel counting for windows given as arbitrary record ranges (the .dat path): every
+// micro-bin segment is cut into chunks of kRangeChunk events that are dealt round-robin to the CTAs.
+constexpr int kRangeChunk = 4096;
+
+template <typename OUT_T, typename SRC>
+__global__ void __launch_bounds__(256)
+bin_hist_ranges_kernel(const SRC src, const int64_t* __restrict__ bounds, int64_t B, int H, int W, int Tm,
+                       OUT_T* __restrict__ hist) {
+  const int64_t HW = (int64_t)H * W;
+  const int64_t n_seg = B * Tm;
+  for (int64_t seg = 0; seg < n_seg; ++seg) {
+    const int64_t b = seg / Tm;
+    const int k = (int)(seg - b * Tm);
+    const int64_t s = bounds[b * (Tm + 1) + k], e = bounds[b * (Tm + 1) + k + 1];
+    const int64_t n_chunks = (e - s + kRangeChunk - 1) / kRangeChunk;
+    OUT_T* __restrict__ h = hist + seg * 2 * HW;
+    // chunk j of segment seg belongs to CTA (j + 7*seg) mod gridDim.x
+    int64_t j = ((int64_t)blockIdx.x - 7 * seg) % (int64_t)gridDim.x;
+    if (j < 0) j += gridDim.x;
+    for (; j < n_chunks; j += gridDim.x) {
+      const int64_t cs = s + j * kRangeChunk;
+      const int64_t ce = cs + kRangeChunk < e ? cs + kRangeChunk : e;
+      for (int64_t i = cs + threadIdx.x; i < ce; i += 256) {
+        int xi, yi, ci;
+        src.xyc(i, xi, yi, ci);
+        if ((unsigned)xi < (unsigned)W && (unsigned)yi < (unsigned)H) atomicAdd(h + ci * HW + (int64_t)yi * W + xi, (OUT_T)1);
+      }
+    }
+  }
+}
+
+// tile geometry shared by both front doors
+struct SlabGeo {
+  int n_slabs, slab_rows;
+  size_t smem;
+  bool fits;
+};
+SlabGeo slab_geo(int H, int W) {
+  SlabGeo g;
+  const int64_t HW = (int64_t)H * W;
+  g.n_slabs = (int)eas_ceil_div(HW * 2, kSlabMaxBytes);
+  if (g.n_slabs > H) g.n_slabs = H;
+  g.slab_rows = (int)eas_ceil_div(H, g.n_slabs);
+  g.n_slabs = (int)eas_ceil_div(H, g.slab_rows);
+  g.smem = (size_t)((((int64_t)g.slab_rows * W + 1) / 2 + 3) / 4 * 4) * 4;
+  g.fits = g.smem <= (size_t)kSlabMaxBytes + 4096 && g.n_slabs <= 8;
+  return g;
+}
+
+template <typename OUT_T, typename SRC>
+int launch_tiles(const SRC& src, const int64_t* bounds, int64_t n_items, int H, int W, int Tm, const SlabGeo& g,
+                 void* hist, unsigned int* counter, cudaStream_t stream) {
+  auto kern = bin_hist_smem_kernel<OUT_T, SRC>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+  if (e != cudaSuccess) return (int)e;
+  const int per_sm = (int)((220 * 1024) / (g.smem + 1024));
+  int64_t grid = (int64_t)EAS_NUM_SMS * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
+  if (grid > n_items) grid = n_items;
+  kern<<<(unsigned)grid, kSmemThreads, g.smem, stream>>>(src, bounds, n_items, H, W, Tm, g.n_slabs, g.slab_rows,
+                                                         (uint32_t*)hist, counter);
+  EAS_LAUNCH_CHECK();
+  return EAS_OK;
+}
+
+// ---- .dat window search (one thread per labelled timestamp) ---------------------------------
+// first record in [lo, hi) with t >= key
+__device__ __forceinline__ int64_t dat_lower_bound(const uint2* __restrict__ rec, int64_t lo, int64_t hi, int64_t key) {
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)rec[mid].x < key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void dat_windows_kernel(const uint2* __restrict__ rec, int64_t n, const int64_t* __restrict__ t_label,
+                                   int64_t B, int64_t win_lo, int64_t win_hi, int max_backoff,
+                                   int64_t* __restrict__ ranges) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int64_t delta = win_hi - win_lo;
+  const int64_t total = n > 0 ? (int64_t)rec[n - 1].x : 0;   // PSEELoader.total_time()
+  int64_t cur = t_label[b] + win_lo;
+  int64_t lo = 0, hi = 0;
+  for (int trigger = 0;; ++trigger) {
+    // ---- PSEELoader.seek_time(cur), psee_loader.py:196-238 ----
+    int64_t cursor, now;
+    bool done;
+    if (cur > total) {
+      cursor = n, now = total + 1, done = true;
+    } else if (cur <= 0) {
+      cursor = 0, now = 0, done = false;
+    } else {
+      int64_t low = 0, high = n;
+      bool hit = false;
+      while (high - low > 100000) {                 // term_criterion
+        const int64_t middle = (low + high) / 2;
+        const int64_t mid = (int64_t)rec[middle].x;
+        if (mid > cur) high = middle;
+        else if (mid < cur) low = middle + 1;
+        else {                                       // the probe read left the file cursor one event further
+          cursor = middle + 1, hit = true;
+          break;
+        }
+      }
+      if (!hit) cursor = dat_lower_bound(rec, low, high, cur);
+      now = cur, done = cursor >= n;
+    }
+    // ---- PSEELoader.load_delta_t(delta), psee_loader.py:128-171 ----
+    lo = hi = cursor;
+    if (!done && cursor < n) hi = dat_lower_bound(rec, cursor, n, now + delta);
+    // ---- GEN1Dataset.search_events zero_trigger loop, gen1.py:223-232 ----
+    if (hi > lo || trigger > max_backoff) break;
+    cur -= delta;
+  }
+  ranges[2 * b] = lo;
+  ranges[2 * b + 1] = hi;
+}
+
 }  // namespace
+
+extern "C" int eas_dat_windows(const void* rec, int64_t n_rec, const int64_t* t_label, int64_t B, int64_t win_lo,
+                               int64_t win_hi, int32_t max_backoff, int64_t* ranges, void* stream) {
+  EAS_REQUIRE(n_rec >= 0 && B >= 0 && win_hi > win_lo && max_backoff >= 0, EAS_E_SHAPE);
+  if (B == 0) return EAS_OK;
+  EAS_REQUIRE(t_label && ranges && (rec || n_rec == 0), EAS_E_NULL);
+  EAS_REQUIRE((uintptr_t)rec % 8 == 0, EAS_E_ALIGN);
+  dat_windows_kernel<<<(unsigned)eas_ceil_div(B, 64), 64, 0, (cudaStream_t)stream>>>(
+      (const uint2*)rec, n_rec, t_label, B, win_lo, win_hi, max_backoff, ranges);
+  EAS_LAUNCH_CHECK();
+  return EAS_OK;
+}
+
+extern "C" size_t eas_bin_dat_ws_bytes(int64_t B, int Tm) { return eas_bin_events_ws_bytes(B, Tm); }
+
+extern "C" int eas_bin_dat(const void* rec, int64_t n_rec, const int64_t* ranges, int64_t B, int H, int W, int Tm,
+                           void* hist, void* ws, size_t ws_bytes, void* stream_, int strategy, int out_dtype) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EAS_REQUIRE(B >= 0 && n_rec >= 0, EAS_E_SHAPE);
+  EAS_REQUIRE(H > 0 && W > 0 && H <= 16384 && W <= 16384 && Tm > 0 && Tm <= 1024, EAS_E_SHAPE);
+  EAS_REQUIRE((int64_t)H * W < (1ll << 30), EAS_E_SHAPE);
+  EAS_REQUIRE(strategy >= 0 && strategy <= 2, EAS_E_UNSUPPORTED);
+  EAS_REQUIRE(out_dtype == EAS_I32 || out_dtype == EAS_F32, EAS_E_UNSUPPORTED);
+  if (B == 0) return EAS_OK;
+  EAS_REQUIRE(ranges && hist && ws && (rec || n_rec == 0), EAS_E_NULL);
+  EAS_REQUIRE(ws_bytes >= eas_bin_dat_ws_bytes(B, Tm), EAS_E_WORKSPACE);
+  EAS_REQUIRE(((uintptr_t)rec % 8 == 0) && ((uintptr_t)hist % 16 == 0) && ((uintptr_t)ws % 8 == 0), EAS_E_ALIGN);
+  int64_t* bounds = (int64_t*)ws;
+  unsigned int* counter =
+      (unsigned int*)((char*)ws + eas_align_up((size_t)B * (size_t)(Tm + 1) * sizeof(int64_t), 256));
+  const DatSrc src{(const uint2*)rec, ranges};
+  const int64_t nb = B * (Tm + 1);
+  bin_bounds_kernel<DatSrc><<<(unsigned)eas_ceil_div(nb * 32, 128), 128, 0, stream>>>(src, B, Tm, bounds, counter);
+  EAS_LAUNCH_CHECK();
+  const SlabGeo g = slab_geo(H, W);
+  const int64_t n_items = B * Tm * 2 * g.n_slabs;
+  // window lengths live on the device: "auto" takes the write-once tiles whenever the frame fits them
+  // (event windows of tens of ms), the event-parallel kernel otherwise
+  if (strategy == 0) strategy = (g.fits && n_items >= EAS_NUM_SMS) ? 2 : 1;
+  if (strategy == 2) {
+    EAS_REQUIRE(g.fits, EAS_E_UNSUPPORTED);
+    return out_dtype == EAS_F32 ? launch_tiles<float>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream)
+                                : launch_tiles<int32_t>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream);
+  }
+  const int64_t HW = (int64_t)H * W;
+  cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)B * Tm * 2 * HW * sizeof(int32_t), stream);
+  if (e != cudaSuccess) return (int)e;
+  const unsigned grid = EAS_NUM_SMS * 8;
+  if (out_dtype == EAS_F32)
+    bin_hist_ranges_kernel<float><<<grid, 256, 0, stream>>>(src, bounds, B, H, W, Tm, (float*)hist);
+  else
+    bin_hist_ranges_kernel<int32_t><<<grid, 256, 0, stream>>>(src, bounds, B, H, W, Tm, (int32_t*)hist);
+  EAS_LAUNCH_CHECK();
+  return EAS_OK;
+}
 
 extern "C" size_t eas_bin_events_ws_bytes(int64_t B, int Tm) {
   if (B <= 0 || Tm <= 0) return 0;
@@ -238,17 +441,14 @@ extern "C" int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64
       (unsigned int*)((char*)ws + eas_align_up((size_t)B * (size_t)(Tm + 1) * sizeof(int64_t), 256));
   const int64_t HW = (int64_t)H * W;
   const int64_t nb = B * (Tm + 1);
-  bin_bounds_kernel<<<(unsigned)eas_ceil_div(nb * 32, 128), 128, 0, stream>>>(t, offsets, B, Tm, bounds, counter);
+  const SoaSrc src{x, y, t, p, offsets};
+  bin_bounds_kernel<SoaSrc><<<(unsigned)eas_ceil_div(nb * 32, 128), 128, 0, stream>>>(src, B, Tm, bounds, counter);
   EAS_LAUNCH_CHECK();
 
   // row slabs so that one slab of 16-bit counters fits the per-CTA shared memory budget
-  int n_slabs = (int)eas_ceil_div(HW * 2, kSlabMaxBytes);
-  if (n_slabs > H) n_slabs = H;
-  const int slab_rows = (int)eas_ceil_div(H, n_slabs);
-  n_slabs = (int)eas_ceil_div(H, slab_rows);
-  const size_t smem = (size_t)((((int64_t)slab_rows * W + 1) / 2 + 3) / 4 * 4) * 4;
-  const bool fits = smem <= (size_t)kSlabMaxBytes + 4096 && n_slabs <= 8;
-  const int64_t n_items = B * Tm * 2 * n_slabs;
+  const SlabGeo g = slab_geo(H, W);
+  const bool fits = g.fits;
+  const int64_t n_items = B * Tm * 2 * g.n_slabs;
   if (strategy == 0) {
     // tiles: every event of a segment is scanned by 2*n_slabs CTAs (from L2); only worth it while
     // the write-once output dominates, i.e. for short windows; long windows go event-parallel.
@@ -257,15 +457,8 @@ extern "C" int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64
   }
   if (strategy == 2) {
     EAS_REQUIRE(fits, EAS_E_UNSUPPORTED);
-    auto kern = out_dtype == EAS_F32 ? bin_hist_smem_kernel<float> : bin_hist_smem_kernel<int32_t>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    const int per_sm = (int)((220 * 1024) / (smem + 1024));
-    int64_t grid = (int64_t)EAS_NUM_SMS * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
-    if (grid > n_items) grid = n_items;
-    kern<<<(unsigned)grid, kSmemThreads, smem, stream>>>(x, y, p, bounds, n_items, H, W, Tm, n_slabs, slab_rows,
-                                                         (uint32_t*)hist, counter);
-    EAS_LAUNCH_CHECK();
+    return out_dtype == EAS_F32 ? launch_tiles<float>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream)
+                                : launch_tiles<int32_t>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream);
   } else {
     cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)B * Tm * 2 * HW * sizeof(int32_t), stream);
     if (e != cudaSuccess) return (int)e;

@@ -190,3 +190,10 @@ class AdaptiveRSNNEmbedding(nn.Module):
         """
         hist = bin_events(x, y, t, p, offsets, H, W, self.nb_steps, strategy=strategy, dtype=torch.float32)
         return self.forward(hist)
+
+    def forward_dat(self, records, ranges, H: int, W: int, strategy: str = "auto"):
+        """Raw PSEE ``.dat`` records + one record range per window (:func:`eas_snn_b200.psee.dat_windows`)
+        -> adaptive frames ``[Ts, B, 2, H, W]``: decode, binning and sampling without leaving the GPU."""
+        from .psee import bin_dat
+        hist = bin_dat(records, ranges, H, W, self.nb_steps, strategy=strategy, dtype=torch.float32)
+        return self.forward(hist)

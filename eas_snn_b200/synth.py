@@ -51,3 +51,46 @@ def gen1_batch(B: int, cfg: int = 2, first_sample: int = 0):
 def mpx_batch(B: int, cfg: int = 3, first_sample: int = 0):
     """1Mpx-rate windows: N ~ LogUniform[5e5, 5e6] at 720x1280."""
     return make_batch(cfg, B, MPX[0], MPX[1], 5e5, 5e6, first_sample)
+
+
+def dat_stream(seed: int, n: int, H: int, W: int, span_us: int, t_start: int = 1000, gap=None):
+    """A time-sorted synthetic recording for the PSEE ``.dat`` path: (x, y, t, p) with ``t`` in
+    ``[t_start, t_start + span_us)``; ``gap = (a, b)`` removes every event with ``a <= t < b``.
+    Regenerated from the seed by the golden script and by the tests (the fixture stores outputs only)."""
+    rng = np.random.default_rng(seed)
+    t = np.sort(rng.integers(t_start, t_start + span_us, int(n), dtype=np.int64))
+    x = rng.integers(0, W, int(n), dtype=np.int64)
+    y = rng.integers(0, H, int(n), dtype=np.int64)
+    p = (rng.random(int(n)) < 0.5).astype(np.uint8)
+    if gap is not None:
+        keep = (t < gap[0]) | (t >= gap[1])
+        x, y, t, p = x[keep], y[keep], t[keep], p[keep]
+    return x.astype(np.int16), y.astype(np.int16), t, p
+
+
+# name -> (stream kwargs, window (us), num_slice, Tm): shared by tests/golden/make_golden.py and the tests
+DAT_CASES = {
+    "small_24x32": (dict(seed=11, n=30_000, H=24, W=32, span_us=2_000_000), (-50_000, 0), 1, 4),
+    "gap_backoff": (dict(seed=12, n=40_000, H=24, W=32, span_us=2_000_000, gap=(600_000, 1_000_000)), (-50_000, 0), 3, 4),
+    "dense_bisect": (dict(seed=13, n=260_000, H=24, W=32, span_us=1_000_000), (-20_000, 0), 1, 5),
+    "long_window": (dict(seed=14, n=50_000, H=40, W=48, span_us=1_500_000, t_start=0), (-200_000, 0), 2, 4),
+}
+
+
+def dat_label_times(name: str, t: np.ndarray, window, seed: int = 0):
+    """Label timestamps that exercise every branch of the reference's window search: before the first
+    event, inside, exactly on event timestamps, inside a hole, past the end, and (for streams with more
+    than 100000 events) exactly on the bisection probes of PSEELoader.seek_time."""
+    rng = np.random.default_rng(1000 + seed)
+    n = len(t)
+    ts = [int(t[0]) - 10, int(t[0]) + 5, int(t[0]) - window[0], int(t[n // 3]) - window[0], int(t[n // 2]),
+          int(t[-1]), int(t[-1]) - window[0], int(t[-1]) - window[0] + 1, int(t[-1]) + 10 * (window[1] - window[0])]
+    ts += [int(v) for v in rng.integers(int(t[0]), int(t[-1]), 12)]
+    if name == "gap_backoff":
+        ts += [650_000, 700_000, 790_000, 800_000, 860_000, 990_000, 1_000_000, 1_049_000]
+    lo, hi = 0, n
+    while hi - lo > 100000:                       # the probes of the reference's bisection for a late target
+        mid = (lo + hi) // 2
+        ts += [int(t[mid]) - window[0], int(t[mid]) - window[0] + 1]
+        lo = mid + 1
+    return np.asarray(ts, dtype=np.int64)

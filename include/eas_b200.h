@@ -68,6 +68,29 @@ int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64_t* t, cons
                       void* hist, void* ws, size_t ws_bytes, void* stream, int strategy, int out_dtype);
 
 /* ------------------------------------------------------------------------------------------
+ * (f-1) PSEE .dat recordings on the GPU.  rec = n_rec raw 8-byte little-endian Event2D records
+ *       {uint32 t_us; uint32 x:14 | y:14 << 14 | p << 28}, time-sorted, resident in device memory:
+ *       the payload of a `_td.dat` file after its text header, as the reference's loader reads it
+ *       (yolox/utils/psee_loader/io/dat_events_tools.py:24, 40-51).
+ *
+ * eas_dat_windows replaces GEN1Dataset.search_events (yolox/data/datasets/gen1.py:217-236) over
+ * PSEELoader.seek_time / load_delta_t (psee_loader.py:128-238): for every label time t_label[b] the
+ * window is [t + win_lo, t + win_hi) us; while it holds no event it is moved back by its own
+ * length, at most max_backoff + 1 times (the reference's zero_trigger loop with
+ * max_backoff = slice_args['num_slice']).  ranges[b] = {first record, one past the last record}.
+ * Reproduces the loader exactly, including seek_time's exact-hit cursor advance while more than
+ * 100000 records remain in its bisection.
+ *
+ * eas_bin_dat = eas_bin_events_ex on record ranges (decode + slice_events + agrregate('micro_sum'),
+ * gen1.py:313-360): hist [B][Tm][2][H][W] int32 or f32.
+ * ---------------------------------------------------------------------------------------- */
+int eas_dat_windows(const void* rec, int64_t n_rec, const int64_t* t_label, int64_t B, int64_t win_lo,
+                    int64_t win_hi, int32_t max_backoff, int64_t* ranges, void* stream);
+size_t eas_bin_dat_ws_bytes(int64_t B, int Tm);
+int eas_bin_dat(const void* rec, int64_t n_rec, const int64_t* ranges, int64_t B, int H, int W, int Tm,
+                void* hist, void* ws, size_t ws_bytes, void* stream, int strategy, int out_dtype);
+
+/* ------------------------------------------------------------------------------------------
  * (a-2) Adaptive event sampler.  Replaces AdaptiveRSNNEmbedding.forward / update,
  *       yolox/models/embedding.py:132-226 with the Rectangle surrogate, activation.py:17-30.
  *

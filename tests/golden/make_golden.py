@@ -2,7 +2,7 @@
 
     python tests/golden/make_golden.py          # needs /root/reference (read-only)
 
-Outputs (small, committed): tests/golden/binning.npz, sampler.npz, backbone.npz.
+Outputs (small, committed): tests/golden/binning.npz, sampler.npz, backbone.npz, psee.npz.
 The reference is imported in place through ``oracle/ref_loader.py``; nothing is copied from it.
 ``/root/reference`` does not exist on the GPU box, so tests only ever read the .npz files.
 """
@@ -165,12 +165,74 @@ def make_backbone():
     print("backbone.npz written, params:", sum(p.numel() for p in bb.parameters()))
 
 
+def make_psee(gen1):
+    """PSEE .dat path: synthetic recordings written in the reference's format (records by its own
+    ``write_event_buffer``; the header by hand because the reference's ``write_header`` references an
+    undefined name), searched by the reference's ``GEN1Dataset.search_events`` -> ``PSEELoader`` and
+    aggregated by ``agrregate('micro_sum')``.  The fixture keeps outputs only; inputs come from seeds."""
+    import importlib
+    import tempfile
+    dat_tools = importlib.import_module("yolox.utils.psee_loader.io.dat_events_tools")
+    # numpy >= 2 refuses `python_int // np.uint8(8)` in PSEELoader.__init__ (the reference targets numpy 1.x):
+    # hand it the same header values as Python ints; nothing else of the reference is touched
+    _parse = dat_tools.parse_header
+    dat_tools.parse_header = lambda f: tuple(int(v) if isinstance(v, np.integer) else v for v in _parse(f))
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, (kw, window, num_slice, Tm) in synth.DAT_CASES.items():
+            x, y, t, p = synth.dat_stream(**kw)
+            H, W = kw["H"], kw["W"]
+            path = os.path.join(tmp, name + "_td.dat")
+            with open(path, "w") as f:
+                f.write("%% Data file containing Event2D events.\n%% Version 2\n%% Height %d\n%% Width %d\n" % (H, W))
+                np.array([0, 8], dtype=np.uint8).tofile(f)
+                f.flush()
+                buf = np.zeros(len(t), dtype=[("x", "u2"), ("y", "u2"), ("p", "u1"), ("t", "u4")])
+                buf["x"], buf["y"], buf["p"], buf["t"] = x, y, p, t
+                dat_tools.write_event_buffer(f, buf)
+            ds = object.__new__(gen1.GEN1Dataset)
+            ds.img_size = (H, W)
+            ds.files = [os.path.join(tmp, name + "_bbox.npy")]
+            ds.slice_policy = "fix_t"
+            ds.slice_args = {"window": window, "num_slice": num_slice, "micro_slice": Tm, "aggregation": "micro_sum"}
+            ts = synth.dat_label_times(name, t, window)
+            first = np.zeros(len(ts), np.int64)      # index of the first returned event in the recording
+            count = np.zeros(len(ts), np.int64)
+            hists = np.zeros((len(ts), Tm, 2, H, W), np.int32)
+            for k, stamp in enumerate(ts):
+                ev = ds.search_events(0, int(stamp))
+                count[k] = len(ev)
+                if len(ev):
+                    # locate the slice in the recording: (t, x, y, p) of its first event + its length
+                    cand = np.flatnonzero(t == ev["t"][0])
+                    hit = [c for c in cand if c + len(ev) <= len(t) and np.array_equal(t[c:c + len(ev)], ev["t"])
+                           and np.array_equal(x[c:c + len(ev)], ev["x"]) and np.array_equal(y[c:c + len(ev)], ev["y"])]
+                    assert len(hit) >= 1
+                    first[k] = hit[0]
+                fr = ds.agrregate(ev, "micro_sum")
+                assert fr.shape == (Tm, 2, H, W) and np.all(fr == np.round(fr))
+                hists[k] = fr.astype(np.int32)
+            out[f"{name}/ts"] = ts
+            out[f"{name}/first"] = first
+            out[f"{name}/count"] = count
+            out[f"{name}/hist"] = hists
+            print("psee", name, "labels", len(ts), "empty windows", int((count == 0).sum()),
+                  "events/window max", int(count.max()))
+    out["names"] = np.array(list(synth.DAT_CASES))
+    np.savez_compressed(os.path.join(HERE, "psee.npz"), **out)
+
+
 if __name__ == "__main__":
     assert ref_loader.available(), "reference tree not found"
     torch.set_num_threads(8)
     emb, act, gen1 = ref_loader.load_hot_modules()
+    if len(sys.argv) > 1 and sys.argv[1] == "psee":
+        make_psee(gen1)
+        print("psee.npz", os.path.getsize(os.path.join(HERE, "psee.npz")) // 1024, "KiB")
+        sys.exit(0)
     make_binning(gen1)
     make_sampler(emb, act)
     make_backbone()
-    for f in ("binning.npz", "sampler.npz", "backbone.npz"):
+    make_psee(gen1)
+    for f in ("binning.npz", "sampler.npz", "backbone.npz", "psee.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

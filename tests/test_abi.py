@@ -81,3 +81,21 @@ def test_module_surface_matches_reference():
     n.v = torch.ones(3)
     eas.reset_net(torch.nn.Sequential(n))
     assert n.v == 0.0
+
+
+def test_read_dat_parses_header_and_records(tmp_path):
+    """Host side of the .dat path: header lines, type/size bytes, raw records (dat_events_tools.py:126-181)."""
+    import numpy as np
+    from eas_snn_b200 import psee, synth
+    from oracle import psee as opsee
+    x, y, t, p = synth.dat_stream(seed=3, n=1000, H=24, W=32, span_us=10_000)
+    path = tmp_path / "a_td.dat"
+    with open(path, "wb") as f:
+        f.write(b"% Data file containing Event2D events.\n% Version 2\n% Height 24\n% Width 32\n")
+        f.write(bytes([0, 8]))
+        opsee.pack_records(x, y, t, p).tofile(f)
+    rec, (h, w) = psee.read_dat(str(path))
+    assert (h, w) == (24, 32) and rec.shape == (1000, 2)
+    assert np.array_equal(rec, psee.pack_records(x, y, t, p))
+    dx, dy, dt, dp = opsee.decode(rec.view(opsee.EV_DTYPE).reshape(-1))
+    assert np.array_equal(dx, x) and np.array_equal(dy, y) and np.array_equal(dt, t) and np.array_equal(dp, p)

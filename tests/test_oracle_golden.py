@@ -7,6 +7,7 @@ import torch
 from oracle import binning, sampler, backbone
 from oracle.plif import ATan
 from helpers import load_golden, sampler_case, sampler_kwargs
+from eas_snn_b200 import synth
 
 
 def test_binning_golden_all_cases():
@@ -65,3 +66,26 @@ def test_backbone_golden():
     for k in ("dark3", "dark4", "dark5"):
         assert torch.equal(outs[k], torch.from_numpy(z["out/" + k]).float()), k
         assert 0.01 < float(outs[k].mean()) < 0.9
+
+
+@pytest.mark.parametrize("name", list(synth.DAT_CASES))
+def test_psee_oracle_matches_reference_loader(name):
+    """oracle.psee (seek_time / load_delta_t / search_events / decode) against what the reference's own
+    PSEELoader + GEN1Dataset returned on the same synthetic .dat recording (tests/golden/psee.npz)."""
+    from oracle import psee
+    z = load_golden("psee")
+    kw, window, num_slice, Tm = synth.DAT_CASES[name]
+    x, y, t, p = synth.dat_stream(**kw)
+    rec = psee.pack_records(x, y, t, p)
+    dx, dy, dt, dp = psee.decode(rec)
+    assert np.array_equal(dx, x) and np.array_equal(dy, y) and np.array_equal(dt, t) and np.array_equal(dp, p)
+    ts = synth.dat_label_times(name, t, window)
+    assert np.array_equal(ts, z[f"{name}/ts"])
+    ranges = psee.windows(rec, ts, window, num_slice)
+    count = ranges[:, 1] - ranges[:, 0]
+    assert np.array_equal(count, z[f"{name}/count"])
+    nz = count > 0
+    assert np.array_equal(ranges[nz, 0], z[f"{name}/first"][nz])
+    hist = psee.micro_sum_windows(rec, ranges, kw["H"], kw["W"], Tm)
+    assert np.array_equal(hist.astype(np.int32), z[f"{name}/hist"])
+    assert (count == 0).any() and hist.sum() > 0
