@@ -322,7 +322,7 @@ def run_ours(args):
                           "conv+BN+PLIF launches), %d windows per GPU; FPN/head not included (out of scope)"
                           % (n_conv, BATCH),
                   "tensor": {"achieved": gflop / (fms / fsteps), "unit": "TFLOP/s (1x conv FLOPs; the kernel "
-                             "runs 3 bf16 passes for fp32-equivalent weights)", "peak": 1394.4,
+                             "runs 2 fp16 passes for fp32-equivalent weights)", "peak": 1394.4,
                              "frac": gflop / (fms / fsteps) / 1394.4},
                   "spike_rate": {k: round(float(v.float().mean()), 4) for k, v in outs.items()}}
 

@@ -42,7 +42,7 @@ class ConvCfg(C.Structure):
                 ("n_wsplit", C.c_int32), ("n_xsplit", C.c_int32), ("v_threshold", C.c_float),
                 ("hard_reset", C.c_int32), ("v_reset", C.c_float), ("decay_input", C.c_int32),
                 ("out_mode", C.c_int32), ("x_ld", C.c_int32), ("out_ld", C.c_int32), ("res_ld", C.c_int32),
-                ("residual", C.c_void_p)]
+                ("residual", C.c_void_p), ("w_unscale", C.c_void_p)]
 
 
 # name -> (restype, argtypes); the single source the "exports every symbol" test walks.

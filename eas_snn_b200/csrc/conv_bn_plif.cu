@@ -6,23 +6,26 @@
 // Implicit GEMM, one CTA per (128-pixel, BLOCK_N-channel) output tile:
 //   M = 128 output pixels = NB images x TH rows x TW cols of ONE time step,
 //   N = BLOCK_N output channels, K = taps x Cin walked in 64-channel blocks (one 128 B swizzle row).
-//   A (activations, channels-last bf16) arrives by TMA as a 5-D box [1 plane][NB][TH][TW][64 ch]: the
+//   A (activations, channels-last fp16) arrives by TMA as a 5-D box [1 plane][NB][TH][TW][64 ch]: the
 //     box origin is shifted per filter tap, out-of-image rows/cols/channels are zero filled by the
 //     TMA unit (= conv padding), stride-2 convs use the tensor map's element strides.  The box lands
 //     in shared memory exactly in the K-major SWIZZLE_128B layout tcgen05 wants.
-//   B (weights [split][Cout][tap][Cin] bf16) arrives by TMA as [BLOCK_N][1][64].
+//   B (weights [split][Cout][tap][Cin] fp16) arrives by TMA as [BLOCK_N][1][64].
 //   D: one fp32 accumulator per time step in TMEM (T x BLOCK_N columns), tcgen05.mma issued by one
-//     thread.  fp32 accuracy on bf16 tensor cores comes from splitting the folded fp32 weight into
-//     up to three bf16 planes (hi + mid + lo); spikes / SEW sums are small integers, exact in bf16,
-//     so A needs no split except for real-valued inputs (n_xsplit planes).
+//     thread.  fp32-equivalent accuracy on the 16-bit tensor cores comes from splitting the folded fp32
+//     weight, scaled per output channel by a power of two (w_unscale undoes it in the epilogue), into
+//     two fp16 planes hi + lo (22 mantissa bits); spikes / SEW sums are small integers, exact in fp16,
+//     so A needs no split except for real-valued inputs (n_xsplit = 2 planes).  Two planes instead of
+//     bf16's three = 2/3 of the MMAs, and every MMA costs a fixed 64 cycles here.
 //   Epilogue (4 warps, one TMEM lane = one pixel each): tcgen05.ld the T accumulators of a 16-channel
-//     chunk, add the folded BN shift, run the LIF recurrence over t with v in registers, store bf16
+//     chunk, add the folded BN shift, run the LIF recurrence over t with v in registers, store fp16
 //     spikes channels-last.  The conv output and the membrane potential never touch HBM.
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
 // Two mbarrier rings: B tiles are loaded once per K block and reused by all T time steps / input
 // planes, A tiles stream through a deeper ring.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 #include "lif.cuh"
 
 namespace {
@@ -38,10 +41,11 @@ struct ConvArgs {
   int NB, TH, TW;
   int tiles_w, tiles_h, tiles_b, tiles_n;
   int out_ld, out_mode, res_ld;
-  const __nv_bfloat16* residual;   // SEW shortcut added to the spikes (network_blocks.py:99-103) or null
+  const __half* residual;   // SEW shortcut added to the spikes (network_blocks.py:99-103) or null
   float vth, vreset;
   int hard_reset, decay_input;
   const float* bias;
+  const float* unscale;   // per output channel, multiplies the accumulator (null = 1)
   const float* plif_w;
   void* out;
 };
@@ -88,8 +92,8 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by ONE thread for the whole CTA.
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+// D[tmem] (+)= A[smem] * B[smem], fp16 x fp16 -> fp32, issued by ONE thread for the whole CTA.
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -98,7 +102,7 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// K-major swizzled shared-memory operand descriptor.  One K block is one swizzle row of BK bf16
+// K-major swizzled shared-memory operand descriptor.  One K block is one swizzle row of BK fp16
 // (128 / 64 / 32 B), 8-row groups are 8 rows apart (1024 / 512 / 256 B).
 template <int BK>
 __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
@@ -119,8 +123,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  const __half2 v = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
@@ -134,7 +138,7 @@ struct SmemLayout {
   static constexpr int OFF_B = OFF_A + SA * A_BYTES;
   static constexpr int OFF_BAR = OFF_B + SB * MAX_WSPLIT * B_BYTES;
   static constexpr int OFF_BIAS = OFF_BAR + 256;
-  static constexpr int TOTAL = OFF_BIAS + BLOCK_N * 4 + 1024;  // + slack for the 1024 B alignment
+  static constexpr int TOTAL = OFF_BIAS + 2 * BLOCK_N * 4 + 1024;  // bias + unscale, + slack for the alignment
 };
 
 template <int BLOCK_N, int TMAX, int BK>
@@ -155,6 +159,7 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   uint64_t* accum_full = bars + 2 * SA + 2 * SB;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 1);
   float* sBias = reinterpret_cast<float*>(smem + L::OFF_BIAS);
+  float* sUnscale = sBias + BLOCK_N;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Tacc = a.Tx;  // accumulators: one per distinct input time step
@@ -189,7 +194,10 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) sBias[i] = (n0 + i < a.Cout) ? a.bias[n0 + i] : 0.0f;
+    for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
+      sBias[i] = (n0 + i < a.Cout) ? a.bias[n0 + i] : 0.0f;
+      sUnscale[i] = (a.unscale && n0 + i < a.Cout) ? a.unscale[n0 + i] : 1.0f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -220,8 +228,8 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
-                               ((uint32_t)(BLOCK_M >> 4) << 24);
+    // D = f32 (bit 4), A = B = f16 (format fields 0), K-major operands
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
     for (int kb = 0; kb < nkb; ++kb) {
@@ -237,7 +245,7 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k) {
               const uint32_t acc = (kb > 0 || i > 0 || j > 0 || k > 0) ? 1u : 0u;
-              tc_mma_bf16(tmem_base + (uint32_t)(t * BLOCK_N), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2),
+              tc_mma_f16(tmem_base + (uint32_t)(t * BLOCK_N), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2),
                           idesc, acc);
             }
           }
@@ -277,7 +285,7 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = lif_v_init(d);
-        __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
+        __half* outp = reinterpret_cast<__half*>(a.out);
         for (int t = 0; t < a.T; ++t) {
           float s[16];
 #pragma unroll
@@ -286,36 +294,36 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
 #pragma unroll
             for (int tt = 0; tt < TMAX; ++tt)
               if (tt == (Tacc == 1 ? 0 : t)) xin = __uint_as_float(acc[tt][j]);
-            const float h = lif_charge(d, v[j], __fadd_rn(xin, sBias[c16 * 16 + j]));
+            const float h = lif_charge(d, v[j], __fadd_rn(__fmul_rn(xin, sUnscale[c16 * 16 + j]), sBias[c16 * 16 + j]));
             s[j] = lif_fire(d, h);
             v[j] = lif_reset(d, h, s[j]);
           }
-          __nv_bfloat16* dst = outp + ((int64_t)t * step + pix) * a.out_ld + ch0;
-          if (a.residual) {  // SEW add: y = spikes + x (small integers, exact in bf16)
-            const __nv_bfloat16* rp = a.residual + ((int64_t)t * step + pix) * a.res_ld + ch0;
+          __half* dst = outp + ((int64_t)t * step + pix) * a.out_ld + ch0;
+          if (a.residual) {  // SEW add: y = spikes + x (small integers, exact in fp16)
+            const __half* rp = a.residual + ((int64_t)t * step + pix) * a.res_ld + ch0;
             if (nch == 16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
               const uint4 r0 = reinterpret_cast<const uint4*>(rp)[0], r1 = reinterpret_cast<const uint4*>(rp)[1];
-              const __nv_bfloat16* rb0 = reinterpret_cast<const __nv_bfloat16*>(&r0);
-              const __nv_bfloat16* rb1 = reinterpret_cast<const __nv_bfloat16*>(&r1);
+              const __half* rb0 = reinterpret_cast<const __half*>(&r0);
+              const __half* rb1 = reinterpret_cast<const __half*>(&r1);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) s[j] += __bfloat162float(rb0[j]), s[8 + j] += __bfloat162float(rb1[j]);
+              for (int j = 0; j < 8; ++j) s[j] += __half2float(rb0[j]), s[8 + j] += __half2float(rb1[j]);
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (j < nch) s[j] += __bfloat162float(rp[j]);
+                if (j < nch) s[j] += __half2float(rp[j]);
             }
           }
           if (nch == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-            uint4 q0 = make_uint4(pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]), pack_bf16(s[4], s[5]),
-                                  pack_bf16(s[6], s[7]));
-            uint4 q1 = make_uint4(pack_bf16(s[8], s[9]), pack_bf16(s[10], s[11]), pack_bf16(s[12], s[13]),
-                                  pack_bf16(s[14], s[15]));
+            uint4 q0 = make_uint4(pack_f16(s[0], s[1]), pack_f16(s[2], s[3]), pack_f16(s[4], s[5]),
+                                  pack_f16(s[6], s[7]));
+            uint4 q1 = make_uint4(pack_f16(s[8], s[9]), pack_f16(s[10], s[11]), pack_f16(s[12], s[13]),
+                                  pack_f16(s[14], s[15]));
             reinterpret_cast<uint4*>(dst)[0] = q0;
             reinterpret_cast<uint4*>(dst)[1] = q1;
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (j < nch) dst[j] = __float2bfloat16(s[j]);
+              if (j < nch) dst[j] = __float2half_rn(s[j]);
           }
         }
       } else {
@@ -326,21 +334,38 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
               float* dst = reinterpret_cast<float*>(a.out) + ((int64_t)t * step + pix) * a.out_ld + ch0;
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (j < nch) dst[j] = __fadd_rn(__uint_as_float(acc[t][j]), sBias[c16 * 16 + j]);
-            } else {  // SiLU, written as three bf16 planes whose sum is the fp32 value
-              __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
+                if (j < nch)
+                  dst[j] = __fadd_rn(__fmul_rn(__uint_as_float(acc[t][j]), sUnscale[c16 * 16 + j]), sBias[c16 * 16 + j]);
+            } else {  // SiLU, written as two fp16 planes hi + lo whose sum is the fp32 value to 2^-22
+              __half* outp = reinterpret_cast<__half*>(a.out);
               const int64_t plane = (int64_t)Tacc * step * a.out_ld;
-              __nv_bfloat16* dst = outp + ((int64_t)t * step + pix) * a.out_ld + ch0;
+              __half* dst = outp + ((int64_t)t * step + pix) * a.out_ld + ch0;
+              float y[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                if (j < nch) {
-                  const float xv = __fadd_rn(__uint_as_float(acc[t][j]), sBias[c16 * 16 + j]);
-                  const float y = xv * eas_sigmoid(xv);
-                  const __nv_bfloat16 hi = __float2bfloat16(y);
-                  const float r1 = y - __bfloat162float(hi);
-                  const __nv_bfloat16 mid = __float2bfloat16(r1);
-                  const __nv_bfloat16 lo = __float2bfloat16(r1 - __bfloat162float(mid));
-                  dst[j] = hi, dst[plane + j] = mid, dst[2 * plane + j] = lo;
+                const float xv = __fadd_rn(__fmul_rn(__uint_as_float(acc[t][j]), sUnscale[c16 * 16 + j]), sBias[c16 * 16 + j]);
+                y[j] = fminf(fmaxf(xv * eas_sigmoid(xv), -65504.0f), 65504.0f);
+              }
+              if (nch == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((plane & 7) == 0)) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const __half2 h2 = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+                  const float2 hf = __half22float2(h2);
+                  const __half2 l2 = __floats2half2_rn(y[2 * j] - hf.x, y[2 * j + 1] - hf.y);
+                  hi[j] = *reinterpret_cast<const uint32_t*>(&h2), lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+                reinterpret_cast<uint4*>(dst)[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                reinterpret_cast<uint4*>(dst)[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                reinterpret_cast<uint4*>(dst + plane)[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                reinterpret_cast<uint4*>(dst + plane)[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  if (j < nch) {
+                    const __half hi = __float2half_rn(y[j]);
+                    dst[j] = hi, dst[plane + j] = __float2half_rn(y[j] - __half2float(hi));
+                  }
                 }
               }
             }
@@ -377,7 +402,7 @@ int check_conv(const eas_conv_cfg* c) {
   EAS_REQUIRE(c->Cin % 8 == 0, EAS_E_SHAPE);  // TMA global strides are multiples of 16 B
   EAS_REQUIRE((c->ksize == 1 || c->ksize == 3) && (c->stride == 1 || c->stride == 2), EAS_E_UNSUPPORTED);
   EAS_REQUIRE(c->n_wsplit >= 1 && c->n_wsplit <= MAX_WSPLIT && c->n_xsplit >= 1 && c->n_xsplit <= 3, EAS_E_UNSUPPORTED);
-  EAS_REQUIRE(c->out_mode >= EAS_CONV_OUT_SPIKES && c->out_mode <= EAS_CONV_OUT_SILU3, EAS_E_UNSUPPORTED);
+  EAS_REQUIRE(c->out_mode >= EAS_CONV_OUT_SPIKES && c->out_mode <= EAS_CONV_OUT_SILU2, EAS_E_UNSUPPORTED);
   EAS_REQUIRE(c->x_ld == 0 || (c->x_ld >= c->Cin && c->x_ld % 8 == 0), EAS_E_SHAPE);
   EAS_REQUIRE(c->out_ld == 0 || c->out_ld >= c->Cout, EAS_E_SHAPE);
   EAS_REQUIRE(c->res_ld == 0 || c->res_ld >= c->Cout, EAS_E_SHAPE);
@@ -464,13 +489,13 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
   a.tiles_w = (int)eas_ceil_div(Wo, a.TW), a.tiles_h = (int)eas_ceil_div(Ho, a.TH);
   a.tiles_b = (int)eas_ceil_div(c->B, a.NB), a.tiles_n = (int)eas_ceil_div(c->Cout, BLOCK_N);
   a.out_ld = out_ld, a.out_mode = c->out_mode;
-  a.residual = (const __nv_bfloat16*)c->residual, a.res_ld = c->res_ld ? c->res_ld : c->Cout;
+  a.residual = (const __half*)c->residual, a.res_ld = c->res_ld ? c->res_ld : c->Cout;
   a.vth = c->v_threshold, a.vreset = c->v_reset, a.hard_reset = c->hard_reset, a.decay_input = c->decay_input;
-  a.bias = bias, a.plif_w = plif_w, a.out = out;
+  a.bias = bias, a.unscale = c->w_unscale, a.plif_w = plif_w, a.out = out;
   const int64_t grid = (int64_t)a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
   EAS_REQUIRE(grid > 0 && grid < (1ll << 31), EAS_E_SHAPE);
 
-  // activations: [plane*Tx][B][H][W][x_ld] bf16, innermost first for the tensor map
+  // activations: [plane*Tx][B][H][W][x_ld] fp16, innermost first for the tensor map
   CUtensorMap xmap, wmap;
   const CUtensorMapSwizzle swz = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -482,7 +507,7 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
     cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)(a.TW * c->stride), (cuuint32_t)(a.TH * c->stride),
                          (cuuint32_t)a.NB, 1};
     cuuint32_t estr[5] = {1, (cuuint32_t)c->stride, (cuuint32_t)c->stride, 1, 1};
-    CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
+    CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return EAS_E_SHAPE;
@@ -493,7 +518,7 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
     cuuint64_t strides[2] = {(cuuint64_t)c->Cin * 2, (cuuint64_t)taps * c->Cin * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, 1, (cuuint32_t)BLOCK_N};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_planes), dims, strides, box,
+    CUresult r = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(w_planes), dims, strides, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return EAS_E_SHAPE;

@@ -6,11 +6,11 @@ Drop-in seam: the reference turns every ``BaseConv`` into
 (``yolox/utils/utils_snn.py:16-58``, ``yolox/models/network_blocks.py:31-56``).  :class:`FusedConvBNPLIF`
 keeps those three children and their state-dict keys (``conv.0.weight``, ``bn.*``, ``act.w``) but in
 eval mode runs ONE kernel (``eas_conv_bn_plif_fwd``): implicit-GEMM conv on tcgen05 with the BN
-folded into bf16-split weights (``yolox/utils/model_utils.py:61-75``) and the LIF recurrence over T in
+folded into fp16-split weights (``yolox/utils/model_utils.py:61-75``) and the LIF recurrence over T in
 the epilogue, so neither the conv output nor the membrane potential reaches HBM.
 
-Activations between fused layers are channels-last bf16 ``[T, B, H, W, C]`` (spikes and SEW sums
-are small integers, exact in bf16).  :class:`SpikingCSPDarknet` is the reference topology
+Activations between fused layers are channels-last fp16 ``[T, B, H, W, C]`` (spikes and SEW sums
+are small integers, exact in fp16).  :class:`SpikingCSPDarknet` is the reference topology
 (``yolox/models/darknet.py:97-180``) executed on that layout, with concatenations realised by
 writing conv outputs straight into channel slices of the concat buffer.
 """
@@ -26,17 +26,18 @@ import torch.nn.functional as F
 from . import _lib
 from .neuron import ATan, ParametricLIFNode
 
-OUT_SPIKES, OUT_PREACT, OUT_SILU3 = 0, 1, 2
+OUT_SPIKES, OUT_PREACT, OUT_SILU2 = 0, 1, 2
+ACT_DTYPE = torch.float16      # activations, weight planes
 
 
 # ------------------------------------------------------------------------------------------------
 # functional layer
 # ------------------------------------------------------------------------------------------------
-def split_bf16(x: torch.Tensor, n: int) -> torch.Tensor:
-    """fp32 tensor -> ``[n, ...]`` bf16 planes whose (fp32) sum reproduces x to ~2^-(8n)."""
-    planes, r = [], x.float()
+def split_f16(x: torch.Tensor, n: int = 2) -> torch.Tensor:
+    """fp32 tensor -> ``[n, ...]`` fp16 planes whose (fp32) sum reproduces x to ~2^-(11n) (|x| < 65504)."""
+    planes, r = [], x.float().clamp(-65504.0, 65504.0)
     for _ in range(n):
-        p = r.to(torch.bfloat16)
+        p = r.to(torch.float16)
         planes.append(p)
         r = r - p.float()
     return torch.stack(planes)
@@ -48,27 +49,39 @@ def fold_bn(conv_w: torch.Tensor, bn_w, bn_b, mean, var, eps: float):
     return conv_w.float() * scale.view(-1, 1, 1, 1), bn_b.float() - mean.float() * scale
 
 
-def pack_weight(w_folded: torch.Tensor, n_wsplit: int) -> torch.Tensor:
-    """``[Cout, Cin, kh, kw]`` fp32 -> ``[n_wsplit, Cout, kh, kw, Cin]`` bf16 planes (K-major for TMA)."""
-    return split_bf16(w_folded.permute(0, 2, 3, 1).contiguous(), n_wsplit).contiguous()
+def pack_weight(w_folded: torch.Tensor, n_wsplit: int = 2):
+    """``[Cout, Cin, kh, kw]`` fp32 -> (``[n_wsplit, Cout, kh, kw, Cin]`` fp16 planes, K-major for TMA;
+    ``[Cout]`` fp32 unscale).  Every output channel is scaled by a power of two (exact) that puts its
+    largest weight in [2^13, 2^14), so the hi and lo planes are normal fp16 numbers; the kernel multiplies
+    the accumulator by ``unscale`` = the inverse power of two before adding the bias."""
+    w = w_folded.float()
+    amax = w.abs().amax(dim=(1, 2, 3)).clamp_min(2.0 ** -100)
+    e = (13 - torch.floor(torch.log2(amax))).clamp(-24, 40)
+    scale = torch.exp2(e)
+    planes = split_f16((w * scale.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).contiguous(), n_wsplit).contiguous()
+    return planes, torch.exp2(-e).contiguous()
 
 
 def conv_bn_plif(x: torch.Tensor, w_planes: torch.Tensor, bias: torch.Tensor, plif_w: torch.Tensor | None,
                  T: int, ksize: int, stride: int, n_xsplit: int = 1, out: torch.Tensor | None = None,
                  out_mode: int = OUT_SPIKES, v_threshold: float = 1.0, v_reset: float | None = None,
-                 decay_input: bool = False, residual: torch.Tensor | None = None) -> torch.Tensor:
+                 decay_input: bool = False, residual: torch.Tensor | None = None,
+                 w_unscale: torch.Tensor | None = None) -> torch.Tensor:
     """One fused layer.
 
-    x        : channels-last bf16 ``[Tx, B, H, W, Cin]`` (``[n_xsplit, Tx, B, H, W, Cin]`` for split
+    x        : channels-last fp16 ``[Tx, B, H, W, Cin]`` (``[n_xsplit, Tx, B, H, W, Cin]`` for split
                real-valued input); may be a channel slice of a wider buffer (pixel stride ``x_ld``).
-    w_planes : ``[n_wsplit, Cout, k, k, Cin]`` bf16 (:func:`pack_weight`), bias ``[Cout]`` fp32.
+    w_planes : ``[n_wsplit, Cout, k, k, Cin]`` fp16 and ``w_unscale`` ``[Cout]`` fp32 (:func:`pack_weight`),
+               bias ``[Cout]`` fp32.
     out      : optional destination view ``[T, B, Ho, Wo, Cout]`` (channel slice of a concat buffer).
-    residual : optional bf16 ``[T, B, Ho, Wo, Cout]`` added to the spikes in the epilogue (SEW shortcut).
-    Returns spikes ``[T, B, Ho, Wo, Cout]`` bf16 (or the fp32 pre-activation / 3 SiLU planes).
+    residual : optional fp16 ``[T, B, Ho, Wo, Cout]`` added to the spikes in the epilogue (SEW shortcut).
+    Returns spikes ``[T, B, Ho, Wo, Cout]`` fp16 (or the fp32 pre-activation / 2 SiLU planes).
     """
-    _lib.require_cuda(x, w_planes, bias)
-    if x.dtype != torch.bfloat16 or w_planes.dtype != torch.bfloat16:
-        raise TypeError("conv_bn_plif expects bf16 activations and weight planes")
+    _lib.require_cuda(x, w_planes, bias, w_unscale)
+    if x.dtype != ACT_DTYPE or w_planes.dtype != ACT_DTYPE:
+        raise TypeError("conv_bn_plif expects fp16 activations and weight planes")
+    if w_unscale is not None and (w_unscale.dtype != torch.float32 or w_unscale.numel() != w_planes.shape[1]):
+        raise TypeError("w_unscale must be fp32 [Cout]")
     xs = x if n_xsplit > 1 or x.dim() == 6 else x.unsqueeze(0)
     if xs.dim() != 6 or xs.shape[0] != n_xsplit:
         raise ValueError("x must be [Tx,B,H,W,C] or [n_xsplit,Tx,B,H,W,C]")
@@ -90,11 +103,11 @@ def conv_bn_plif(x: torch.Tensor, w_planes: torch.Tensor, bias: torch.Tensor, pl
     To = T if out_mode == OUT_SPIKES else Tx
     if out is None:
         if out_mode == OUT_SPIKES:
-            out = torch.empty((To, B, Ho, Wo, Cout), dtype=torch.bfloat16, device=dev)
+            out = torch.empty((To, B, Ho, Wo, Cout), dtype=ACT_DTYPE, device=dev)
         elif out_mode == OUT_PREACT:
             out = torch.empty((To, B, Ho, Wo, Cout), dtype=torch.float32, device=dev)
         else:
-            out = torch.empty((3, To, B, Ho, Wo, Cout), dtype=torch.bfloat16, device=dev)
+            out = torch.empty((2, To, B, Ho, Wo, Cout), dtype=ACT_DTYPE, device=dev)
     oshape = tuple(out.shape[-5:])
     if oshape != (To, B, Ho, Wo, Cout) or (Cout > 1 and out.stride(-1) != 1):
         raise ValueError("out has the wrong shape %s, expected %s" % (oshape, (To, B, Ho, Wo, Cout)))
@@ -104,8 +117,8 @@ def conv_bn_plif(x: torch.Tensor, w_planes: torch.Tensor, bias: torch.Tensor, pl
         raise ValueError("out must be a dense channels-last tensor or a channel slice of one")
     res_ld = 0
     if residual is not None:
-        if residual.dtype != torch.bfloat16 or tuple(residual.shape) != (T, B, Ho, Wo, Cout):
-            raise ValueError("residual must be bf16 [T, B, Ho, Wo, Cout]")
+        if residual.dtype != ACT_DTYPE or tuple(residual.shape) != (T, B, Ho, Wo, Cout):
+            raise ValueError("residual must be fp16 [T, B, Ho, Wo, Cout]")
         res_ld = residual.stride(-2) if Wo > 1 else (residual.stride(-3) if Ho > 1 else Cout)
         rwant = (B * Ho * Wo * res_ld, Ho * Wo * res_ld, Wo * res_ld, res_ld, 1)
         if any(d > 1 and s_ != w_ for s_, w_, d in zip(residual.stride(), rwant, residual.shape)):
@@ -114,7 +127,8 @@ def conv_bn_plif(x: torch.Tensor, w_planes: torch.Tensor, bias: torch.Tensor, pl
                        n_wsplit=n_wsplit, n_xsplit=n_xsplit, v_threshold=float(v_threshold),
                        hard_reset=0 if v_reset is None else 1, v_reset=0.0 if v_reset is None else float(v_reset),
                        decay_input=int(bool(decay_input)), out_mode=out_mode, x_ld=x_ld, out_ld=out_ld,
-                       res_ld=res_ld, residual=None if residual is None else residual.data_ptr())
+                       res_ld=res_ld, residual=None if residual is None else residual.data_ptr(),
+                       w_unscale=None if w_unscale is None else w_unscale.contiguous().data_ptr())
     L = _lib.lib()
     with torch.cuda.device(dev):
         rc = L.eas_conv_bn_plif_fwd(C.byref(cfg), _lib.ptr(xs), _lib.ptr(w_planes), _lib.ptr(bias),
@@ -123,12 +137,12 @@ def conv_bn_plif(x: torch.Tensor, w_planes: torch.Tensor, bias: torch.Tensor, pl
     return out
 
 
-def to_channels_last_bf16(x_seq: torch.Tensor) -> torch.Tensor:
-    """``[T, B, C, H, W]`` (any strides / float dtype) -> ``[T, B, H, W, C]`` bf16 contiguous.
+def to_channels_last_f16(x_seq: torch.Tensor) -> torch.Tensor:
+    """``[T, B, C, H, W]`` (any strides / float dtype) -> ``[T, B, H, W, C]`` fp16 contiguous.
     Free when x_seq is already a permuted view of such a buffer (what the fused layers return)."""
     y = x_seq.permute(0, 1, 3, 4, 2)
-    if y.dtype != torch.bfloat16:
-        y = y.to(torch.bfloat16)
+    if y.dtype != ACT_DTYPE:
+        y = y.to(ACT_DTYPE)
     return y.contiguous()
 
 
@@ -157,7 +171,7 @@ class MultiStepBatchNorm2d(nn.BatchNorm2d):
 class FusedConvBNPLIF(nn.Module):
     """``BaseConv`` after ``convert_to_spiking`` (network_blocks.py:31-56, utils_snn.py:25-53)."""
 
-    def __init__(self, in_channels, out_channels, ksize, stride, spike_fn=None, n_wsplit: int = 3,
+    def __init__(self, in_channels, out_channels, ksize, stride, spike_fn=None, n_wsplit: int = 2,
                  eps: float = 1e-3, momentum: float = 0.03):
         super().__init__()
         self.conv = SeqToANNContainer(nn.Conv2d(in_channels, out_channels, ksize, stride, (ksize - 1) // 2,
@@ -171,7 +185,7 @@ class FusedConvBNPLIF(nn.Module):
         self._cache = None
 
     @classmethod
-    def from_modules(cls, conv: nn.Conv2d, bn: nn.BatchNorm2d, act=None, spike_fn=None, n_wsplit: int = 3):
+    def from_modules(cls, conv: nn.Conv2d, bn: nn.BatchNorm2d, act=None, spike_fn=None, n_wsplit: int = 2):
         if conv.groups != 1 or conv.bias is not None or conv.kernel_size[0] != conv.kernel_size[1]:
             raise NotImplementedError("fused layer covers the reference's BaseConv: square, groups=1, no bias")
         m = cls(conv.in_channels, conv.out_channels, conv.kernel_size[0], conv.stride[0], spike_fn=spike_fn,
@@ -192,17 +206,18 @@ class FusedConvBNPLIF(nn.Module):
             with torch.no_grad():
                 w, shift = fold_bn(self.conv[0].weight, self.bn.weight, self.bn.bias, self.bn.running_mean,
                                    self.bn.running_var, self.bn.eps)
-                self._cache = (key, pack_weight(w, self.n_wsplit), shift.contiguous())
-        return self._cache[1], self._cache[2]
+                wp, unscale = pack_weight(w, self.n_wsplit)
+                self._cache = (key, wp, shift.contiguous(), unscale)
+        return self._cache[1], self._cache[2], self._cache[3]
 
     # -- channels-last fast path (used by SpikingCSPDarknet) -------------------------------------
     def run(self, x_cl: torch.Tensor, T: int, out: torch.Tensor | None = None, n_xsplit: int = 1,
             residual: torch.Tensor | None = None) -> torch.Tensor:
-        wp, shift = self.packed()
+        wp, shift, unscale = self.packed()
         a = self.act
         return conv_bn_plif(x_cl, wp, shift, a.w.detach().float(), T, self.ksize, self.stride, n_xsplit=n_xsplit,
                             out=out, out_mode=OUT_SPIKES, v_threshold=a.v_threshold, v_reset=a.v_reset,
-                            decay_input=a.decay_input, residual=residual)
+                            decay_input=a.decay_input, residual=residual, w_unscale=unscale)
 
     # -- reference-shaped forward: [T, B, C, H, W] in, [T, B, C', H', W'] out -----------------------
     def forward(self, x_seq: torch.Tensor) -> torch.Tensor:
@@ -212,10 +227,10 @@ class FusedConvBNPLIF(nn.Module):
             return self.act(self.bn(self.conv(x_seq)))
         T = x_seq.shape[0]
         x_cl = x_seq.permute(0, 1, 3, 4, 2)
-        if x_seq.dtype == torch.bfloat16 or self.assume_integer_input:
-            y = self.run(x_cl.to(torch.bfloat16).contiguous(), T)
+        if x_seq.dtype in (torch.float16, torch.bfloat16) or self.assume_integer_input:
+            y = self.run(x_cl.to(ACT_DTYPE).contiguous(), T)     # spikes / SEW sums: exact in fp16
         else:  # real-valued input (e.g. the SiLU stem output): split it so the product stays fp32-accurate
-            y = self.run(split_bf16(x_cl.contiguous(), 3), T, n_xsplit=3)
+            y = self.run(split_f16(x_cl.contiguous(), 2), T, n_xsplit=2)
         self.act.reset()                                   # stateless: the reference resets per batch
         return y.permute(0, 1, 4, 2, 3).to(x_seq.dtype)    # logical [T, B, C, H, W], channels-last memory
 
@@ -240,8 +255,9 @@ class _AnnStemConv(nn.Module):
             with torch.no_grad():
                 w, shift = fold_bn(self.conv.weight, self.bn.weight, self.bn.bias, self.bn.running_mean,
                                    self.bn.running_var, self.bn.eps)
-                self._cache = (key, pack_weight(w, 3), shift.contiguous())
-        return self._cache[1], self._cache[2]
+                wp, unscale = pack_weight(w, 2)
+                self._cache = (key, wp, shift.contiguous(), unscale)
+        return self._cache[1], self._cache[2], self._cache[3]
 
 
 class _Focus(nn.Module):
@@ -250,13 +266,14 @@ class _Focus(nn.Module):
         self.conv = _AnnStemConv(cin * 4, cout, k)
 
     def run(self, frames: torch.Tensor) -> torch.Tensor:
-        """frames ``[Tx, B, C, H, W]`` fp32 -> SiLU(BN(conv(space_to_depth))) as 3 bf16 planes
-        ``[3, Tx, B, H/2, W/2, cout]`` (network_blocks.py:191-213)."""
+        """frames ``[Tx, B, C, H, W]`` fp32 -> SiLU(BN(conv(space_to_depth))) as 2 fp16 planes
+        ``[2, Tx, B, H/2, W/2, cout]`` (network_blocks.py:191-213)."""
         a, b = frames[..., ::2, ::2], frames[..., 1::2, ::2]
         c, d = frames[..., ::2, 1::2], frames[..., 1::2, 1::2]
         x = torch.cat((a, b, c, d), dim=2).permute(0, 1, 3, 4, 2).contiguous()      # channels-last fp32
-        wp, shift = self.conv.packed()
-        return conv_bn_plif(split_bf16(x, 3), wp, shift, None, x.shape[0], 3, 1, n_xsplit=3, out_mode=OUT_SILU3)
+        wp, shift, unscale = self.conv.packed()
+        return conv_bn_plif(split_f16(x, 2), wp, shift, None, x.shape[0], 3, 1, n_xsplit=2, out_mode=OUT_SILU2,
+                            w_unscale=unscale)
 
 
 class _Bottleneck(nn.Module):
@@ -284,7 +301,7 @@ class _SPP(nn.Module):
     def run(self, x, T):
         Tn, B, H, W, _ = x.shape
         hid = self.conv1.conv[0].out_channels
-        cat = torch.empty((T, B, H, W, hid * (len(self.ks) + 1)), dtype=torch.bfloat16, device=x.device)
+        cat = torch.empty((T, B, H, W, hid * (len(self.ks) + 1)), dtype=ACT_DTYPE, device=x.device)
         y = self.conv1.run(x, T, out=cat[..., :hid])
         y4 = y.flatten(0, 1).permute(0, 3, 1, 2)       # [T*B, C, H, W] view, channels-last memory
         for i, k in enumerate(self.ks):
@@ -305,7 +322,7 @@ class _CSPLayer(nn.Module):
     def run(self, x, T):
         Tn, B, H, W, _ = x.shape
         hid = self.conv1.conv[0].out_channels
-        cat = torch.empty((T, B, H, W, 2 * hid), dtype=torch.bfloat16, device=x.device)
+        cat = torch.empty((T, B, H, W, 2 * hid), dtype=ACT_DTYPE, device=x.device)
         self.conv2.run(x, T, out=cat[..., hid:])
         y = self.conv1.run(x, T)
         blocks = list(self.m)
@@ -348,8 +365,8 @@ class SpikingCSPDarknet(nn.Module):
         T = self.T
         if frames.shape[0] not in (1, T):
             raise ValueError("the timestep of SNN is not matched with that of input")   # spiking_yolox.py:57
-        stem3 = self.stem[0].run(frames.float())                     # [3, Tx, B, H/2, W/2, c] bf16 planes
-        x = self.dark2[0].run(stem3, T, n_xsplit=3)                   # first spiking conv: real-valued input
+        stem2 = self.stem[0].run(frames.float())                     # [2, Tx, B, H/2, W/2, c] fp16 planes
+        x = self.dark2[0].run(stem2, T, n_xsplit=2)                   # first spiking conv: real-valued input
         outs = {}
         x = self.dark2[1].run(x, T)
         outs["dark2"] = x
@@ -363,7 +380,7 @@ class SpikingCSPDarknet(nn.Module):
         return {k: outs[k].permute(0, 1, 4, 2, 3) for k in keys}
 
 
-def convert_to_spiking(model: nn.Module, spike_fn, fuse: bool = True, n_wsplit: int = 3) -> nn.Module:
+def convert_to_spiking(model: nn.Module, spike_fn, fuse: bool = True, n_wsplit: int = 2) -> nn.Module:
     """``yolox/utils/utils_snn.py:16-58`` with the fused layer: every child that looks like the
     reference's ``BaseConv`` (``.conv`` Conv2d, ``.bn`` BatchNorm2d, ``.act``) becomes a
     :class:`FusedConvBNPLIF` (same keys); ``Focus`` is wrapped whole and stays ANN; lone Conv2d /

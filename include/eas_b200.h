@@ -35,7 +35,7 @@ enum {
   EAS_E_ALIGN = -5        /* pointer not aligned as required                */
 };
 
-enum { EAS_F32 = 0, EAS_I32 = 1, EAS_BF16 = 2, EAS_U8 = 3 };
+enum { EAS_F32 = 0, EAS_I32 = 1, EAS_BF16 = 2, EAS_U8 = 3, EAS_F16 = 4 };
 enum { EAS_READOUT_SUM = 0, EAS_READOUT_LAST = 1, EAS_READOUT_AVG = 2 };
 enum { EAS_SG_ATAN = 0, EAS_SG_SIGMOID = 1, EAS_SG_RECT = 2 };
 
@@ -179,12 +179,12 @@ int eas_plif_bwd(const eas_plif_cfg* cfg, const void* x, const float* w, const f
  *       layer.BatchNorm2d('m') -> ParametricLIFNode, yolox/models/network_blocks.py:52-53,
  *       yolox/utils/utils_snn.py:25-53; BN folding per yolox/utils/model_utils.py:61-75.
  *
- * Activations are channels-last bf16: x [Tx][B][H][W][Cin] with Tx == T, or Tx == 1 when the
+ * Activations are channels-last fp16: x [Tx][B][H][W][Cin] with Tx == T, or Tx == 1 when the
  * input is the same for every time step (sampler output broadcast, spiking_yolox.py:54-55).
- * Weights: n_wsplit bf16 planes [n_wsplit][Cout][kh][kw][Cin] whose sum is the BN-folded fp32
- * weight (1 plane = "fast", 3 planes = fp32-equivalent for integer-valued spike inputs);
- * n_xsplit input planes likewise for real-valued inputs.  bias [Cout] f32 (folded BN shift).
- * Output spikes [T][B][Ho][Wo][Cout] bf16 (0/1).  Tensor-core path (tcgen05 + TMEM + TMA).
+ * Weights: n_wsplit fp16 planes [n_wsplit][Cout][kh][kw][Cin] whose sum, times w_unscale[c], is the
+ * BN-folded fp32 weight (1 plane = "fast", 2 planes = 22 mantissa bits: fp32-equivalent for the
+ * integer-valued spike inputs); n_xsplit input planes likewise for real-valued inputs (|x| < 65504).
+ * bias [Cout] f32 (folded BN shift).  Output spikes [T][B][Ho][Wo][Cout] fp16 (0/1).  Tensor-core path (tcgen05 + TMEM + TMA).
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t T, Tx, B, H, W, Cin, Cout, ksize, stride;
@@ -199,14 +199,17 @@ typedef struct {
   int32_t out_ld;       /* channels per pixel of the output buffer (>= Cout; 0 = Cout): lets the
                            output land in a channel slice of a concat buffer (CSPLayer / SPP cat) */
   int32_t res_ld;       /* channels per pixel of the residual buffer (0 = Cout) */
-  const void* residual; /* optional bf16 [T][B][Ho][Wo][res_ld]: SEW shortcut added to the spikes
+  const void* residual; /* optional fp16 [T][B][Ho][Wo][res_ld]: SEW shortcut added to the spikes
                            (Bottleneck, network_blocks.py:99-103); NULL = none */
+  const float* w_unscale; /* optional [Cout] f32: the accumulator of channel c is multiplied by
+                           w_unscale[c] before the bias (undoes the per-channel power-of-two scale
+                           that keeps the fp16 weight planes in range); NULL = 1 */
 } eas_conv_cfg;
 
 enum {
-  EAS_CONV_OUT_SPIKES = 0, /* bf16 spikes [T][B][Ho][Wo][out_ld]                                  */
+  EAS_CONV_OUT_SPIKES = 0, /* fp16 spikes [T][B][Ho][Wo][out_ld]                                  */
   EAS_CONV_OUT_PREACT = 1, /* f32 conv + bias [Tx][B][Ho][Wo][out_ld] (no neuron)                 */
-  EAS_CONV_OUT_SILU3 = 2   /* SiLU(conv + bias) as 3 bf16 planes hi/mid/lo [3][Tx][B][Ho][Wo][out_ld]
+  EAS_CONV_OUT_SILU2 = 2   /* SiLU(conv + bias) as 2 fp16 planes hi/lo [2][Tx][B][Ho][Wo][out_ld]
                               (the ANN stem, network_blocks.py:191-213, feeding a spiking conv)   */
 };
 

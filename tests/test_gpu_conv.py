@@ -44,26 +44,29 @@ def test_preact_matches_fp32_conv(cuda, shape):
     w = torch.randn((Cout, Cin, k, k), generator=g) / (Cin * k * k) ** 0.5
     bias = torch.randn(Cout, generator=g)
     want = _ref_conv(x, w, stride) + bias.double()
-    wp = fused.pack_weight(w.to(cuda), 3)
-    got = fused.conv_bn_plif(x.to(cuda).bfloat16(), wp, bias.to(cuda), None, Tx, k, stride, out_mode=fused.OUT_PREACT)
+    wp, un = fused.pack_weight(w.to(cuda), 2)
+    got = fused.conv_bn_plif(x.to(cuda).half(), wp, bias.to(cuda), None, Tx, k, stride, out_mode=fused.OUT_PREACT,
+                             w_unscale=un)
     assert got.shape == want.shape, (got.shape, want.shape)
-    # tcgen05 accumulates in fp32 with truncation: the error grows ~1.6e-8 * K (K = taps * Cin); the bf16x3
-    # weight split itself is exact to 2^-24.  (cuDNN's default TF32 path is ~1e-3 on the same data.)
+    # tcgen05 accumulates in fp32 with truncation: the error grows ~1.6e-8 * K (K = taps * Cin); the fp16 hi/lo
+    # weight split itself is exact to 2^-22.  (cuDNN's default TF32 path is ~1e-3 on the same data.)
     K = Cin * k * k
     ok, msg = close_report(got, want, rtol=1e-6, atol=2e-6 + 2.5e-8 * K)
     print("preact %s: %s" % (shape, msg))
     assert ok, "%s: %s" % (shape, msg)
 
 
-def test_single_plane_is_bf16_accurate(cuda):
+def test_single_plane_is_fp16_accurate(cuda):
     g = torch.Generator().manual_seed(1)
     x = torch.randint(0, 2, (1, 1, 16, 16, 64), generator=g).float()
     w = torch.randn((64, 64, 3, 3), generator=g) / 24.0
     bias = torch.zeros(64)
-    got = fused.conv_bn_plif(x.to(cuda).bfloat16(), fused.pack_weight(w.to(cuda), 1), bias.to(cuda), None, 1, 3, 1,
-                             out_mode=fused.OUT_PREACT)
-    want = _ref_conv(x, w.bfloat16().float(), 1)
+    wp, un = fused.pack_weight(w.to(cuda), 1)
+    got = fused.conv_bn_plif(x.to(cuda).half(), wp, bias.to(cuda), None, 1, 3, 1, out_mode=fused.OUT_PREACT, w_unscale=un)
+    want = _ref_conv(x, (wp[0].float() * un.view(-1, 1, 1, 1)).permute(0, 3, 1, 2).cpu(), 1)   # the single fp16 plane
     ok, msg = close_report(got, want, rtol=1e-5, atol=1e-5)
+    assert ok, msg
+    ok, msg = close_report(got, _ref_conv(x, w, 1), rtol=2e-3, atol=2e-3)      # and ~2^-11 of the fp32 weights
     assert ok, msg
 
 
@@ -73,13 +76,16 @@ def test_real_valued_input_split(cuda):
     w = torch.randn((32, 8, 3, 3), generator=g) / 8.0
     bias = torch.randn(32, generator=g) * 0.1
     want = _ref_conv(x, w, 1) + bias.double()
-    got = fused.conv_bn_plif(fused.split_bf16(x.to(cuda), 3), fused.pack_weight(w.to(cuda), 3), bias.to(cuda), None,
-                             1, 3, 1, n_xsplit=3, out_mode=fused.OUT_PREACT)
+    wp, un = fused.pack_weight(w.to(cuda), 2)
+    got = fused.conv_bn_plif(fused.split_f16(x.to(cuda), 2), wp, bias.to(cuda), None,
+                             1, 3, 1, n_xsplit=2, out_mode=fused.OUT_PREACT, w_unscale=un)
     ok, msg = close_report(got, want, rtol=3e-6, atol=3e-6)
+    print("real-valued input:", msg)
     assert ok, msg
     # SiLU planes sum back to the fp32 activation
-    planes = fused.conv_bn_plif(fused.split_bf16(x.to(cuda), 3), fused.pack_weight(w.to(cuda), 3), bias.to(cuda),
-                                None, 1, 3, 1, n_xsplit=3, out_mode=fused.OUT_SILU3)
+    planes = fused.conv_bn_plif(fused.split_f16(x.to(cuda), 2), wp, bias.to(cuda),
+                                None, 1, 3, 1, n_xsplit=2, out_mode=fused.OUT_SILU2, w_unscale=un)
+    assert planes.shape[0] == 2 and planes.dtype == torch.float16
     silu = F.silu(want).float()
     ok, msg = close_report(planes.float().sum(0), silu, rtol=1e-5, atol=1e-5)
     assert ok, msg
@@ -103,7 +109,7 @@ def test_layer_vs_oracle_conv_bn_plif(cuda, cfg):
     m.load_state_dict(ref.state_dict())
     m.eval()
     with torch.no_grad():
-        got_cl = m.run(x.to(cuda).permute(0, 1, 3, 4, 2).contiguous().bfloat16(), 3)
+        got_cl = m.run(x.to(cuda).permute(0, 1, 3, 4, 2).contiguous().half(), 3)
         got = got_cl.permute(0, 1, 4, 2, 3).float().cpu()
         got_mod = m(x.to(cuda))                                        # drop-in [T,B,C,H,W] fp32 path
     mism = (got != want).float().mean().item()
@@ -115,19 +121,19 @@ def test_layer_vs_oracle_conv_bn_plif(cuda, cfg):
 
 def test_output_into_concat_slice(cuda):
     g = torch.Generator().manual_seed(4)
-    x = torch.randint(0, 2, (2, 1, 8, 16, 64), generator=g).float().to(cuda).bfloat16()
-    w = fused.pack_weight((torch.randn((32, 64, 1, 1), generator=g) / 8).to(cuda), 3)
+    x = torch.randint(0, 2, (2, 1, 8, 16, 64), generator=g).float().to(cuda).half()
+    w, un = fused.pack_weight((torch.randn((32, 64, 1, 1), generator=g) / 8).to(cuda), 2)
     bias = torch.randn(32, generator=g).to(cuda)
     pw = torch.tensor(0.0, device=cuda)
-    cat = torch.full((2, 1, 8, 16, 96), 7.0, dtype=torch.bfloat16, device=cuda)
-    alone = fused.conv_bn_plif(x, w, bias, pw, 2, 1, 1)
-    fused.conv_bn_plif(x, w, bias, pw, 2, 1, 1, out=cat[..., 32:64])
+    cat = torch.full((2, 1, 8, 16, 96), 7.0, dtype=torch.float16, device=cuda)
+    alone = fused.conv_bn_plif(x, w, bias, pw, 2, 1, 1, w_unscale=un)
+    fused.conv_bn_plif(x, w, bias, pw, 2, 1, 1, out=cat[..., 32:64], w_unscale=un)
     assert torch.equal(cat[..., 32:64], alone)
     assert bool((cat[..., :32] == 7).all()) and bool((cat[..., 64:] == 7).all())
     # and a channel slice as INPUT
-    wide = torch.zeros((2, 1, 8, 16, 160), dtype=torch.bfloat16, device=cuda)
+    wide = torch.zeros((2, 1, 8, 16, 160), dtype=torch.float16, device=cuda)
     wide[..., 64:128] = x
-    assert torch.equal(fused.conv_bn_plif(wide[..., 64:128], w, bias, pw, 2, 1, 1), alone)
+    assert torch.equal(fused.conv_bn_plif(wide[..., 64:128], w, bias, pw, 2, 1, 1, w_unscale=un), alone)
 
 
 def test_residual_and_wide_tiles(cuda):
@@ -140,10 +146,11 @@ def test_residual_and_wide_tiles(cuda):
         pre = (_ref_conv(x, w, 1) + bias.double()).float()
         want = op.plif_forward(pre, torch.tensor(0.2), op.ATan(2.0), 1.0, None, False, False)
         res = torch.randint(0, 3, want.shape, generator=g).float()
-        xg, wp = x.to(cuda).bfloat16(), fused.pack_weight(w.to(cuda), 3)
+        xg, (wp, un) = x.to(cuda).half(), fused.pack_weight(w.to(cuda), 2)
         pw = torch.tensor(0.2, device=cuda)
-        got = fused.conv_bn_plif(xg, wp, bias.to(cuda), pw, 3, k, 1).float().cpu()
-        got_r = fused.conv_bn_plif(xg, wp, bias.to(cuda), pw, 3, k, 1, residual=res.to(cuda).bfloat16()).float().cpu()
+        got = fused.conv_bn_plif(xg, wp, bias.to(cuda), pw, 3, k, 1, w_unscale=un).float().cpu()
+        got_r = fused.conv_bn_plif(xg, wp, bias.to(cuda), pw, 3, k, 1, residual=res.to(cuda).half(),
+                                   w_unscale=un).float().cpu()
         mism = (got != want).float().mean().item()
         print("wide/residual (%d,%d,%d): mismatch %.3e rate %.3f" % (Cin, Cout, k, mism, want.mean().item()))
         assert 0.02 < want.mean().item() < 0.95
