@@ -286,14 +286,14 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = lif_v_init(d);
         __half* outp = reinterpret_cast<__half*>(a.out);
-        for (int t = 0; t < a.T; ++t) {
+        // unrolled over t so that acc[t][j] stays in registers (a runtime t would spill the tile to local memory)
+#pragma unroll
+        for (int t = 0; t < (TMAX == 1 ? 8 : TMAX); ++t) {
+          if (t >= a.T) break;
           float s[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float xin = 0.0f;
-#pragma unroll
-            for (int tt = 0; tt < TMAX; ++tt)
-              if (tt == (Tacc == 1 ? 0 : t)) xin = __uint_as_float(acc[tt][j]);
+            const float xin = __uint_as_float(TMAX == 1 ? acc[0][j] : (Tacc == 1 ? acc[0][j] : acc[t < TMAX ? t : 0][j]));
             const float h = lif_charge(d, v[j], __fadd_rn(__fmul_rn(xin, sUnscale[c16 * 16 + j]), sBias[c16 * 16 + j]));
             s[j] = lif_fire(d, h);
             v[j] = lif_reset(d, h, s[j]);
