@@ -26,6 +26,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include "lif.cuh"
 
 namespace {
@@ -85,6 +86,15 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -226,10 +236,15 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // The whole warp walks the (warp-uniform) loop nest so that descriptors live in uniform registers;
+    // only the elected lane issues tcgen05.mma / tcgen05.commit (a lone diverged lane would pay an
+    // ELECT + five R2UR per MMA and become the bottleneck of these small-N MMAs).
+    const bool leader = elect_one();
     // D = f32 (bit 4), A = B = f16 (format fields 0), K-major operands
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    const uint64_t a_desc0 = make_kmajor_desc<BK>(smem_u32(sA)), b_desc0 = make_kmajor_desc<BK>(smem_u32(sB));
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
     for (int kb = 0; kb < nkb; ++kb) {
@@ -238,25 +253,26 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         for (int i = 0; i < a.n_xsplit; ++i) {
           mbar_wait(fullA + sa, pa);
           tc_fence_after();
-          const uint64_t adesc = make_kmajor_desc<BK>(smem_u32(sA + sa * A_BYTES));
+          const uint64_t adesc = a_desc0 + (uint64_t)((sa * A_BYTES) >> 4);
           // product terms a_i * w_j with i + j < n_wsplit (the dropped ones are below fp32 rounding)
           for (int j = 0; j + i < a.n_wsplit; ++j) {
-            const uint64_t bdesc = make_kmajor_desc<BK>(smem_u32(sB + (sb * MAX_WSPLIT + j) * L::B_BYTES));
+            const uint64_t bdesc = b_desc0 + (uint64_t)(((sb * MAX_WSPLIT + j) * L::B_BYTES) >> 4);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k) {
               const uint32_t acc = (kb > 0 || i > 0 || j > 0 || k > 0) ? 1u : 0u;
-              tc_mma_f16(tmem_base + (uint32_t)(t * BLOCK_N), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2),
-                          idesc, acc);
+              if (leader)
+                tc_mma_f16(tmem_base + (uint32_t)(t * BLOCK_N), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2),
+                           idesc, acc);
             }
           }
-          tc_commit(emptyA + sa);  // frees the A slot once the MMAs above have read it
+          if (leader) tc_commit(emptyA + sa);  // frees the A slot once the MMAs above have read it
           if (++sa == SA) sa = 0, pa ^= 1;
         }
       }
-      tc_commit(emptyB + sb);
+      if (leader) tc_commit(emptyB + sb);
       if (++sb == SB) sb = 0, pb ^= 1;
     }
-    tc_commit(accum_full);
+    if (leader) tc_commit(accum_full);
   } else if (warp >= 2) {
     // ===================== epilogue: bias + LIF over t + store =====================
     const int lg = warp & 3;                 // TMEM lane group this warp may read
@@ -447,6 +463,10 @@ int launch_conv_t(int Tacc, const CUtensorMap& xmap, const CUtensorMap& wmap, co
 
 // K block = one swizzle row of 64 / 32 / 16 channels: least padded K plus a per-block overhead.
 int pick_bk(int Cin) {
+  if (const char* e = getenv("EAS_CONV_BK")) {   // experiment knob
+    const int v = atoi(e);
+    if (v == 64 || v == 32 || v == 16) return v;
+  }
   int best = 64, best_cost = 1 << 30;
   for (int bk : {64, 32, 16}) {
     const int nb = (Cin + bk - 1) / bk;
