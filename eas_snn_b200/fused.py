@@ -303,10 +303,16 @@ class _SPP(nn.Module):
         hid = self.conv1.conv[0].out_channels
         cat = torch.empty((T, B, H, W, hid * (len(self.ks) + 1)), dtype=ACT_DTYPE, device=x.device)
         y = self.conv1.run(x, T, out=cat[..., :hid])
-        y4 = y.flatten(0, 1).permute(0, 3, 1, 2)       # [T*B, C, H, W] view, channels-last memory
-        for i, k in enumerate(self.ks):
-            p = F.max_pool2d(y4, k, 1, k // 2)
-            cat[..., (i + 1) * hid:(i + 2) * hid].copy_(p.permute(0, 2, 3, 1).reshape(T, B, H, W, hid))
+        if len(self.ks) == 3 and hid % 8 == 0 and H * W * 256 <= 200 * 1024:
+            with torch.cuda.device(x.device):          # the three pools in one pass, into the concat slices
+                rc = _lib.lib().eas_spp_pool_fwd(_lib.ptr(cat), T * B, H, W, hid, cat.shape[-1], *self.ks,
+                                                 _lib.stream_ptr())
+            _lib.check(rc, "eas_spp_pool_fwd")
+        else:
+            y4 = y.flatten(0, 1).permute(0, 3, 1, 2)   # [T*B, C, H, W] view, channels-last memory
+            for i, k in enumerate(self.ks):
+                p = F.max_pool2d(y4, k, 1, k // 2)
+                cat[..., (i + 1) * hid:(i + 2) * hid].copy_(p.permute(0, 2, 3, 1).reshape(T, B, H, W, hid))
         return self.conv2.run(cat, T)
 
 

@@ -218,6 +218,12 @@ int eas_conv_bn_plif_fwd(const eas_conv_cfg* cfg, const void* x, const void* w_p
                          const float* bias, const float* plif_w, void* out, void* ws,
                          size_t ws_bytes, void* stream);
 
+/* SPP max-pools of the backbone (SPPBottleneck.m, yolox/models/network_blocks.py:128-147; stride 1,
+ * padding k/2).  cat: fp16 channels-last [n_images][H][W][ld] whose channels [0, C) hold x; channels
+ * [C, 2C), [2C, 3C), [3C, 4C) receive maxpool_k1 / k2 / k3 of x (the torch.cat of :146).  In place. */
+int eas_spp_pool_fwd(void* cat, int64_t n_images, int H, int W, int C, int ld, int k1, int k2, int k3,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

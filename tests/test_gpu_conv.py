@@ -176,3 +176,22 @@ def test_backbone_golden(cuda):
         assert got.shape == want.shape
         assert mism <= 2e-3, "%s mismatch %.3e (rate %.3f)" % (k, mism, want.mean().item())
         assert torch.equal(outs_T[k].float().cpu(), got), k + ": broadcast path differs from explicit T frames"
+
+
+@pytest.mark.parametrize("shape", [(5, 8, 10, 64), (3, 12, 20, 40), (2, 3, 4, 8)])
+def test_spp_pools_match_torch(cuda, shape):
+    """eas_spp_pool_fwd (5 / 9 / 13 max-pools into the concat slices) against torch.max_pool2d: exact."""
+    import torch.nn.functional as F
+    from eas_snn_b200 import _lib
+    N, H, W, C = shape
+    g = torch.Generator().manual_seed(N + H)
+    x = (torch.rand((N, H, W, C), generator=g) < 0.08).half() + (torch.rand((N, H, W, C), generator=g) < 0.02).half()
+    cat = torch.full((N, H, W, 4 * C + 8), 7.0, dtype=torch.float16, device=cuda)
+    cat[..., :C] = x.to(cuda)
+    rc = _lib.lib().eas_spp_pool_fwd(_lib.ptr(cat), N, H, W, C, 4 * C + 8, 5, 9, 13, _lib.stream_ptr())
+    assert rc == 0
+    x4 = x.permute(0, 3, 1, 2).float()
+    for i, k in enumerate((5, 9, 13)):
+        want = F.max_pool2d(x4, k, 1, k // 2).permute(0, 2, 3, 1)
+        assert torch.equal(cat[..., (i + 1) * C:(i + 2) * C].float().cpu(), want), k
+    assert torch.equal(cat[..., :C].cpu(), x) and bool((cat[..., 4 * C:] == 7).all())
