@@ -32,14 +32,16 @@
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int MAX_WSPLIT = 3;
-constexpr int NUM_THREADS = 192;
-constexpr uint32_t SPIN_LIMIT = 1u << 27;  // watchdog: trap instead of hanging the GPU
+constexpr int MAX_WSPLIT = 2;
+constexpr int N_ISSUERS = 3;        // MMA issuing warps (time steps t = w, w + 3, ...)
+constexpr int NUM_THREADS = (1 + N_ISSUERS + 8) * 32;   // TMA producer, MMA issuers, 2 x 4 epilogue warps
+constexpr uint32_t SPIN_LIMIT = 1u << 23;  // watchdog (~1 s): trap instead of hanging the GPU
 
 struct ConvArgs {
   int T, Tx, B, Ho, Wo, Cin, Cout, ksize, stride, pad;
   int n_wsplit, n_xsplit;
   int NB, TH, TW;
+  int TWp;                // tap-reuse mode: tile width incl. the 2 halo columns (rows of the tile = TH x TWp)
   int tiles_w, tiles_h, tiles_b, tiles_n;
   int out_ld, out_mode, res_ld;
   const __half* residual;   // SEW shortcut added to the spikes (network_blocks.py:99-103) or null
@@ -55,6 +57,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -109,8 +114,8 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate));   // volatile: ordered with the
+  // surrounding mbarrier waits / commits (all asm volatile); no memory clobber, so loop invariants stay in registers
 }
 // K-major swizzled shared-memory operand descriptor.  One K block is one swizzle row of BK fp16
 // (128 / 64 / 32 B), 8-row groups are 8 rows apart (1024 / 512 / 256 B).
@@ -138,24 +143,48 @@ __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-template <int BLOCK_N, int BK>
+// Tap-reuse mode (3x3, stride 1): an A slot holds the whole haloed input tile [(TH+2) x TWp pixels][BK] once;
+// the nine taps are nine start-address shifts (ky*TWp + kx rows) of the same operand.  TWp <= 64.
+constexpr int REUSE_ROWS = BLOCK_M + 2 * 64 + 8;
+
+template <int BLOCK_N, int BK, bool REUSE = false>
 struct SmemLayout {
-  static constexpr int A_BYTES = BLOCK_M * BK * 2;
+  static constexpr int A_BYTES = (REUSE ? REUSE_ROWS : BLOCK_M) * BK * 2;
   static constexpr int B_BYTES = BLOCK_N * BK * 2;
-  static constexpr int SA = (48 * 1024 / A_BYTES) > 8 ? 8 : (48 * 1024 / A_BYTES);  // A ring depth (<= 48 KB)
-  static constexpr int SB = BK == 64 ? 2 : 4;                                       // B ring depth
+  // one persistent CTA per SM: deep rings (A <= 128 KB, B <= 64 KB)
+  static constexpr int SA = 8;
+  static constexpr int SB = (64 * 1024 / (MAX_WSPLIT * B_BYTES)) > 8 ? 8 : (64 * 1024 / (MAX_WSPLIT * B_BYTES));
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + SA * A_BYTES;
   static constexpr int OFF_BAR = OFF_B + SB * MAX_WSPLIT * B_BYTES;
-  static constexpr int OFF_BIAS = OFF_BAR + 256;
-  static constexpr int TOTAL = OFF_BIAS + 2 * BLOCK_N * 4 + 1024;  // bias + unscale, + slack for the alignment
+  static constexpr int OFF_BIAS = OFF_BAR + 512;
+  static constexpr int TOTAL = OFF_BIAS + 4 * BLOCK_N * 4 + 1024;  // (bias + unscale) x 2 groups, + alignment slack
 };
 
-template <int BLOCK_N, int TMAX, int BK>
-__global__ void __launch_bounds__(NUM_THREADS)
+struct TileCoord {
+  int n0, wo0, ho0, b0;
+};
+__device__ __forceinline__ TileCoord tile_coord(const ConvArgs& a, int tile, int block_n) {
+  TileCoord c;
+  const int tn = tile % a.tiles_n;
+  tile /= a.tiles_n;
+  const int tw = tile % a.tiles_w;
+  tile /= a.tiles_w;
+  const int th = tile % a.tiles_h;
+  const int tb = tile / a.tiles_h;
+  c.n0 = tn * block_n, c.wo0 = tw * a.TW, c.ho0 = th * a.TH, c.b0 = tb * a.NB;
+  return c;
+}
+
+// Persistent kernel, one CTA per SM, tiles blockIdx.x, blockIdx.x + gridDim.x, ... (N tiles of the same
+// pixels are neighbours, so co-running CTAs share their A tiles in L2).  Warp 0 = TMA producer, warp 1 =
+// MMA issuer, warps 2-5 / 6-9 = two epilogue groups taking alternate tiles; the T accumulators are
+// double buffered in TMEM so that the main loop of tile i+1 overlaps the epilogue of tile i.
+template <int BLOCK_N, int TMAX, int BK, bool REUSE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
                     const ConvArgs a) {
-  using L = SmemLayout<BLOCK_N, BK>;
+  using L = SmemLayout<BLOCK_N, BK, REUSE>;
   constexpr int SA = L::SA, SB = L::SB, A_BYTES = L::A_BYTES, BLOCK_K = BK;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -166,48 +195,36 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   uint64_t* emptyA = bars + SA;         // [SA]
   uint64_t* fullB = bars + 2 * SA;      // [SB]
   uint64_t* emptyB = bars + 2 * SA + SB;
-  uint64_t* accum_full = bars + 2 * SA + 2 * SB;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 1);
-  float* sBias = reinterpret_cast<float*>(smem + L::OFF_BIAS);
-  float* sUnscale = sBias + BLOCK_N;
+  uint64_t* accum_full = bars + 2 * SA + 2 * SB;    // [2]
+  uint64_t* accum_empty = accum_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_empty + 2);
+  float* sBiasAll = reinterpret_cast<float*>(smem + L::OFF_BIAS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Tacc = a.Tx;  // accumulators: one per distinct input time step
-  constexpr uint32_t kCols = TMAX * BLOCK_N <= 32 ? 32 : TMAX * BLOCK_N <= 64 ? 64 : TMAX * BLOCK_N <= 128 ? 128
-                             : TMAX * BLOCK_N <= 256 ? 256 : 512;
-
-  // tile coordinates
-  int tile = blockIdx.x;
-  const int tn = tile % a.tiles_n;
-  tile /= a.tiles_n;
-  const int tw = tile % a.tiles_w;
-  tile /= a.tiles_w;
-  const int th = tile % a.tiles_h;
-  const int tb = tile / a.tiles_h;
-  const int n0 = tn * BLOCK_N, wo0 = tw * a.TW, ho0 = th * a.TH, b0 = tb * a.NB;
+  constexpr uint32_t kBufCols = TMAX * BLOCK_N;     // one accumulator set
+  constexpr uint32_t kCols = 2 * kBufCols <= 32 ? 32 : 2 * kBufCols <= 64 ? 64 : 2 * kBufCols <= 128 ? 128
+                             : 2 * kBufCols <= 256 ? 256 : 512;
+  static_assert(2 * kBufCols <= 512, "double-buffered accumulators must fit TMEM");
   const int ncb = (a.Cin + BLOCK_K - 1) / BLOCK_K;
   const int taps = a.ksize * a.ksize;
   const int nkb = taps * ncb;
+  const int n_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
+  const int n_issuers = Tacc < N_ISSUERS ? Tacc : N_ISSUERS;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
     for (int i = 0; i < SA; ++i) mbar_init(fullA + i, 1), mbar_init(emptyA + i, 1);
-    for (int i = 0; i < SB; ++i) mbar_init(fullB + i, 1), mbar_init(emptyB + i, 1);
-    mbar_init(accum_full, 1);
+    for (int i = 0; i < SB; ++i) mbar_init(fullB + i, 1), mbar_init(emptyB + i, n_issuers);
+    for (int i = 0; i < 2; ++i) mbar_init(accum_full + i, n_issuers), mbar_init(accum_empty + i, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == 1) {   // (also the first MMA issuer)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(kCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
-      sBias[i] = (n0 + i < a.Cout) ? a.bias[n0 + i] : 0.0f;
-      sUnscale[i] = (a.unscale && n0 + i < a.Cout) ? a.unscale[n0 + i] : 1.0f;
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -218,169 +235,281 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     // ===================== TMA producer =====================
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int tap = kb / ncb, cb = kb - tap * ncb;
-      const int ky = tap / a.ksize, kx = tap - ky * a.ksize;
-      mbar_wait(emptyB + sb, pb ^ 1);
-      mbar_expect_tx(fullB + sb, (uint32_t)(a.n_wsplit * L::B_BYTES));
-      for (int j = 0; j < a.n_wsplit; ++j)
-        tma_load_3d(sB + (sb * MAX_WSPLIT + j) * L::B_BYTES, &wmap, fullB + sb, cb * BLOCK_K, tap, j * a.Cout + n0);
-      if (++sb == SB) sb = 0, pb ^= 1;
-      for (int t = 0; t < Tacc; ++t) {
-        for (int i = 0; i < a.n_xsplit; ++i) {
-          mbar_wait(emptyA + sa, pa ^ 1);
-          mbar_expect_tx(fullA + sa, (uint32_t)A_BYTES);
-          tma_load_5d(sA + sa * A_BYTES, &xmap, fullA + sa, cb * BLOCK_K, wo0 * a.stride + kx - a.pad,
-                      ho0 * a.stride + ky - a.pad, b0, i * a.Tx + t);
-          if (++sa == SA) sa = 0, pa ^= 1;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    // The whole warp walks the (warp-uniform) loop nest so that descriptors live in uniform registers;
-    // only the elected lane issues tcgen05.mma / tcgen05.commit (a lone diverged lane would pay an
-    // ELECT + five R2UR per MMA and become the bottleneck of these small-N MMAs).
-    const bool leader = elect_one();
-    // D = f32 (bit 4), A = B = f16 (format fields 0), K-major operands
-    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-    const uint64_t a_desc0 = make_kmajor_desc<BK>(smem_u32(sA)), b_desc0 = make_kmajor_desc<BK>(smem_u32(sB));
-    int sa = 0, sb = 0;
-    uint32_t pa = 0, pb = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      mbar_wait(fullB + sb, pb);
-      for (int t = 0; t < Tacc; ++t) {
-        for (int i = 0; i < a.n_xsplit; ++i) {
-          mbar_wait(fullA + sa, pa);
-          tc_fence_after();
-          const uint64_t adesc = a_desc0 + (uint64_t)((sa * A_BYTES) >> 4);
-          // product terms a_i * w_j with i + j < n_wsplit (the dropped ones are below fp32 rounding)
-          for (int j = 0; j + i < a.n_wsplit; ++j) {
-            const uint64_t bdesc = b_desc0 + (uint64_t)(((sb * MAX_WSPLIT + j) * L::B_BYTES) >> 4);
-#pragma unroll
-            for (int k = 0; k < BLOCK_K / 16; ++k) {
-              const uint32_t acc = (kb > 0 || i > 0 || j > 0 || k > 0) ? 1u : 0u;
-              if (leader)
-                tc_mma_f16(tmem_base + (uint32_t)(t * BLOCK_N), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2),
-                           idesc, acc);
-            }
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const TileCoord tc = tile_coord(a, tile, BLOCK_N);
+      if constexpr (REUSE) {
+        // channel block outer: the haloed tile of every time step once, then the nine weight taps
+        const uint32_t box_bytes = (uint32_t)((a.TH + 2) * a.TWp * BLOCK_K * 2);
+        for (int cb = 0; cb < ncb; ++cb) {
+          for (int t = 0; t < Tacc; ++t) {
+            mbar_wait(emptyA + sa, pa ^ 1);
+            mbar_expect_tx(fullA + sa, box_bytes);
+            tma_load_5d(sA + sa * A_BYTES, &xmap, fullA + sa, cb * BLOCK_K, tc.wo0 - 1, tc.ho0 - 1, tc.b0, t);
+            if (++sa == SA) sa = 0, pa ^= 1;
           }
-          if (leader) tc_commit(emptyA + sa);  // frees the A slot once the MMAs above have read it
-          if (++sa == SA) sa = 0, pa ^= 1;
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(emptyB + sb, pb ^ 1);
+            mbar_expect_tx(fullB + sb, (uint32_t)(a.n_wsplit * L::B_BYTES));
+            for (int j = 0; j < a.n_wsplit; ++j)
+              tma_load_3d(sB + (sb * MAX_WSPLIT + j) * L::B_BYTES, &wmap, fullB + sb, cb * BLOCK_K, tap,
+                          j * a.Cout + tc.n0);
+            if (++sb == SB) sb = 0, pb ^= 1;
+          }
+        }
+        continue;
+      }
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int tap = kb / ncb, cb = kb - tap * ncb;
+        const int ky = tap / a.ksize, kx = tap - ky * a.ksize;
+        mbar_wait(emptyB + sb, pb ^ 1);
+        mbar_expect_tx(fullB + sb, (uint32_t)(a.n_wsplit * L::B_BYTES));
+        for (int j = 0; j < a.n_wsplit; ++j)
+          tma_load_3d(sB + (sb * MAX_WSPLIT + j) * L::B_BYTES, &wmap, fullB + sb, cb * BLOCK_K, tap, j * a.Cout + tc.n0);
+        if (++sb == SB) sb = 0, pb ^= 1;
+        for (int t = 0; t < Tacc; ++t) {
+          for (int i = 0; i < a.n_xsplit; ++i) {
+            mbar_wait(emptyA + sa, pa ^ 1);
+            mbar_expect_tx(fullA + sa, (uint32_t)A_BYTES);
+            tma_load_5d(sA + sa * A_BYTES, &xmap, fullA + sa, cb * BLOCK_K, tc.wo0 * a.stride + kx - a.pad,
+                        tc.ho0 * a.stride + ky - a.pad, tc.b0, i * a.Tx + t);
+            if (++sa == SA) sa = 0, pa ^= 1;
+          }
         }
       }
-      if (leader) tc_commit(emptyB + sb);
-      if (++sb == SB) sb = 0, pb ^= 1;
     }
-    if (leader) tc_commit(accum_full);
-  } else if (warp >= 2) {
-    // ===================== epilogue: bias + LIF over t + store =====================
-    const int lg = warp & 3;                 // TMEM lane group this warp may read
+  } else if (warp >= 1 && warp <= N_ISSUERS) {
+    // ===================== MMA issuers =====================
+    // One issuing warp per time step (t = warp-1, + N_ISSUERS): the T accumulator chains are independent and issuing,
+    // not the tensor pipe, is what bounds these small-N MMAs.  Each warp walks the
+    // (warp-uniform) loop nest so that descriptors live in uniform registers; only its elected lane issues
+    // tcgen05.mma / tcgen05.commit.
+    const int wi = warp - 1;
+    if (wi < n_issuers) {
+      const bool leader = elect_one();
+      // D = f32 (bit 4), A = B = f16 (format fields 0), K-major operands
+      constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+      const uint64_t a_desc0 = make_kmajor_desc<BK>(smem_u32(sA)), b_desc0 = make_kmajor_desc<BK>(smem_u32(sB));
+      const int nx = REUSE ? 1 : a.n_xsplit, nw = a.n_wsplit;
+      const int per_kb = Tacc * nx;           // A slots consumed per K block (per channel block in tap-reuse mode)
+      int sa = 0, sb = 0;                     // ring positions at the start of the current K block
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(accum_empty + buf, ((it >> 1) & 1) ^ 1);   // the epilogue of tile it-2 has drained this buffer
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)buf * kBufCols;
+        const int n_outer = REUSE ? ncb : nkb;
+        for (int kb = 0; kb < n_outer; ++kb) {
+          const int n_taps = REUSE ? 9 : 1;
+          for (int tap = 0; tap < n_taps; ++tap) {
+            mbar_wait(fullB + sb, pb);
+            const uint64_t bdesc = b_desc0 + (uint64_t)((sb * MAX_WSPLIT * L::B_BYTES) >> 4);
+            uint32_t shift = 0;
+            if constexpr (REUSE) {
+              const int ky = tap / 3, kx = tap - ky * 3;
+              shift = (uint32_t)(((ky * a.TWp + kx) * BLOCK_K * 2) >> 4);   // rows -> descriptor units
+            }
+#pragma unroll
+            for (int tt = 0; tt < (TMAX + N_ISSUERS - 1) / N_ISSUERS; ++tt) {
+              const int t = wi + N_ISSUERS * tt;
+              if (t < Tacc) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  if (i < nx) {
+                    int st = sa + t * nx + i;
+                    uint32_t pt = pa;
+                    while (st >= SA) st -= SA, pt ^= 1;
+                    if (tap == 0) {
+                      mbar_wait(fullA + st, pt);
+                      tc_fence_after();
+                    }
+                    const uint64_t adesc = a_desc0 + (uint64_t)((st * A_BYTES) >> 4) + (uint64_t)shift;
+                    if (leader) {
+                      // product terms a_i * w_j with i + j < n_wsplit (the dropped ones are below fp32 rounding)
+#pragma unroll
+                      for (int j = 0; j < 2; ++j) {
+                        if (j + i < nw) {
+#pragma unroll
+                          for (int k = 0; k < BLOCK_K / 16; ++k)
+                            tc_mma_f16(d0 + (uint32_t)(t * BLOCK_N), adesc + (uint64_t)(k * 2),
+                                       bdesc + (uint64_t)(((j * L::B_BYTES) >> 4) + k * 2), idesc,
+                                       (kb > 0 || tap > 0 || i > 0 || j > 0 || k > 0) ? 1u : 0u);
+                        }
+                      }
+                      if (tap == n_taps - 1) tc_commit(emptyA + st);  // frees the A slot once its MMAs have read it
+                    }
+                  }
+                }
+              }
+            }
+            if (leader) tc_commit(emptyB + sb);
+            if (++sb == SB) sb = 0, pb ^= 1;
+          }
+          sa += per_kb;
+          while (sa >= SA) sa -= SA, pa ^= 1;
+        }
+        if (leader) tc_commit(accum_full + buf);
+      }
+    }
+  } else if (warp > N_ISSUERS) {
+    // ===================== epilogue: bias + LIF over t + store (two groups, alternate tiles) =====================
+    const int ew = warp - 1 - N_ISSUERS;     // epilogue warp 0..7
+    const int grp = ew >> 2;                 // 0: even tiles of this CTA, 1: odd tiles
+    const int lg = warp & 3;                 // TMEM lane group this warp may read (any 4 consecutive warps cover all)
     const int m = lg * 32 + lane;            // pixel of the tile
-    const int nb = m / (a.TH * a.TW);
-    const int rem = m - nb * (a.TH * a.TW);
-    const int ph = rem / a.TW, pw = rem - ph * a.TW;
-    const int b = b0 + nb, ho = ho0 + ph, wo = wo0 + pw;
-    const bool valid = b < a.B && ho < a.Ho && wo < a.Wo;
+    const int gtid = (ew & 3) * 32 + lane;
+    float* sBias = sBiasAll + grp * 2 * BLOCK_N;
+    float* sUnscale = sBias + BLOCK_N;
+    // row m of the tile -> (image, row, column); in tap-reuse mode rows run over the haloed width TWp and
+    // the last two columns of every row (and the rows past TH) are garbage positions
+    int nb, ph, pw;
+    bool row_ok = true;
+    if constexpr (REUSE) {
+      nb = 0, ph = m / a.TWp, pw = m - ph * a.TWp;
+      row_ok = ph < a.TH && pw < a.TW;
+    } else {
+      nb = m / (a.TH * a.TW);
+      const int rem = m - nb * (a.TH * a.TW);
+      ph = rem / a.TW, pw = rem - ph * a.TW;
+    }
     const LifDyn d = make_lif(a.plif_w ? *a.plif_w : 0.0f, a.vth, a.hard_reset, a.vreset, a.decay_input);
-    const int64_t pix = ((int64_t)b * a.Ho + ho) * a.Wo + wo;          // within one time step
     const int64_t step = (int64_t)a.B * a.Ho * a.Wo;                   // pixels per time step
-    mbar_wait(accum_full, 0);
-    tc_fence_after();
-    for (int c16 = 0; c16 < BLOCK_N / 16; ++c16) {
-      const int ch0 = n0 + c16 * 16;
-      if (ch0 >= a.Cout) break;  // warp-uniform
-      uint32_t acc[TMAX][16];
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != grp) continue;
+      const TileCoord tc = tile_coord(a, tile, BLOCK_N);
+      const int n0 = tc.n0;
+      const int b = tc.b0 + nb, ho = tc.ho0 + ph, wo = tc.wo0 + pw;
+      const bool valid = row_ok && b < a.B && ho < a.Ho && wo < a.Wo;
+      const int64_t pix = ((int64_t)b * a.Ho + ho) * a.Wo + wo;          // within one time step
+      // the group's previous tile is done with sBias (every thread passed this barrier after its last read)
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      for (int i = gtid; i < BLOCK_N; i += 128) {
+        sBias[i] = (n0 + i < a.Cout) ? a.bias[n0 + i] : 0.0f;
+        sUnscale[i] = (a.unscale && n0 + i < a.Cout) ? a.unscale[n0 + i] : 1.0f;
+      }
+      const bool res_vec = a.residual != nullptr && valid && a.out_mode == EAS_CONV_OUT_SPIKES &&
+                           (a.res_ld & 7) == 0 && (n0 & 7) == 0;
+      constexpr int RT = TMAX == 4 ? 4 : 1;   // time steps whose shortcut is prefetched (T <= 4 layers)
+      uint4 rres[RT][2];
+      auto load_res = [&](int c16, uint4 (&r)[RT][2]) {
+        const int ch0 = n0 + c16 * 16;
 #pragma unroll
-      for (int t = 0; t < TMAX; ++t)
-        if (t < Tacc) tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(t * BLOCK_N + c16 * 16), acc[t]);
-      tmem_ld_wait();
-      if (!valid) continue;
-      const int nch = min(16, a.Cout - ch0);
-      if (a.out_mode == EAS_CONV_OUT_SPIKES) {
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = lif_v_init(d);
-        __half* outp = reinterpret_cast<__half*>(a.out);
-        // unrolled over t so that acc[t][j] stays in registers (a runtime t would spill the tile to local memory)
-#pragma unroll
-        for (int t = 0; t < (TMAX == 1 ? 8 : TMAX); ++t) {
-          if (t >= a.T) break;
-          float s[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float xin = __uint_as_float(TMAX == 1 ? acc[0][j] : (Tacc == 1 ? acc[0][j] : acc[t < TMAX ? t : 0][j]));
-            const float h = lif_charge(d, v[j], __fadd_rn(__fmul_rn(xin, sUnscale[c16 * 16 + j]), sBias[c16 * 16 + j]));
-            s[j] = lif_fire(d, h);
-            v[j] = lif_reset(d, h, s[j]);
-          }
-          __half* dst = outp + ((int64_t)t * step + pix) * a.out_ld + ch0;
-          if (a.residual) {  // SEW add: y = spikes + x (small integers, exact in fp16)
-            const __half* rp = a.residual + ((int64_t)t * step + pix) * a.res_ld + ch0;
-            if (nch == 16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-              const uint4 r0 = reinterpret_cast<const uint4*>(rp)[0], r1 = reinterpret_cast<const uint4*>(rp)[1];
-              const __half* rb0 = reinterpret_cast<const __half*>(&r0);
-              const __half* rb1 = reinterpret_cast<const __half*>(&r1);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) s[j] += __half2float(rb0[j]), s[8 + j] += __half2float(rb1[j]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (j < nch) s[j] += __half2float(rp[j]);
-            }
-          }
-          if (nch == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-            uint4 q0 = make_uint4(pack_f16(s[0], s[1]), pack_f16(s[2], s[3]), pack_f16(s[4], s[5]),
-                                  pack_f16(s[6], s[7]));
-            uint4 q1 = make_uint4(pack_f16(s[8], s[9]), pack_f16(s[10], s[11]), pack_f16(s[12], s[13]),
-                                  pack_f16(s[14], s[15]));
-            reinterpret_cast<uint4*>(dst)[0] = q0;
-            reinterpret_cast<uint4*>(dst)[1] = q1;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < nch) dst[j] = __float2half_rn(s[j]);
+        for (int t = 0; t < RT; ++t) {
+          if (TMAX == 4 && t < a.T && res_vec && ch0 + 16 <= a.Cout) {
+            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + ((int64_t)t * step + pix) * a.res_ld + ch0);
+            r[t][0] = ld_stream_u4(rp), r[t][1] = ld_stream_u4(rp + 1);
           }
         }
-      } else {
+      };
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // sBias visible to the group
+      mbar_wait(accum_full + grp, (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)grp * kBufCols;
+      // live 16-channel chunks of this N tile (warp-uniform)
+      const int NCH = min(BLOCK_N / 16, (a.Cout - n0 + 15) / 16);
+#pragma unroll 1
+      for (int c16 = 0; c16 < NCH; ++c16) {
+        const int ch0 = n0 + c16 * 16;
+        load_res(c16, rres);    // SEW shortcut of this chunk: in flight during the TMEM reads and the first LIF steps
+        uint32_t acc[TMAX][16];
 #pragma unroll
-        for (int t = 0; t < TMAX; ++t) {
-          if (t < Tacc) {
-            if (a.out_mode == EAS_CONV_OUT_PREACT) {
-              float* dst = reinterpret_cast<float*>(a.out) + ((int64_t)t * step + pix) * a.out_ld + ch0;
+        for (int t = 0; t < TMAX; ++t)
+          if (t < Tacc) tmem_ld16(tbase + (uint32_t)(t * BLOCK_N + c16 * 16), acc[t]);
+        tmem_ld_wait();
+        if (c16 == NCH - 1) {   // last TMEM read of this tile: hand the accumulator buffer back (once per warp)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(accum_empty + grp);
+        }
+        if (valid) {
+          const int nch = min(16, a.Cout - ch0);
+          if (a.out_mode == EAS_CONV_OUT_SPIKES) {
+            float v[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (j < nch)
-                  dst[j] = __fadd_rn(__fmul_rn(__uint_as_float(acc[t][j]), sUnscale[c16 * 16 + j]), sBias[c16 * 16 + j]);
-            } else {  // SiLU, written as two fp16 planes hi + lo whose sum is the fp32 value to 2^-22
-              __half* outp = reinterpret_cast<__half*>(a.out);
-              const int64_t plane = (int64_t)Tacc * step * a.out_ld;
-              __half* dst = outp + ((int64_t)t * step + pix) * a.out_ld + ch0;
-              float y[16];
+            for (int j = 0; j < 16; ++j) v[j] = lif_v_init(d);
+            __half* outp = reinterpret_cast<__half*>(a.out);
+            // unrolled over t so that acc[t][j] stays in registers (a runtime t would spill the tile to local memory)
+#pragma unroll
+            for (int t = 0; t < (TMAX == 1 ? 8 : TMAX); ++t) {
+              if (t >= a.T) break;
+              float sp[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const float xv = __fadd_rn(__fmul_rn(__uint_as_float(acc[t][j]), sUnscale[c16 * 16 + j]), sBias[c16 * 16 + j]);
-                y[j] = fminf(fmaxf(xv * eas_sigmoid(xv), -65504.0f), 65504.0f);
+                const float xin = __uint_as_float(TMAX == 1 ? acc[0][j] : (Tacc == 1 ? acc[0][j] : acc[t < TMAX ? t : 0][j]));
+                const float h = lif_charge(d, v[j], __fadd_rn(__fmul_rn(xin, sUnscale[c16 * 16 + j]), sBias[c16 * 16 + j]));
+                sp[j] = lif_fire(d, h);
+                v[j] = lif_reset(d, h, sp[j]);
               }
-              if (nch == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((plane & 7) == 0)) {
-                uint32_t hi[8], lo[8];
+              __half* dst = outp + ((int64_t)t * step + pix) * a.out_ld + ch0;
+              if (a.residual) {  // SEW add: y = spikes + x (small integers, exact in fp16)
+                if (TMAX == 4 && res_vec && nch == 16) {
+                  const __half* rb0 = reinterpret_cast<const __half*>(&rres[t < RT ? t : 0][0]);
+                  const __half* rb1 = reinterpret_cast<const __half*>(&rres[t < RT ? t : 0][1]);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const __half2 h2 = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
-                  const float2 hf = __half22float2(h2);
-                  const __half2 l2 = __floats2half2_rn(y[2 * j] - hf.x, y[2 * j + 1] - hf.y);
-                  hi[j] = *reinterpret_cast<const uint32_t*>(&h2), lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                  for (int j = 0; j < 8; ++j) sp[j] += __half2float(rb0[j]), sp[8 + j] += __half2float(rb1[j]);
+                } else {
+                  const __half* rp = a.residual + ((int64_t)t * step + pix) * a.res_ld + ch0;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (j < nch) sp[j] += __half2float(rp[j]);
                 }
-                reinterpret_cast<uint4*>(dst)[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                reinterpret_cast<uint4*>(dst)[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                reinterpret_cast<uint4*>(dst + plane)[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                reinterpret_cast<uint4*>(dst + plane)[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+              }
+              if (nch == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                uint4 q0 = make_uint4(pack_f16(sp[0], sp[1]), pack_f16(sp[2], sp[3]), pack_f16(sp[4], sp[5]),
+                                      pack_f16(sp[6], sp[7]));
+                uint4 q1 = make_uint4(pack_f16(sp[8], sp[9]), pack_f16(sp[10], sp[11]), pack_f16(sp[12], sp[13]),
+                                      pack_f16(sp[14], sp[15]));
+                reinterpret_cast<uint4*>(dst)[0] = q0;
+                reinterpret_cast<uint4*>(dst)[1] = q1;
               } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  if (j < nch) {
-                    const __half hi = __float2half_rn(y[j]);
-                    dst[j] = hi, dst[plane + j] = __float2half_rn(y[j] - __half2float(hi));
+                for (int j = 0; j < 16; ++j)
+                  if (j < nch) dst[j] = __float2half_rn(sp[j]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < TMAX; ++t) {
+              if (t < Tacc) {
+                if (a.out_mode == EAS_CONV_OUT_PREACT) {
+                  float* dst = reinterpret_cast<float*>(a.out) + ((int64_t)t * step + pix) * a.out_ld + ch0;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (j < nch)
+                      dst[j] = __fadd_rn(__fmul_rn(__uint_as_float(acc[t][j]), sUnscale[c16 * 16 + j]), sBias[c16 * 16 + j]);
+                } else {  // SiLU, written as two fp16 planes hi + lo whose sum is the fp32 value to 2^-22
+                  __half* outp = reinterpret_cast<__half*>(a.out);
+                  const int64_t plane = (int64_t)Tacc * step * a.out_ld;
+                  __half* dst = outp + ((int64_t)t * step + pix) * a.out_ld + ch0;
+                  float y[16];
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const float xv = __fadd_rn(__fmul_rn(__uint_as_float(acc[t][j]), sUnscale[c16 * 16 + j]), sBias[c16 * 16 + j]);
+                    y[j] = fminf(fmaxf(xv * eas_sigmoid(xv), -65504.0f), 65504.0f);
+                  }
+                  if (nch == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((plane & 7) == 0)) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      const __half2 h2 = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+                      const float2 hf = __half22float2(h2);
+                      const __half2 l2 = __floats2half2_rn(y[2 * j] - hf.x, y[2 * j + 1] - hf.y);
+                      hi[j] = *reinterpret_cast<const uint32_t*>(&h2), lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                    }
+                    reinterpret_cast<uint4*>(dst)[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    reinterpret_cast<uint4*>(dst)[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    reinterpret_cast<uint4*>(dst + plane)[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    reinterpret_cast<uint4*>(dst + plane)[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                      if (j < nch) {
+                        const __half hi = __float2half_rn(y[j]);
+                        dst[j] = hi, dst[plane + j] = __float2half_rn(y[j] - __half2float(hi));
+                      }
+                    }
                   }
                 }
               }
@@ -417,7 +546,7 @@ int check_conv(const eas_conv_cfg* c) {
   EAS_REQUIRE(c->B >= 1 && c->H >= 1 && c->W >= 1 && c->Cin >= 8 && c->Cout >= 1, EAS_E_SHAPE);
   EAS_REQUIRE(c->Cin % 8 == 0, EAS_E_SHAPE);  // TMA global strides are multiples of 16 B
   EAS_REQUIRE((c->ksize == 1 || c->ksize == 3) && (c->stride == 1 || c->stride == 2), EAS_E_UNSUPPORTED);
-  EAS_REQUIRE(c->n_wsplit >= 1 && c->n_wsplit <= MAX_WSPLIT && c->n_xsplit >= 1 && c->n_xsplit <= 3, EAS_E_UNSUPPORTED);
+  EAS_REQUIRE(c->n_wsplit >= 1 && c->n_wsplit <= 2 && c->n_xsplit >= 1 && c->n_xsplit <= 2, EAS_E_UNSUPPORTED);
   EAS_REQUIRE(c->out_mode >= EAS_CONV_OUT_SPIKES && c->out_mode <= EAS_CONV_OUT_SILU2, EAS_E_UNSUPPORTED);
   EAS_REQUIRE(c->x_ld == 0 || (c->x_ld >= c->Cin && c->x_ld % 8 == 0), EAS_E_SHAPE);
   EAS_REQUIRE(c->out_ld == 0 || c->out_ld >= c->Cout, EAS_E_SHAPE);
@@ -441,10 +570,10 @@ void pick_tile(int B, int Ho, int Wo, int stride, int* NB, int* TH, int* TW) {
   }
 }
 
-template <int BLOCK_N, int TMAX, int BK>
+template <int BLOCK_N, int TMAX, int BK, bool REUSE = false>
 int launch_conv(const CUtensorMap& xmap, const CUtensorMap& wmap, const ConvArgs& a, int64_t grid, cudaStream_t st) {
-  using L = SmemLayout<BLOCK_N, BK>;
-  auto kern = conv_bn_plif_kernel<BLOCK_N, TMAX, BK>;
+  using L = SmemLayout<BLOCK_N, BK, REUSE>;
+  auto kern = conv_bn_plif_kernel<BLOCK_N, TMAX, BK, REUSE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
   if (e != cudaSuccess) return (int)e;
   kern<<<(unsigned)grid, NUM_THREADS, L::TOTAL, st>>>(xmap, wmap, a);
@@ -455,10 +584,33 @@ int launch_conv(const CUtensorMap& xmap, const CUtensorMap& wmap, const ConvArgs
 template <int BLOCK_N, int BK>
 int launch_conv_t(int Tacc, const CUtensorMap& xmap, const CUtensorMap& wmap, const ConvArgs& a, int64_t grid,
                   cudaStream_t st) {
+  // two accumulator sets of Tacc x BLOCK_N columns must fit the 512 TMEM columns
   if (Tacc <= 1) return launch_conv<BLOCK_N, 1, BK>(xmap, wmap, a, grid, st);
-  if (Tacc <= 4 || BLOCK_N == 128) return launch_conv<BLOCK_N, 4, BK>(xmap, wmap, a, grid, st);
-  if constexpr (BLOCK_N <= 64) return launch_conv<BLOCK_N, 8, BK>(xmap, wmap, a, grid, st);
+  if (Tacc <= 4) return launch_conv<BLOCK_N, 4, BK>(xmap, wmap, a, grid, st);
+  if constexpr (BLOCK_N <= 32) return launch_conv<BLOCK_N, 8, BK>(xmap, wmap, a, grid, st);
   return EAS_E_UNSUPPORTED;
+}
+
+template <int BLOCK_N>
+int launch_conv_reuse(int Tacc, const CUtensorMap& xmap, const CUtensorMap& wmap, const ConvArgs& a, int64_t grid,
+                      cudaStream_t st) {
+  if (Tacc <= 1) return launch_conv<BLOCK_N, 1, 32, true>(xmap, wmap, a, grid, st);
+  if (Tacc <= 4) return launch_conv<BLOCK_N, 4, 32, true>(xmap, wmap, a, grid, st);
+  if constexpr (BLOCK_N <= 32) return launch_conv<BLOCK_N, 8, 32, true>(xmap, wmap, a, grid, st);
+  return EAS_E_UNSUPPORTED;
+}
+
+// Tap-reuse tile for a 3x3 stride-1 layer: TH x (TW + 2) <= 128 rows with the best useful fraction.
+double pick_reuse_tile(int Ho, int Wo, int* TH, int* TW) {
+  double best = 0.0;
+  for (int tw = 4; tw <= Wo && tw <= 62; ++tw) {
+    const int th_max = 128 / (tw + 2);
+    for (int th = 1; th <= th_max && th <= Ho; ++th) {
+      const double eff = (double)Ho * Wo / ((double)eas_ceil_div(Ho, th) * eas_ceil_div(Wo, tw) * 128.0);
+      if (eff > best) best = eff, *TH = th, *TW = tw;
+    }
+  }
+  return best;
 }
 
 // K block = one swizzle row of 64 / 32 / 16 channels: least padded K plus a per-block overhead.
@@ -499,21 +651,27 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
   a.T = c->T, a.Tx = c->Tx, a.B = c->B, a.Ho = Ho, a.Wo = Wo, a.Cin = c->Cin, a.Cout = c->Cout;
   a.ksize = c->ksize, a.stride = c->stride, a.pad = pad, a.n_wsplit = c->n_wsplit, a.n_xsplit = c->n_xsplit;
   pick_tile(c->B, Ho, Wo, c->stride, &a.NB, &a.TH, &a.TW);
-  const int BK = pick_bk(c->Cin);
+  // 3x3 stride-1 layers on spike inputs: load every haloed input tile once and realise the nine taps as
+  // descriptor shifts (9x less activation traffic from L2), when the padded tiles waste < 30 % of the MMA rows
+  bool reuse = false;
+  if (c->ksize == 3 && c->stride == 1 && c->n_xsplit == 1 && c->Cin >= 32 && !getenv("EAS_CONV_NO_REUSE")) {
+    int th = 0, tw = 0;
+    if (pick_reuse_tile(Ho, Wo, &th, &tw) >= 0.70) reuse = true, a.NB = 1, a.TH = th, a.TW = tw, a.TWp = tw + 2;
+  }
+  const int BK = reuse ? 32 : pick_bk(c->Cin);
   const int taps_ = c->ksize * c->ksize;
   const int nkb_ = taps_ * (int)eas_ceil_div(c->Cin, BK);
-  // wide N tile (A re-read from L2 half as often) only where the K loop is long enough to hide the
-  // single-CTA-per-SM epilogue, and the T accumulators still fit 512 TMEM columns
-  const bool wide = BK == 64 && c->Cout >= 128 && nkb_ >= 16 && c->Tx <= 4;
-  const int BLOCK_N = c->Cout <= 32 ? 32 : (wide ? 128 : 64);
+  // 64 output channels per tile; 32 for thin layers and for more than 4 distinct time steps (TMEM)
+  const int BLOCK_N = (c->Cout <= 32 || c->Tx > 4) ? 32 : 64;
   a.tiles_w = (int)eas_ceil_div(Wo, a.TW), a.tiles_h = (int)eas_ceil_div(Ho, a.TH);
   a.tiles_b = (int)eas_ceil_div(c->B, a.NB), a.tiles_n = (int)eas_ceil_div(c->Cout, BLOCK_N);
   a.out_ld = out_ld, a.out_mode = c->out_mode;
   a.residual = (const __half*)c->residual, a.res_ld = c->res_ld ? c->res_ld : c->Cout;
   a.vth = c->v_threshold, a.vreset = c->v_reset, a.hard_reset = c->hard_reset, a.decay_input = c->decay_input;
   a.bias = bias, a.unscale = c->w_unscale, a.plif_w = plif_w, a.out = out;
-  const int64_t grid = (int64_t)a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
-  EAS_REQUIRE(grid > 0 && grid < (1ll << 31), EAS_E_SHAPE);
+  const int64_t n_tiles = (int64_t)a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
+  EAS_REQUIRE(n_tiles > 0 && n_tiles < (1ll << 31), EAS_E_SHAPE);
+  const int64_t grid = n_tiles < EAS_NUM_SMS ? n_tiles : EAS_NUM_SMS;   // persistent: one CTA per SM
 
   // activations: [plane*Tx][B][H][W][x_ld] fp16, innermost first for the tensor map
   CUtensorMap xmap, wmap;
@@ -526,6 +684,7 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
                              (cuuint64_t)c->B * c->H * c->W * x_ld * 2};
     cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)(a.TW * c->stride), (cuuint32_t)(a.TH * c->stride),
                          (cuuint32_t)a.NB, 1};
+    if (reuse) box[1] = (cuuint32_t)a.TWp, box[2] = (cuuint32_t)(a.TH + 2);
     cuuint32_t estr[5] = {1, (cuuint32_t)c->stride, (cuuint32_t)c->stride, 1, 1};
     CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -549,8 +708,9 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
   (BK == 64 ? launch_conv_t<BN_, 64>(Tacc, xmap, wmap, a, grid, st)                   \
    : BK == 32 ? launch_conv_t<BN_, 32>(Tacc, xmap, wmap, a, grid, st)                 \
               : launch_conv_t<BN_, 16>(Tacc, xmap, wmap, a, grid, st))
+  if (reuse) return BLOCK_N == 32 ? launch_conv_reuse<32>(Tacc, xmap, wmap, a, grid, st)
+                                  : launch_conv_reuse<64>(Tacc, xmap, wmap, a, grid, st);
   if (BLOCK_N == 32) return EAS_CONV_BK(32);
-  if (BLOCK_N == 128) return launch_conv_t<128, 64>(Tacc, xmap, wmap, a, grid, st);
   return EAS_CONV_BK(64);
 #undef EAS_CONV_BK
 }
