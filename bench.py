@@ -266,9 +266,12 @@ def run_ours(args):
                 sl["in_ready"].record(s_in)
             with torch.cuda.stream(s_cmp):
                 s_cmp.wait_event(sl["in_ready"])
+                # the frames this slot produced two steps ago have reached the host: their memory (freed just
+                # below, when the slot's reference is replaced) may be reused by this step's allocations
+                s_cmp.wait_event(sl["out_done"])
                 with torch.no_grad():
                     frames = model.forward_dat(sl["rec"][:nrec], sl["rng"], H, W)   # public module API
-                frames.record_stream(s_out)
+                sl["frames"] = frames
                 sl["cmp_done"].record(s_cmp)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(sl["cmp_done"])
@@ -277,7 +280,7 @@ def run_ours(args):
             n += nrec
         return n
 
-    e2e_loop(max(args.warmup, 3))
+    e2e_loop(max(args.warmup, 10))       # long enough for the caching allocator to reach its steady state
     barrier()
     t0 = time.perf_counter()
     n_e2e = e2e_loop(args.steps)
