@@ -351,6 +351,23 @@ def run_ours(args):
         model.algo = "fp32"
         t_smp_fp32 = time_call(lambda r: model(hist_fixed))
         model.algo = "auto"
+    # stand-alone multi-step PLIF (a-4) through the C ABI: T = 3, the SYOLOX-M dark2 activation size
+    import ctypes as C
+    from eas_snn_b200 import _lib
+    Lc = _lib.lib()
+    pT, pN = 3, BATCH * 96 * 64 * 80
+    px = torch.rand((pT, pN), device=dev) * 1.5
+    ps, pg, pdx = torch.empty_like(px), torch.rand((pT, pN), device=dev), torch.empty_like(px)
+    pw, pgw = torch.zeros((), device=dev), torch.zeros((), device=dev)
+    pcfg = _lib.PlifCfg(T=pT, N=pN, v_threshold=1.0, hard_reset=0, v_reset=0.0, decay_input=0, detach_reset=0,
+                        surrogate=0, alpha=2.0, dtype=_lib.EAS_F32)
+    pwsb = Lc.eas_plif_bwd_ws_bytes(C.byref(pcfg))
+    pws = torch.empty(pwsb, dtype=torch.uint8, device=dev)
+    t_plif_f = time_call(lambda r: Lc.eas_plif_fwd(C.byref(pcfg), _lib.ptr(px), _lib.ptr(pw), None, _lib.ptr(ps), None,
+                                                   _lib.stream_ptr()))
+    t_plif_b = time_call(lambda r: Lc.eas_plif_bwd(C.byref(pcfg), _lib.ptr(px), _lib.ptr(pw), None, _lib.ptr(pg),
+                                                   _lib.ptr(pdx), _lib.ptr(pgw), _lib.ptr(pws), pwsb, _lib.stream_ptr()))
+    del px, ps, pg, pdx
     n_avg = float(np.mean([h.n for h in host]))
     bins = BATCH * TM * 2 * H * W
     bin_bytes = 13.0 * n_avg + 4.0 * bins                 # 13 B/event + 4 B/bin
@@ -391,7 +408,13 @@ def run_ours(args):
             "bin_dat (bounds + tiles on raw 8-byte records)": {
                 "bound": "hbm", "call_ms": t_bin_dat, "achieved": (8.0 * n_avg + 4.0 * bins) / t_bin_dat / 1e6,
                 "peak": peak_gbs, "unit": "GB/s", "frac": (8.0 * n_avg + 4.0 * bins) / t_bin_dat / 1e6 / peak_gbs,
-                "note": "algorithmic bytes = 8 B/record + 4 B/bin"}},
+                "note": "algorithmic bytes = 8 B/record + 4 B/bin"},
+            "plif_fwd_kernel (f32, T=3)": {
+                "bound": "hbm", "call_ms": t_plif_f, "achieved": 8.0 * pT * pN / t_plif_f / 1e6, "peak": peak_gbs,
+                "unit": "GB/s", "frac": 8.0 * pT * pN / t_plif_f / 1e6 / peak_gbs, "note": "8 B per element-step"},
+            "plif_bwd_kernel (f32, T=3, ATan)": {
+                "bound": "hbm", "call_ms": t_plif_b, "achieved": 12.0 * pT * pN / t_plif_b / 1e6, "peak": peak_gbs,
+                "unit": "GB/s", "frac": 12.0 * pT * pN / t_plif_b / 1e6 / peak_gbs, "note": "12 B per element-step"}},
     }
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

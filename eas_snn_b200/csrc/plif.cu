@@ -84,7 +84,7 @@ plif_fwd_kernel(eas_plif_cfg c, const T* __restrict__ x, const float* __restrict
 __device__ __forceinline__ float surrogate_grad(int kind, float alpha, float xx) {
   if (kind == EAS_SG_ATAN) {
     const float z = 1.5707963267948966f * alpha * xx;
-    return alpha * 0.5f / (1.0f + z * z);
+    return __fdividef(alpha * 0.5f, 1.0f + z * z);
   }
   if (kind == EAS_SG_SIGMOID) {
     const float sg = eas_sigmoid(alpha * xx);
@@ -93,12 +93,19 @@ __device__ __forceinline__ float surrogate_grad(int kind, float alpha, float xx)
   return fabsf(xx) < 0.5f / alpha ? alpha : 0.0f;  // Rectangle, yolox/models/activation.py:26-30
 }
 
-template <typename T, int V, int TMAX>
+// FAST = the configuration the reference builds (utils_snn.py:44-53): soft reset, decay_input False,
+// ATan surrogate, reset not detached.  The kernel is instruction bound (~40 instructions per element-step
+// against 12 B), so the run-time switches of the general path are folded at compile time here.
+template <typename T, int V, int TMAX, bool FAST>
 __global__ void __launch_bounds__(256)
 plif_bwd_kernel(eas_plif_cfg c, const T* __restrict__ x, const float* __restrict__ w,
                 const float* __restrict__ v0, const T* __restrict__ g, T* __restrict__ dx,
                 float* __restrict__ partial) {
-  const Dyn d = make_dyn(c, w);
+  Dyn d = make_dyn(c, w);
+  if (FAST) {
+    d.hard = false, d.decay_in = false, d.vr_eff = 0.0f;
+    c.surrogate = EAS_SG_ATAN, c.detach_reset = 0;
+  }
   const int64_t nvec = c.N / V;
   const int Tn = (int)c.T;
   float dsw = 0.0f;
@@ -107,15 +114,27 @@ plif_bwd_kernel(eas_plif_cfg c, const T* __restrict__ x, const float* __restrict
     const int64_t i = iv * V;
     float h[TMAX][V];
     float vinit[V], v[V], xt[V];
+    // short sequences: every load of x and of the incoming gradient is issued before any arithmetic
+    // (2T independent 16 B loads in flight per thread); h is then recomputed from registers
+    constexpr bool kPreload = TMAX <= 4;
+    float xs[kPreload ? TMAX : 1][V], gs[kPreload ? TMAX : 1][V];
+    if (kPreload) {
+#pragma unroll
+      for (int t = 0; t < TMAX; ++t)
+        if (t < Tn) load_vec<T, V>(x + (int64_t)t * c.N + i, xs[t]);
+#pragma unroll
+      for (int t = 0; t < TMAX; ++t)
+        if (t < Tn) load_vec<T, V>(g + (int64_t)t * c.N + i, gs[t]);
+    }
 #pragma unroll
     for (int j = 0; j < V; ++j) vinit[j] = v[j] = v0 ? v0[i + j] : (d.hard ? d.vr : 0.0f);
 #pragma unroll
     for (int t = 0; t < TMAX; ++t) {
       if (t < Tn) {
-        load_vec<T, V>(x + (int64_t)t * c.N + i, xt);
+        if (!kPreload) load_vec<T, V>(x + (int64_t)t * c.N + i, xt);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-          h[t][j] = charge(d, v[j], xt[j]);
+          h[t][j] = charge(d, v[j], kPreload ? xs[t][j] : xt[j]);
           v[j] = reset(d, h[t][j], fire(d, h[t][j]));
         }
       }
@@ -127,8 +146,13 @@ plif_bwd_kernel(eas_plif_cfg c, const T* __restrict__ x, const float* __restrict
     for (int t = TMAX - 1; t >= 0; --t) {
       if (t < Tn) {
         float gt[V], dxt[V];
-        load_vec<T, V>(g + (int64_t)t * c.N + i, gt);
-        if (d.decay_in) load_vec<T, V>(x + (int64_t)t * c.N + i, xt);
+        if (kPreload) {
+#pragma unroll
+          for (int j = 0; j < V; ++j) gt[j] = gs[t][j], xt[j] = xs[t][j];
+        } else {
+          load_vec<T, V>(g + (int64_t)t * c.N + i, gt);
+          if (d.decay_in) load_vec<T, V>(x + (int64_t)t * c.N + i, xt);
+        }
 #pragma unroll
         for (int j = 0; j < V; ++j) {
           const float hh = h[t][j];
@@ -237,9 +261,11 @@ int bwd_launch(const eas_plif_cfg* c, const void* x, const float* w, const float
   const T* xp = (const T*)x;
   const T* gp = (const T*)g;
   T* dp = (T*)dx;
-  if (c->T <= 4) plif_bwd_kernel<T, V, 4><<<grid, 256, 0, st>>>(*c, xp, w, v0, gp, dp, partial);
-  else if (c->T <= 8) plif_bwd_kernel<T, V, 8><<<grid, 256, 0, st>>>(*c, xp, w, v0, gp, dp, partial);
-  else if (c->T <= 16) plif_bwd_kernel<T, V, 16><<<grid, 256, 0, st>>>(*c, xp, w, v0, gp, dp, partial);
+  const bool fast = !c->hard_reset && !c->decay_input && c->surrogate == EAS_SG_ATAN && !c->detach_reset;
+  if (c->T <= 4 && fast) plif_bwd_kernel<T, V, 4, true><<<grid, 256, 0, st>>>(*c, xp, w, v0, gp, dp, partial);
+  else if (c->T <= 4) plif_bwd_kernel<T, V, 4, false><<<grid, 256, 0, st>>>(*c, xp, w, v0, gp, dp, partial);
+  else if (c->T <= 8) plif_bwd_kernel<T, V, 8, false><<<grid, 256, 0, st>>>(*c, xp, w, v0, gp, dp, partial);
+  else if (c->T <= 16) plif_bwd_kernel<T, V, 16, false><<<grid, 256, 0, st>>>(*c, xp, w, v0, gp, dp, partial);
   else return EAS_E_UNSUPPORTED;
   EAS_LAUNCH_CHECK();
   return EAS_OK;
