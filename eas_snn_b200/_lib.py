@@ -70,6 +70,7 @@ SIGNATURES = {
     "eas_plif_bwd": (C.c_int, [C.POINTER(PlifCfg), _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "eas_conv_bn_plif_ws_bytes": (C.c_size_t, [C.POINTER(ConvCfg)]),
     "eas_conv_bn_plif_fwd": (C.c_int, [C.POINTER(ConvCfg), _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "eas_rvt_event_sum": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, _P]),
     "eas_spp_pool_fwd": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }
 

@@ -74,3 +74,19 @@ class HostEventBatch:
 
     def to_device(self, device):
         return tuple(a.to(device, non_blocking=True) for a in (self.x, self.y, self.t, self.p, self.offsets))
+
+
+def rvt_event_sum(repr_u8: torch.Tensor, n_bins: int = 10) -> torch.Tensor:
+    """RVT stacked histograms ``uint8 [n, 2*n_bins, H, W]`` (channel = polarity*n_bins + bin) -> per-polarity
+    counts ``float32 [n, 2, H, W]``: the reference's ``'event_sum'`` reduction
+    (``yolox/data/datasets/rvt_gen4.py:120-122``), on the GPU."""
+    _lib.require_cuda(repr_u8)
+    if repr_u8.dtype != torch.uint8 or repr_u8.dim() != 4 or repr_u8.shape[1] != 2 * n_bins:
+        raise TypeError("expected uint8 [n, 2*n_bins, H, W]")
+    repr_u8 = repr_u8.contiguous()
+    n, _, H, W = repr_u8.shape
+    out = torch.empty((n, 2, H, W), dtype=torch.float32, device=repr_u8.device)
+    with torch.cuda.device(repr_u8.device):
+        rc = _lib.lib().eas_rvt_event_sum(_lib.ptr(repr_u8), n, n_bins, H, W, _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "eas_rvt_event_sum")
+    return out

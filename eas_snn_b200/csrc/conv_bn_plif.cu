@@ -26,7 +26,6 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
-#include <cstdlib>
 #include "lif.cuh"
 
 namespace {
@@ -615,10 +614,6 @@ double pick_reuse_tile(int Ho, int Wo, int* TH, int* TW) {
 
 // K block = one swizzle row of 64 / 32 / 16 channels: least padded K plus a per-block overhead.
 int pick_bk(int Cin) {
-  if (const char* e = getenv("EAS_CONV_BK")) {   // experiment knob
-    const int v = atoi(e);
-    if (v == 64 || v == 32 || v == 16) return v;
-  }
   int best = 64, best_cost = 1 << 30;
   for (int bk : {64, 32, 16}) {
     const int nb = (Cin + bk - 1) / bk;
@@ -654,7 +649,7 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
   // 3x3 stride-1 layers on spike inputs: load every haloed input tile once and realise the nine taps as
   // descriptor shifts (9x less activation traffic from L2), when the padded tiles waste < 30 % of the MMA rows
   bool reuse = false;
-  if (c->ksize == 3 && c->stride == 1 && c->n_xsplit == 1 && c->Cin >= 32 && !getenv("EAS_CONV_NO_REUSE")) {
+  if (c->ksize == 3 && c->stride == 1 && c->n_xsplit == 1 && c->Cin >= 32) {
     int th = 0, tw = 0;
     if (pick_reuse_tile(Ho, Wo, &th, &tw) >= 0.70) reuse = true, a.NB = 1, a.TH = th, a.TW = tw, a.TWp = tw + 2;
   }

@@ -1,0 +1,62 @@
+// (f-4) RVT-preprocessed stacked histograms -> per-polarity event counts.  Replaces the 'event_sum' branch of
+// RVTGEN4Dataset.generate_slices (yolox/data/datasets/rvt_gen4.py:120-122):
+//   ev_repr.reshape(n, 2, -1, H, W).sum(axis=2)      uint8 [n][2*nb][H][W] -> [n][2][H][W]
+// HBM bound: 2*nb bytes read and 8 bytes (two fp32 counts, exact) written per pixel; 16 pixels per thread
+// with 16 B loads.
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+rvt_event_sum_kernel(const uint8_t* __restrict__ repr, float* __restrict__ out, int64_t n2, int nb, int64_t HW) {
+  // one (frame, polarity) plane group per blockIdx.y; 16 pixels per thread
+  const int64_t np16 = (HW + 15) / 16;
+  for (int64_t g = blockIdx.y; g < n2; g += gridDim.y) {
+    const uint8_t* src = repr + g * nb * HW;
+    float* dst = out + g * HW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np16; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t p0 = i * 16;
+      uint32_t acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 0;
+      if (p0 + 16 <= HW && (HW & 15) == 0) {
+        for (int b = 0; b < nb; ++b) {
+          const uint4 v = ld_stream_u4(reinterpret_cast<const uint4*>(src + b * HW + p0));
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[q * 4 + j] += (w[q] >> (8 * j)) & 0xffu;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          st_stream_f4(reinterpret_cast<float4*>(dst + p0 + 4 * q),
+                       make_float4((float)acc[4 * q], (float)acc[4 * q + 1], (float)acc[4 * q + 2], (float)acc[4 * q + 3]));
+      } else {
+        for (int j = 0; j < 16 && p0 + j < HW; ++j) {
+          uint32_t a = 0;
+          for (int b = 0; b < nb; ++b) a += src[b * HW + p0 + j];
+          dst[p0 + j] = (float)a;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int eas_rvt_event_sum(const uint8_t* repr, int64_t n, int nb, int H, int W, float* out, void* stream) {
+  EAS_REQUIRE(n >= 0 && nb >= 1 && nb <= 255 && H > 0 && W > 0, EAS_E_SHAPE);
+  if (n == 0) return EAS_OK;
+  EAS_REQUIRE(repr && out, EAS_E_NULL);
+  EAS_REQUIRE((uintptr_t)repr % 16 == 0 && (uintptr_t)out % 16 == 0, EAS_E_ALIGN);
+  const int64_t HW = (int64_t)H * W;
+  const int64_t np16 = (HW + 15) / 16;
+  int64_t gx = (np16 + 255) / 256;
+  if (gx > 4 * EAS_NUM_SMS) gx = 4 * EAS_NUM_SMS;
+  int64_t gy = 2 * n;
+  if (gy > 65535) gy = 65535;
+  rvt_event_sum_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(repr, out, 2 * n, nb, HW);
+  EAS_LAUNCH_CHECK();
+  return EAS_OK;
+}

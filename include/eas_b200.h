@@ -218,6 +218,12 @@ int eas_conv_bn_plif_fwd(const eas_conv_cfg* cfg, const void* x, const void* w_p
                          const float* bias, const float* plif_w, void* out, void* ws,
                          size_t ws_bytes, void* stream);
 
+/* (f-4) RVT-preprocessed stacked histograms -> per-polarity counts: the 'event_sum' branch of
+ * RVTGEN4Dataset.generate_slices, yolox/data/datasets/rvt_gen4.py:120-122
+ * (ev_repr.reshape(n, 2, -1, H, W).sum(axis=2)).  repr: uint8 [n][2*nb][H][W] (channel = polarity*nb + bin),
+ * out: f32 [n][2][H][W] (exact integer counts, <= 255*nb). */
+int eas_rvt_event_sum(const uint8_t* repr, int64_t n, int nb, int H, int W, float* out, void* stream);
+
 /* SPP max-pools of the backbone (SPPBottleneck.m, yolox/models/network_blocks.py:128-147; stride 1,
  * padding k/2).  cat: fp16 channels-last [n_images][H][W][ld] whose channels [0, C) hold x; channels
  * [C, 2C), [2C, 3C), [3C, 4C) receive maxpool_k1 / k2 / k3 of x (the torch.cat of :146).  In place. */

@@ -191,3 +191,35 @@ def test_auto_falls_back_beyond_fp16_range(cuda):
         else:   # in range: auto is the tensor-core kernel (fp32-equivalent, not bit-identical)
             ok, frac, msg = _compare(outs["auto"], outs["fp32"].cpu(), budget=2e-3)
             assert ok, msg
+
+
+def test_1mpx_rvt_layout_event_sum_and_sampler(cuda):
+    """BASELINE config 3: RVT-preprocessed uint8 [n, 20, 360, 640] -> 'event_sum' counts (rvt_gen4.py:120-122,
+    bit-exact vs numpy) -> Tm consecutive slices as the sampler's steps at 360x640 (6 strips of the
+    tensor-core kernel) vs the oracle."""
+    g = np.random.default_rng(3)
+    Tm = 4
+    rep = (g.random((Tm, 20, 360, 640)) < 0.04).astype(np.uint8) * g.integers(1, 9, (Tm, 20, 360, 640), dtype=np.uint8)
+    rep[1, 3, 100, 200] = 255
+    want_sum = rep.reshape(Tm, 2, -1, 360, 640).sum(axis=2)              # the reference's two lines
+    got_sum = eas.rvt_event_sum(torch.from_numpy(rep).to(cuda), 10)
+    assert np.array_equal(got_sum.cpu().numpy(), want_sum.astype(np.float32))
+    odd = eas.rvt_event_sum(torch.from_numpy(rep[:, :, :37, :53].copy()).to(cuda), 10)    # ragged plane size
+    assert np.array_equal(odd.cpu().numpy(), rep[:, :, :37, :53].reshape(Tm, 2, -1, 37, 53).sum(axis=2).astype(np.float32))
+    torch.manual_seed(80)
+    kw = dict(kernel_size=5, in_channel=2, out_channel=2, readout="sum", split=False, write_zero=True, abs=False,
+              depth=2, nb_steps=Tm, vreset=0, thresh=1, embedding="arsnn", Ts=1, spike_attach=True)
+    ref = osamp.OracleSampler(**kw)
+    x = got_sum.unsqueeze(0)                                              # [B=1, Tm, 2, 360, 640]
+    with torch.no_grad():
+        want = ref(x.cpu())
+    m = eas.AdaptiveRSNNEmbedding(**kw).to(cuda)
+    m.load_state_dict(ref.state_dict())
+    for algo in ALGOS:
+        m.algo = algo
+        with torch.no_grad():
+            out = m(x)
+        ok, frac, msg = _compare(out, want, budget=1e-4)
+        print(algo, msg)
+        assert ok, algo + ": " + msg
+    assert (want != 0).float().mean().item() > 0.01
