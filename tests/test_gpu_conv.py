@@ -91,13 +91,14 @@ def test_real_valued_input_split(cuda):
     assert ok, msg
 
 
-@pytest.mark.parametrize("cfg", [(64, 64, 1, 1, 3), (32, 64, 3, 2, 3), (96, 48, 3, 1, 3), (64, 64, 1, 1, 1)])
+@pytest.mark.parametrize("cfg", [(64, 64, 1, 1, 3), (32, 64, 3, 2, 3), (96, 48, 3, 1, 3), (64, 64, 1, 1, 1),
+                                 (64, 96, 3, 1, 5), (48, 40, 1, 1, 8), (96, 96, 3, 1, 4)])
 def test_layer_vs_oracle_conv_bn_plif(cuda, cfg):
     """Teacher-forced single layer: identical spike input, conv -> BN(eval) -> PLIF oracle vs the fused kernel."""
     Cin, Cout, k, stride, T = cfg
     torch.manual_seed(Cin + Cout + k)
     ref = ob.SpikingBaseConv(Cin, Cout, k, stride, op.ATan(2.0))
-    x = (torch.rand(3, 2, Cin, 24, 32) < 0.2).float()
+    x = (torch.rand(T, 2, Cin, 24, 32) < 0.2).float()
     x = x + (torch.rand_like(x) < 0.05).float()                       # a few 2s (SEW sums)
     ob.calibrate_bn(ref, x)
     ref.act.w.data.fill_(0.3)
@@ -109,7 +110,7 @@ def test_layer_vs_oracle_conv_bn_plif(cuda, cfg):
     m.load_state_dict(ref.state_dict())
     m.eval()
     with torch.no_grad():
-        got_cl = m.run(x.to(cuda).permute(0, 1, 3, 4, 2).contiguous().half(), 3)
+        got_cl = m.run(x.to(cuda).permute(0, 1, 3, 4, 2).contiguous().half(), T)
         got = got_cl.permute(0, 1, 4, 2, 3).float().cpu()
         got_mod = m(x.to(cuda))                                        # drop-in [T,B,C,H,W] fp32 path
     mism = (got != want).float().mean().item()
