@@ -34,7 +34,7 @@ constexpr int BLOCK_M = 128;
 constexpr int MAX_WSPLIT = 2;
 constexpr int N_ISSUERS = 3;        // MMA issuing warps (time steps t = w, w + 3, ...)
 constexpr int NUM_THREADS = (1 + N_ISSUERS + 8) * 32;   // TMA producer, MMA issuers, 2 x 4 epilogue warps
-constexpr uint32_t SPIN_LIMIT = 1u << 23;  // watchdog (~1 s): trap instead of hanging the GPU
+constexpr uint32_t SPIN_LIMIT = 1u << 26;  // watchdog (a few seconds): trap instead of hanging the GPU
 
 struct ConvArgs {
   int T, Tx, B, Ho, Wo, Cin, Cout, ksize, stride, pad;

@@ -65,7 +65,7 @@ constexpr int SMEM_BYTES = OFF_MISC + 128 + 1024;          // + slack for the 10
 // warps 0-3 epilogue 1, 4-7 / 8-11 epilogue 2 (even / odd tiles), 12-14 MMA issuers, 15-18 producers
 constexpr int W_E2 = 4, W_MMA = 12, W_PROD = 15;
 constexpr int NUM_THREADS = 19 * 32;
-constexpr uint32_t SPIN_LIMIT = 1u << 23;  // ~1 s
+constexpr uint32_t SPIN_LIMIT = 1u << 26;  // a few seconds
 
 // TMEM columns: D1 = [in: x*w_hi (16) | x_hi*w_lo (16)][gate: same] x 2 buffers (64 apart);
 // D2 = [x_hi*w_hi (16) | x_hi*w_lo (16) | x_lo*w_hi (16)] x 2 buffers (64 apart).  The partial sums

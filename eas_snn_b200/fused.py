@@ -386,6 +386,35 @@ class SpikingCSPDarknet(nn.Module):
         return {k: outs[k].permute(0, 1, 4, 2, 3) for k in keys}
 
 
+class GraphedForward:
+    """CUDA-graph replay of a fused inference forward (``SpikingCSPDarknet`` or any module of fused layers).
+
+    The ~60 launches of a SYOLOX backbone forward (51 conv+BN+PLIF kernels + glue) are launch bound for small
+    batches; captured once into a ``torch.cuda.CUDAGraph`` they replay with one host call.  Input and outputs
+    live in static buffers: ``__call__`` copies the new frames in and returns the (reused) output tensors."""
+
+    def __init__(self, module: nn.Module, example: torch.Tensor, warmup: int = 2):
+        _lib.require_cuda(example)
+        self.module = module
+        self.static_in = example.clone()
+        side = torch.cuda.Stream(example.device)
+        side.wait_stream(torch.cuda.current_stream(example.device))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):                      # packs weights, sizes the allocator pools
+                module(self.static_in)
+        torch.cuda.current_stream(example.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.static_out = module(self.static_in)
+
+    def __call__(self, frames: torch.Tensor):
+        if frames.shape != self.static_in.shape or frames.dtype != self.static_in.dtype:
+            raise ValueError("GraphedForward was captured for %s %s" % (tuple(self.static_in.shape), self.static_in.dtype))
+        self.static_in.copy_(frames)
+        self.graph.replay()
+        return self.static_out
+
+
 def convert_to_spiking(model: nn.Module, spike_fn, fuse: bool = True, n_wsplit: int = 2) -> nn.Module:
     """``yolox/utils/utils_snn.py:16-58`` with the fused layer: every child that looks like the
     reference's ``BaseConv`` (``.conv`` Conv2d, ``.bn`` BatchNorm2d, ``.act``) becomes a

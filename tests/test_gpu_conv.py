@@ -196,3 +196,21 @@ def test_spp_pools_match_torch(cuda, shape):
         want = F.max_pool2d(x4, k, 1, k // 2).permute(0, 2, 3, 1)
         assert torch.equal(cat[..., (i + 1) * C:(i + 2) * C].float().cpu(), want), k
     assert torch.equal(cat[..., :C].cpu(), x) and bool((cat[..., 4 * C:] == 7).all())
+
+
+def test_graphed_backbone_replays_the_eager_forward(cuda):
+    """CUDA-graph capture of the fused spiking CSPDarknet: replay on new frames equals the eager forward."""
+    torch.manual_seed(5)
+    net = fused.SpikingCSPDarknet(0.33, 0.25, in_dim=2, T=3).to(cuda).eval()
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.bias.data.fill_(0.6)
+    x0 = torch.rand(1, 2, 2, 64, 96, device=cuda) * 2
+    g = fused.GraphedForward(net, x0)
+    for seed in (1, 2):
+        x = torch.rand(1, 2, 2, 64, 96, device=cuda, generator=torch.Generator(cuda).manual_seed(seed)) * 2
+        want = {k: v.clone() for k, v in net(x).items()}
+        got = g(x)
+        for k in want:
+            assert torch.equal(got[k], want[k]), k
+        assert 0.01 < float(want["dark5"].float().mean()) < 0.9
