@@ -292,42 +292,49 @@ def run_ours(args):
     checksum = float(slots[(args.steps - 1) % 2]["host_out"].abs().sum())
     clk = clocks.stop()
 
-    # ---- secondary metric: frames/s through sampler + SYOLOX-M spiking CSPDarknet (T=3, 256x320) ----
+    # ---- secondary metric: SYOLOX-M frames/s forward (T=3, 256x320): events -> detections ----
     frames = None
     if not args.no_backbone:
-        from eas_snn_b200 import fused
+        from eas_snn_b200 import detector, fused
         torch.manual_seed(81)
-        bb = fused.SpikingCSPDarknet(0.67, 0.75, in_dim=2, T=3).to(dev).eval()   # e_yolox_m.py:13-14
-        for mod in bb.modules():                   # random init is dead: shift BN so layers fire
+        det = detector.build_syolox(0.67, 0.75, num_classes=2, T=3, embedding=model).to(dev).eval()  # e_yolox_m.py:13-14
+        bb = det.backbone.backbone
+        for mod in det.modules():                  # random init is dead: shift BN so layers fire
             if isinstance(mod, torch.nn.BatchNorm2d):
                 mod.bias.data.fill_(0.6)
 
-        def frame_step(db):
-            fr = step(db)                                                     # [1, B, 2, 240, 304]
-            fr = torch.nn.functional.pad(fr, (0, 320 - W, 0, 256 - H))        # multiples of 32 (event_yolox_base.py:556-559)
-            return bb(fr)
+        def pad(fr):                               # multiples of 32 (event_yolox_base.py:556-559)
+            return torch.nn.functional.pad(fr, (0, 320 - W, 0, 256 - H))
+
+        def time_frames(fn, fsteps):
+            for w in range(3):
+                out = fn(devb[w % NSETS])
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for k in range(fsteps):
+                out = fn(devb[k % NSETS])
+            f1.record()
+            barrier()
+            return parallel.max_over_ranks(f0.elapsed_time(f1), dev) / fsteps, out
 
         fsteps = max(5, args.steps // 10)
-        for w in range(3):
-            outs = frame_step(devb[w % NSETS])
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for k in range(fsteps):
-            outs = frame_step(devb[k % NSETS])
-        f1.record()
-        barrier()
-        fms = parallel.max_over_ranks(f0.elapsed_time(f1), dev)
-        n_conv = sum(1 for mod in bb.modules() if isinstance(mod, fused.FusedConvBNPLIF)) + 1
-        gflop = 6.61 * 3 * BATCH                                             # M@256x320, per sample-step
-        frames = {"value": world * BATCH * fsteps / fms * 1e3, "unit": "frames/s", "ms_per_batch": fms / fsteps,
-                  "what": "events -> bin -> sampler -> SYOLOX-M spiking CSPDarknet fwd (T=3, 256x320, %d tcgen05 "
-                          "conv+BN+PLIF launches), %d windows per GPU; FPN/head not included (out of scope)"
-                          % (n_conv, BATCH),
-                  "tensor": {"achieved": gflop / (fms / fsteps), "unit": "TFLOP/s (1x conv FLOPs; the kernel "
-                             "runs 2 fp16 passes for fp32-equivalent weights)", "peak": 1394.4,
-                             "frac": gflop / (fms / fsteps) / 1394.4},
-                  "spike_rate": {k: round(float(v.float().mean()), 4) for k, v in outs.items()}}
+        bb_ms, outs = time_frames(lambda db: bb(pad(step(db))), fsteps)          # spiking CSPDarknet only
+        det_ms, pred = time_frames(lambda db: det.detect_frames(pad(step(db))), fsteps)   # + PAFPN + head + decode
+        n_spk = sum(1 for mod in bb.modules() if isinstance(mod, fused.FusedConvBNPLIF)) + 1
+        n_ann = sum(1 for mod in det.modules() if isinstance(mod, detector.AnnBaseConv)) + 6
+        gflop_bb = 6.61 * 3 * BATCH                                          # M@256x320, per sample-step
+        frames = {"value": world * BATCH / det_ms * 1e3, "unit": "frames/s", "ms_per_batch": det_ms,
+                  "what": "events -> bin -> sampler -> SYOLOX-M forward (T=3, 256x320): spiking CSPDarknet (%d tcgen05 "
+                          "conv+BN+PLIF launches) -> time mean -> ANN PAFPN + YOLOX head (%d tcgen05 conv launches, "
+                          "fp16 hi/lo split = fp32-equivalent) -> decoded predictions [B, 1680, 7]; %d windows per GPU"
+                          % (n_spk, n_ann, BATCH),
+                  "backbone_only": {"value": world * BATCH / bb_ms * 1e3, "ms_per_batch": bb_ms,
+                                    "tensor": {"achieved": gflop_bb / bb_ms, "unit": "TFLOP/s (1x conv FLOPs; the "
+                                               "kernel runs 2 fp16 passes for fp32-equivalent weights)",
+                                               "peak": 1394.4, "frac": gflop_bb / bb_ms / 1394.4}},
+                  "spike_rate": {k: round(float(v.float().mean()), 4) for k, v in outs.items()},
+                  "pred_checksum": float(pred.float().abs().mean())}
 
     # ---- per-kernel durations (CUDA events on the launching stream) for the roofline -----------
     def time_call(fn, reps=10, warm=3):

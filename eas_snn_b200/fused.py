@@ -62,6 +62,17 @@ def pack_weight(w_folded: torch.Tensor, n_wsplit: int = 2):
     return planes, torch.exp2(-e).contiguous()
 
 
+def _pixel_ld(t: torch.Tensor, C: int) -> int:
+    """Pixel stride (elements) of a channels-last ``[..., B, H, W, C]`` tensor that may be a channel slice of a
+    wider buffer: read off the innermost dimension that has more than one entry."""
+    n = 1
+    for d in range(t.dim() - 2, -1, -1):
+        if t.shape[d] > 1:
+            return t.stride(d) // n
+        n *= t.shape[d]
+    return C
+
+
 def conv_bn_plif(x: torch.Tensor, w_planes: torch.Tensor, bias: torch.Tensor, plif_w: torch.Tensor | None,
                  T: int, ksize: int, stride: int, n_xsplit: int = 1, out: torch.Tensor | None = None,
                  out_mode: int = OUT_SPIKES, v_threshold: float = 1.0, v_reset: float | None = None,
@@ -86,9 +97,7 @@ def conv_bn_plif(x: torch.Tensor, w_planes: torch.Tensor, bias: torch.Tensor, pl
     if xs.dim() != 6 or xs.shape[0] != n_xsplit:
         raise ValueError("x must be [Tx,B,H,W,C] or [n_xsplit,Tx,B,H,W,C]")
     _, Tx, B, H, W, Cin = xs.shape
-    x_ld = xs.stride(-2) if W > 1 else Cin
-    if W == 1 and H > 1:
-        x_ld = xs.stride(-3)
+    x_ld = _pixel_ld(xs, Cin)
     want = (Tx * B * H * W * x_ld, B * H * W * x_ld, H * W * x_ld, W * x_ld, x_ld, 1)
     if x_ld < Cin or any(d > 1 and s_ != w_ for s_, w_, d in zip(xs.stride(), want, xs.shape)):
         raise ValueError("x must be a dense channels-last tensor or a channel slice of one "
@@ -108,18 +117,22 @@ def conv_bn_plif(x: torch.Tensor, w_planes: torch.Tensor, bias: torch.Tensor, pl
             out = torch.empty((To, B, Ho, Wo, Cout), dtype=torch.float32, device=dev)
         else:
             out = torch.empty((2, To, B, Ho, Wo, Cout), dtype=ACT_DTYPE, device=dev)
+    if out_mode == OUT_SILU2 and (out.dim() != 6 or out.shape[0] != 2):
+        raise ValueError("OUT_SILU2 writes two planes: out must be [2, Tx, B, Ho, Wo, Cout]")
     oshape = tuple(out.shape[-5:])
     if oshape != (To, B, Ho, Wo, Cout) or (Cout > 1 and out.stride(-1) != 1):
         raise ValueError("out has the wrong shape %s, expected %s" % (oshape, (To, B, Ho, Wo, Cout)))
-    out_ld = out.stride(-2) if Wo > 1 else (out.stride(-3) if Ho > 1 else max(Cout, out.stride(-4) // max(1, Ho * Wo)))
+    out_ld = _pixel_ld(out, Cout)
     owant = (B * Ho * Wo * out_ld, Ho * Wo * out_ld, Wo * out_ld, out_ld, 1)
     if out_ld < Cout or any(d > 1 and s_ != w_ for s_, w_, d in zip(out.stride()[-5:], owant, oshape)):
         raise ValueError("out must be a dense channels-last tensor or a channel slice of one")
+    if out_mode == OUT_SILU2 and out.stride(0) != To * B * Ho * Wo * out_ld:
+        raise ValueError("the two output planes must be one whole buffer apart")
     res_ld = 0
     if residual is not None:
         if residual.dtype != ACT_DTYPE or tuple(residual.shape) != (T, B, Ho, Wo, Cout):
             raise ValueError("residual must be fp16 [T, B, Ho, Wo, Cout]")
-        res_ld = residual.stride(-2) if Wo > 1 else (residual.stride(-3) if Ho > 1 else Cout)
+        res_ld = _pixel_ld(residual, Cout)
         rwant = (B * Ho * Wo * res_ld, Ho * Wo * res_ld, Wo * res_ld, res_ld, 1)
         if any(d > 1 and s_ != w_ for s_, w_, d in zip(residual.stride(), rwant, residual.shape)):
             raise ValueError("residual must be channels-last (or a channel slice)")
@@ -364,7 +377,8 @@ class SpikingCSPDarknet(nn.Module):
                                    _CSPLayer(c * 16, c * 16, d, False, spike_fn))
 
     @torch.no_grad()
-    def forward(self, frames: torch.Tensor, return_all: bool = False):
+    def run_cl(self, frames: torch.Tensor) -> dict:
+        """All stage outputs as channels-last fp16 spike tensors ``[T, B, H, W, C]`` (what the fused FPN reads)."""
         if self.training:
             raise RuntimeError("SpikingCSPDarknet (fused) is the inference path; call .eval()")
         _lib.require_cuda(frames)
@@ -382,6 +396,11 @@ class SpikingCSPDarknet(nn.Module):
             for blk in list(seq)[1:]:
                 x = blk.run(x, T)
             outs[name] = x
+        return outs
+
+    @torch.no_grad()
+    def forward(self, frames: torch.Tensor, return_all: bool = False):
+        outs = self.run_cl(frames)
         keys = outs.keys() if return_all else self.out_features
         return {k: outs[k].permute(0, 1, 4, 2, 3) for k in keys}
 

@@ -230,6 +230,25 @@ int eas_rvt_event_sum(const uint8_t* repr, int64_t n, int nb, int H, int W, floa
 int eas_spp_pool_fwd(void* cat, int64_t n_images, int H, int W, int C, int ld, int k1, int k2, int k3,
                      void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (f-2) Glue between the spiking backbone, the ANN PAFPN / head and the detections.
+ * Activations: channels-last fp16, real values as two planes hi + lo (plane stride in elements).
+ * ---------------------------------------------------------------------------------------- */
+/* `out_features[f].mean(axis=0)`, yolox/models/spiking_yolo_pafpn.py:98.  spikes: fp16 [T][n_pix][x_ld]
+ * (channels [0,C) used), out: planes hi/lo [n_pix][out_ld] = sum_t / T (a channel slice of a concat buffer). */
+int eas_time_mean_planes(const void* spikes, int T, int64_t n_pix, int C, int x_ld, void* out, int out_ld,
+                         int64_t out_plane_stride, void* stream);
+/* nn.Upsample(scale_factor=2, mode="nearest"), spiking_yolo_pafpn.py:36,102,107 (yolo_pafpn.py same lines).
+ * in: [n_planes][n_images][H][W][in_ld] -> out: [n_planes][n_images][2H][2W][out_ld], channels [0,C). */
+int eas_upsample2x_planes(const void* in, int n_planes, int64_t in_plane_stride, int64_t n_images, int H, int W,
+                          int C, int in_ld, void* out, int out_ld, int64_t out_plane_stride, void* stream);
+/* YOLOXHead inference tail, yolox/models/yolo_head.py:187-199 (sigmoid, flatten, concat over levels) and
+ * :232-250 (decode_outputs).  preds: f32 [n_images][H][W][ld], channels = (x, y, w, h, obj, cls...) raw conv
+ * outputs of one level; out: f32 [n_images][n_anchors_total][n_ch], this level's anchors start at
+ * anchor_offset.  decode = 0 keeps (x, y, w, h) raw (decode_in_inference = False). */
+int eas_yolox_decode(const float* preds, int64_t n_images, int H, int W, int n_ch, int ld, float stride,
+                     int decode, float* out, int64_t anchor_offset, int64_t n_anchors_total, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

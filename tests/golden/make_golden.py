@@ -2,7 +2,7 @@
 
     python tests/golden/make_golden.py          # needs /root/reference (read-only)
 
-Outputs (small, committed): tests/golden/binning.npz, sampler.npz, backbone.npz, psee.npz.
+Outputs (small, committed): tests/golden/binning.npz, sampler.npz, backbone.npz, psee.npz, detector.npz.
 The reference is imported in place through ``oracle/ref_loader.py``; nothing is copied from it.
 ``/root/reference`` does not exist on the GPU box, so tests only ever read the .npz files.
 """
@@ -165,6 +165,84 @@ def make_backbone():
     print("backbone.npz written, params:", sum(p.numel() for p in bb.parameters()))
 
 
+def make_detector():
+    """(f-2) The reference's whole model for ``use_spike True`` -- ``EventExp.get_model()`` = SpikingYOLOX(
+    SpikingYOLOPAFPN, YOLOXHead, AdaptiveRSNNEmbedding) -- at a tiny width, run unmodified through the
+    spikingjelly shim: micro-bin histograms in, decoded predictions out, plus the pyramid features, the sampler
+    frames and the reference's own ``postprocess`` (boxes.py:33-77) on those predictions."""
+    exp, model = ref_loader.load_full_model("e-yolox-s", ["T", 3, "embedding", "arsnn", "embedding_depth", 2,
+                                                          "embedding_ksize", 5, "spike_attach", True,
+                                                          "write_zero", True, "spike_fn", "atan",
+                                                          "use_spike", True, "num_classes", 2,
+                                                          "width", 0.125, "depth", 0.33])
+    from spikingjelly.activation_based import functional
+    from oracle.backbone import calibrate_bn
+    from yolox.utils.boxes import postprocess
+    torch.manual_seed(80)
+    for part in (model.backbone, model.head):   # deterministic weights (get_model consumed an unknown amount of RNG)
+        for m in part.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_uniform_(m.weight, a=5 ** 0.5)
+    model.embedding._init_weight()
+    for m in model.embedding.modules():          # _init_weight leaves the biases alone
+        if isinstance(m, nn.Conv2d):
+            bound = 1.0 / (m.weight[0].numel() ** 0.5)
+            nn.init.uniform_(m.bias, -bound, bound)
+    B, Tm, H, W = 2, exp.Tm, 64, 96
+    g = torch.Generator().manual_seed(11)
+    hist = torch.poisson(torch.full((B, Tm, 2, H, W), 0.6), generator=g)
+    with torch.no_grad():
+        frames = model.embedding(hist)                                   # [Ts=1, B, 2, H, W]
+    nz = float((frames != 0).float().mean())
+    print(" detector sampler frames", tuple(frames.shape), "non-zero %.3f" % nz)
+    assert frames.shape == (1, B, 2, H, W) and 0.01 < nz < 0.9
+    x = frames.expand(3, -1, -1, -1, -1).contiguous()
+    calibrate_bn(model.backbone, x, seed=3)                              # spiking backbone + ANN pyramid BNs
+    gg = torch.Generator().manual_seed(4)
+    for m in model.head.modules():                                       # head BNs: non-trivial running stats
+        if isinstance(m, nn.BatchNorm2d):
+            m.weight.data = torch.empty_like(m.weight).uniform_(0.8, 1.2, generator=gg)
+            m.bias.data = torch.empty_like(m.bias).normal_(0.0, 0.1, generator=gg)
+            m.running_mean.data = torch.empty_like(m.running_mean).normal_(0.0, 0.2, generator=gg)
+            m.running_var.data = torch.empty_like(m.running_var).uniform_(0.5, 1.5, generator=gg)
+    for conv in list(model.head.cls_preds) + list(model.head.reg_preds) + list(model.head.obj_preds):
+        # (the 1e-2 prior of initialize_biases would put every score below any useful threshold)
+        conv.bias.data = torch.empty_like(conv.bias).normal_(0.0, 0.7, generator=gg)
+        conv.weight.data *= 0.3
+    for i, m in enumerate(mm for mm in model.modules() if hasattr(mm, "w") and isinstance(mm.w, nn.Parameter)):
+        m.w.data.fill_(0.3 * ((i % 5) - 2))
+    model.eval()
+    with torch.no_grad():
+        pyramid = model.backbone(x)
+        functional.reset_net(model)
+        pred = model(hist)                                               # [B, A, 7] decoded
+        functional.reset_net(model)
+        model.head.decode_in_inference = False
+        raw = model(hist)
+        functional.reset_net(model)
+        dets = postprocess(pred.clone(), 2, conf_thre=0.3, nms_thre=0.45)
+    A = sum((H // s) * (W // s) for s in (8, 16, 32))
+    assert pred.shape == (B, A, 7), pred.shape
+    out = {"hist": hist.numpy().astype(np.uint8), "frames": frames.numpy(), "pred": pred.numpy(), "raw": raw.numpy()}
+    for k, v in model.state_dict().items():
+        out["sd/" + k] = v.numpy()
+    for i, f in enumerate(pyramid):
+        out["pyramid/%d" % i] = f.numpy()
+        print(" detector pyramid", i, tuple(f.shape), "mean |x| %.3f" % float(f.abs().mean()))
+    n_det = 0
+    for i, d in enumerate(dets):
+        out["dets/%d" % i] = np.zeros((0, 7), np.float32) if d is None else d.numpy()
+        n_det += 0 if d is None else len(d)
+    assert n_det >= 4, "the fixture should produce a few detections (got %d)" % n_det
+    out["meta"] = np.array([repr(dict(depth=0.33, width=0.125, num_classes=2, T=3, Tm=Tm, Ts=1, ksize=5,
+                                      emb_depth=2, readout=exp.readout, vreset=exp.reset, thresh=exp.thresh,
+                                      spike_attach=True, write_zero=True, abs=bool(exp.abs), alpha=float(exp.alpha),
+                                      conf_thre=0.3, nms_thre=0.45))])
+    np.savez_compressed(os.path.join(HERE, "detector.npz"), **out)
+    print("detector.npz written: pred", tuple(pred.shape), "detections", n_det,
+          "obj range %.3f..%.3f" % (float(pred[..., 4].min()), float(pred[..., 4].max())))
+
+
 def make_psee(gen1):
     """PSEE .dat path: synthetic recordings written in the reference's format (records by its own
     ``write_event_buffer``; the header by hand because the reference's ``write_header`` references an
@@ -230,9 +308,14 @@ if __name__ == "__main__":
         make_psee(gen1)
         print("psee.npz", os.path.getsize(os.path.join(HERE, "psee.npz")) // 1024, "KiB")
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "detector":
+        make_detector()
+        print("detector.npz", os.path.getsize(os.path.join(HERE, "detector.npz")) // 1024, "KiB")
+        sys.exit(0)
     make_binning(gen1)
     make_sampler(emb, act)
     make_backbone()
     make_psee(gen1)
-    for f in ("binning.npz", "sampler.npz", "backbone.npz", "psee.npz"):
+    make_detector()
+    for f in ("binning.npz", "sampler.npz", "backbone.npz", "psee.npz", "detector.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

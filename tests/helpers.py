@@ -45,3 +45,18 @@ def close_report(a: torch.Tensor, b: torch.Tensor, rtol=1e-5, atol=1e-5):
         msg += "  first bad idx %s  got %s  want %s" % (idx, [float(a[tuple(i)]) for i in idx],
                                                         [float(b[tuple(i)]) for i in idx])
     return nb == 0, msg
+
+
+def detector_case(z):
+    """(meta, state_dict, hist) of tests/golden/detector.npz."""
+    meta = ast.literal_eval(str(z["meta"][0]))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    hist = torch.from_numpy(z["hist"].astype(np.float32))
+    return meta, sd, hist
+
+
+def detector_sampler_kwargs(meta):
+    return dict(kernel_size=meta["ksize"], in_channel=2, out_channel=2, readout=meta["readout"], split=False,
+                write_zero=meta["write_zero"], abs=meta["abs"], depth=meta["emb_depth"], nb_steps=meta["Tm"],
+                vreset=meta["vreset"], thresh=meta["thresh"], embedding="arsnn", Ts=meta["Ts"],
+                spike_attach=meta["spike_attach"])

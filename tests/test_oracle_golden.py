@@ -89,3 +89,28 @@ def test_psee_oracle_matches_reference_loader(name):
     hist = psee.micro_sum_windows(rec, ranges, kw["H"], kw["W"], Tm)
     assert np.array_equal(hist.astype(np.int32), z[f"{name}/hist"])
     assert (count == 0).any() and hist.sum() > 0
+
+
+def test_detector_golden():
+    """(f-2) oracle.detector (sampler -> spiking CSPDarknet -> ANN PAFPN -> YOLOX head -> decode) loads the
+    reference model's state_dict key for key and reproduces its frames, pyramid and predictions."""
+    from oracle import detector
+    from helpers import detector_case, detector_sampler_kwargs
+    z = load_golden("detector")
+    meta, sd, hist = detector_case(z)
+    emb = sampler.OracleSampler(**detector_sampler_kwargs(meta))
+    net = detector.OracleSpikingYOLOX(meta["depth"], meta["width"], meta["num_classes"], meta["T"], embedding=emb,
+                                      spike_fn=ATan(meta["alpha"]))
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    with torch.no_grad():
+        frames = net.embedding(hist)
+        assert torch.equal(frames, torch.from_numpy(z["frames"]))
+        pyr = net.backbone(frames.expand(meta["T"], -1, -1, -1, -1).contiguous())
+        backbone.reset_net(net)
+        for i, f in enumerate(pyr):
+            assert torch.allclose(f, torch.from_numpy(z["pyramid/%d" % i]), rtol=1e-5, atol=1e-5), i
+        pred = net(hist)
+        raw = net.head(pyr, decode=False)
+    assert torch.allclose(pred, torch.from_numpy(z["pred"]), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(raw, torch.from_numpy(z["raw"]), rtol=1e-5, atol=1e-5)
