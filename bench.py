@@ -336,6 +336,60 @@ def run_ours(args):
                   "spike_rate": {k: round(float(v.float().mean()), 4) for k, v in outs.items()},
                   "pred_checksum": float(pred.float().abs().mean())}
 
+    # ---- secondary metric: SYOLOX-S training step (BASELINE config 4), 8 windows per GPU --------------------
+    train = None
+    if not args.no_train:
+        from eas_snn_b200 import fused
+        TB = 8
+        torch.manual_seed(82)
+        t_emb = eas.AdaptiveRSNNEmbedding(**SAMPLER_KW).to(dev).train()
+        t_bb = fused.SpikingCSPDarknet(0.33, 0.50, in_dim=2, T=3).to(dev).train()       # e_yolox_s.py:13-14
+        for mod in t_bb.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.bias.data.fill_(0.6)
+        t_params = list(t_emb.parameters()) + list(t_bb.parameters())
+        opt = torch.optim.Adam(t_params, lr=1e-4)
+        t_off = devb[0][4][:TB + 1]
+        n_t = int(t_off[-1])
+        t_hist = eas.bin_events(devb[0][0][:n_t], devb[0][1][:n_t], devb[0][2][:n_t], devb[0][3][:n_t], t_off, H, W, TM,
+                                dtype=torch.float32)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+
+        def train_step(timed=False):
+            opt.zero_grad(set_to_none=True)
+            ev[0].record()
+            fr = torch.nn.functional.pad(t_emb(t_hist), (0, 320 - W, 0, 256 - H))
+            outs = t_bb(fr)
+            loss = sum((v.mean() - 0.2) ** 2 for v in outs.values())     # proxy loss (the SimOTA head is out of scope)
+            ev[1].record()
+            loss.backward()
+            ev[2].record()
+            parallel.allreduce_gradients(t_params)                       # the reference's one collective (trainer.py:176)
+            ev[3].record()
+            opt.step()
+            eas.reset_net(t_bb)                                          # trainer.py:115-117
+            ev[4].record()
+            return loss
+
+        for _ in range(3):
+            train_step()
+        barrier()
+        tsteps, parts = 5, np.zeros(4)
+        t0 = time.perf_counter()
+        for _ in range(tsteps):
+            loss = train_step()
+            torch.cuda.synchronize()
+            parts += [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+        barrier()
+        t_ms = parallel.max_over_ranks((time.perf_counter() - t0) * 1e3 / tsteps, dev)
+        train = {"value": world * TB / t_ms * 1e3, "unit": "samples/s", "ms_per_step": t_ms,
+                 "parts_ms": dict(zip(("forward", "backward", "allreduce", "adam+reset"), (parts / tsteps).round(3).tolist())),
+                 "what": "SYOLOX-S training step, %d windows per GPU, T=3, 256x320, fp32: sampler fwd + BPTT bwd (SAT "
+                         "surrogate + RPD) and 34 PLIF fwd/bwd on our kernels, conv / batch-stat BN through cuDNN, "
+                         "proxy loss on dark3-5 firing rates, NCCL gradient all-reduce (%d params), Adam"
+                         % (TB, sum(p.numel() for p in t_params)),
+                 "loss": float(loss.detach())}
+
     # ---- per-kernel durations (CUDA events on the launching stream) for the roofline -----------
     def time_call(fn, reps=10, warm=3):
         ts = []
@@ -440,6 +494,8 @@ def run_ours(args):
             "clocks": clk, "roofline": roofline}
     if frames is not None:
         line["frames"] = frames
+    if train is not None:
+        line["train"] = train
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
@@ -483,6 +539,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-backbone", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

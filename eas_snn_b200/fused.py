@@ -278,6 +278,13 @@ class _Focus(nn.Module):
         super().__init__()
         self.conv = _AnnStemConv(cin * 4, cout, k)
 
+    def forward(self, x):
+        """PyTorch path (training: batch statistics + autograd), ``[N, C, H, W]`` (network_blocks.py:199-213)."""
+        a, b = x[..., ::2, ::2], x[..., 1::2, ::2]
+        c, d = x[..., ::2, 1::2], x[..., 1::2, 1::2]
+        m = self.conv
+        return m.act(m.bn(m.conv(torch.cat((a, b, c, d), dim=1))))
+
     def run(self, frames: torch.Tensor) -> torch.Tensor:
         """frames ``[Tx, B, C, H, W]`` fp32 -> SiLU(BN(conv(space_to_depth))) as 2 fp16 planes
         ``[2, Tx, B, H/2, W/2, cout]`` (network_blocks.py:191-213)."""
@@ -300,6 +307,10 @@ class _Bottleneck(nn.Module):
     def run(self, x, T, out=None):
         # SEW add y + x (network_blocks.py:99-103) happens in the conv epilogue: values {0,1,2,..}
         return self.conv2.run(self.conv1.run(x, T), T, out=out, residual=x if self.use_add else None)
+
+    def forward(self, x):          # reference-shaped [T, B, C, H, W] (training path of the layers)
+        y = self.conv2(self.conv1(x))
+        return y + x if self.use_add else y
 
 
 class _SPP(nn.Module):
@@ -328,6 +339,10 @@ class _SPP(nn.Module):
                 cat[..., (i + 1) * hid:(i + 2) * hid].copy_(p.permute(0, 2, 3, 1).reshape(T, B, H, W, hid))
         return self.conv2.run(cat, T)
 
+    def forward(self, x):
+        x = self.conv1(x)
+        return self.conv2(torch.cat([x] + [m(x) for m in self.m], dim=-3))
+
 
 class _CSPLayer(nn.Module):
     def __init__(self, cin, cout, n, shortcut, spike_fn):
@@ -348,6 +363,9 @@ class _CSPLayer(nn.Module):
         for i, blk in enumerate(blocks):
             y = blk.run(y, T, out=cat[..., :hid] if i == len(blocks) - 1 else None)
         return self.conv3.run(cat, T)
+
+    def forward(self, x):
+        return self.conv3(torch.cat((self.m(self.conv1(x)), self.conv2(x)), dim=-3))
 
 
 class SpikingCSPDarknet(nn.Module):
@@ -380,7 +398,7 @@ class SpikingCSPDarknet(nn.Module):
     def run_cl(self, frames: torch.Tensor) -> dict:
         """All stage outputs as channels-last fp16 spike tensors ``[T, B, H, W, C]`` (what the fused FPN reads)."""
         if self.training:
-            raise RuntimeError("SpikingCSPDarknet (fused) is the inference path; call .eval()")
+            raise RuntimeError("run_cl is the fused inference path; call .eval() (training: forward())")
         _lib.require_cuda(frames)
         T = self.T
         if frames.shape[0] not in (1, T):
@@ -398,8 +416,31 @@ class SpikingCSPDarknet(nn.Module):
             outs[name] = x
         return outs
 
-    @torch.no_grad()
+    def forward_train(self, frames: torch.Tensor, return_all: bool = False):
+        """Training path (cfg 4): batch-statistics BN and autograd need the conv / BN outputs, so those two run as
+        PyTorch ops; every neuron (forward and surrogate-gradient backward) runs on ``eas_plif_fwd / eas_plif_bwd``.
+        ``frames`` ``[Ts or T, B, 2, H, W]``; the Ts == 1 frame is broadcast as spiking_yolox.py:54-55 does."""
+        _lib.require_cuda(frames)
+        T = self.T
+        if frames.shape[0] == 1:
+            frames = frames.expand(T, -1, -1, -1, -1)
+        if frames.shape[0] != T:
+            raise ValueError("the timestep of SNN is not matched with that of input")
+        outs = {}
+        x = self.stem(frames)
+        for name in ("dark2", "dark3", "dark4", "dark5"):
+            x = getattr(self, name)(x)
+            outs[name] = x
+        keys = outs.keys() if return_all else self.out_features
+        return {k: outs[k] for k in keys}
+
     def forward(self, frames: torch.Tensor, return_all: bool = False):
+        if self.training:
+            return self.forward_train(frames, return_all)
+        return self._forward_eval(frames, return_all)
+
+    @torch.no_grad()
+    def _forward_eval(self, frames: torch.Tensor, return_all: bool = False):
         outs = self.run_cl(frames)
         keys = outs.keys() if return_all else self.out_features
         return {k: outs[k].permute(0, 1, 4, 2, 3) for k in keys}

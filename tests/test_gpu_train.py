@@ -1,0 +1,105 @@
+"""GPU parity, training path (BASELINE config 4): spiking CSPDarknet in train mode -- PyTorch conv / batch-stat BN
+around the fused PLIF forward / surrogate backward kernels -- and a whole sampler + backbone optimiser step.
+
+The oracle runs ON THE GPU here (it is plain PyTorch), so both sides see identical cuDNN convolutions and the
+comparison isolates the neuron kernels: spikes must be identical, gradients agree to 2e-3 of max|g| (the w
+reduction and atomics reorder sums)."""
+import numpy as np
+import pytest
+import torch
+
+import eas_snn_b200 as eas
+from eas_snn_b200 import fused
+from oracle import backbone as ob
+from oracle.plif import ATan as OATan
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def strict_fp32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.deterministic)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.deterministic = old
+
+
+def _pair(cuda, wid=0.125):
+    torch.manual_seed(80)
+    onet = ob.SpikingCSPDarknet(0.33, wid, in_dim=2, spike_fn=OATan(2.0))
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand((1, 2, 2, 64, 96), generator=g) * 3.0
+    ob.calibrate_bn(onet, x.expand(3, -1, -1, -1, -1).contiguous(), seed=3)   # every stage fires
+    for i, m in enumerate(mm for mm in onet.modules() if hasattr(mm, "w") and isinstance(mm.w, torch.nn.Parameter)):
+        m.w.data.fill_(0.3 * ((i % 5) - 2))
+    net = fused.SpikingCSPDarknet(0.33, wid, in_dim=2, spike_fn=eas.ATan(2.0), T=3)
+    net.load_state_dict(onet.state_dict(), strict=True)
+    return onet.to(cuda).train(), net.to(cuda).train(), x.to(cuda)
+
+
+def test_train_mode_backbone_matches_oracle_autograd(cuda, strict_fp32):
+    onet, net, x = _pair(cuda)
+    xo = x.expand(3, -1, -1, -1, -1).contiguous().requires_grad_(True)
+    xg = x.clone().requires_grad_(True)
+    want = onet(xo)
+    got = net(xg)
+    loss_o = loss_g = 0.0
+    for i, k in enumerate(("dark3", "dark4", "dark5")):
+        assert torch.equal(got[k], want[k]), k + ": spikes differ in train mode"
+        assert 0.01 < float(want[k].detach().mean()) < 0.9
+        wgt = torch.linspace(-1.0, 1.0, want[k].numel(), device=cuda).view_as(want[k]) * (i + 1)
+        loss_o = loss_o + (want[k] * wgt).sum()
+        loss_g = loss_g + (got[k] * wgt).sum()
+    loss_o.backward()
+    loss_g.backward()
+    ob.reset_net(onet)
+    eas.reset_net(net)
+    po, pg = dict(onet.named_parameters()), dict(net.named_parameters())
+    assert set(po) == set(pg)
+    worst = 0.0
+    for n in po:
+        a, b = pg[n].grad, po[n].grad
+        assert a is not None and b is not None, n
+        err = float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+        worst = max(worst, err)
+        assert err < 2e-3, (n, err)
+    gx = xg.grad
+    gxo = xo.grad.sum(0, keepdim=True)           # the broadcast frame receives the sum over T
+    err = float((gx - gxo).abs().max() / gxo.abs().max())
+    print("train-mode backbone: worst relative gradient error %.2e (params), %.2e (input)" % (worst, err))
+    assert err < 2e-3
+    # BN running statistics moved identically (same batch statistics on both sides)
+    for (n, a), (_, b) in zip(net.named_buffers(), onet.named_buffers()):
+        assert torch.allclose(a.float(), b.float(), rtol=1e-5, atol=1e-6), n
+
+
+def test_sampler_plus_backbone_optimiser_step(cuda):
+    """One training step of the reference's shape (trainer.py:104-117): forward, backward through the PLIF and
+    sampler BPTT kernels (SAT surrogate + RPD), Adam update, reset_net."""
+    torch.manual_seed(1)
+    emb = eas.AdaptiveRSNNEmbedding(kernel_size=5, depth=2, nb_steps=4, thresh=1, vreset=0, Ts=1, write_zero=True,
+                                    spike_attach=True).to(cuda).train()
+    bb = fused.SpikingCSPDarknet(0.33, 0.25, in_dim=2, T=3).to(cuda).train()
+    for m in bb.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.bias.data.fill_(0.6)
+    params = list(emb.parameters()) + list(bb.parameters())
+    opt = torch.optim.Adam(params, lr=1e-3)
+    hist = torch.poisson(torch.full((2, 4, 2, 64, 96), 1.0)).to(cuda)
+    before = [p.detach().clone() for p in params]
+    losses = []
+    for _ in range(2):
+        opt.zero_grad(set_to_none=True)
+        outs = bb(emb(hist))
+        loss = sum((v.mean() - 0.2) ** 2 for v in outs.values())
+        loss.backward()
+        opt.step()
+        eas.reset_net(bb)
+        losses.append(float(loss))
+    assert all(np.isfinite(losses))
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in params)
+    moved = sum(int(not torch.equal(a, b)) for a, b in zip(before, params))
+    assert moved > 0.9 * len(params), (moved, len(params))
+    assert any(p.grad.abs().max() > 0 for p in emb.parameters()), "no gradient reached the sampler"
