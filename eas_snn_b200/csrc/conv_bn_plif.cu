@@ -23,6 +23,7 @@
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
 // Two mbarrier rings: B tiles are loaded once per K block and reused by all T time steps / input
 // planes, A tiles stream through a deeper ring.
+#include <cstdlib>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
@@ -40,6 +41,7 @@ struct ConvArgs {
   int T, Tx, B, Ho, Wo, Cin, Cout, ksize, stride, pad;
   int n_wsplit, n_xsplit;
   int NB, TH, TW;
+  int ksplit;             // single-accumulator layers: 2 = two issuer warps on alternate B stages, two accumulators
   int TWp;                // tap-reuse mode: tile width incl. the 2 halo columns (rows of the tile = TH x TWp)
   int tiles_w, tiles_h, tiles_b, tiles_n;
   int out_ld, out_mode, res_ld;
@@ -150,9 +152,11 @@ template <int BLOCK_N, int BK, bool REUSE = false>
 struct SmemLayout {
   static constexpr int A_BYTES = (REUSE ? REUSE_ROWS : BLOCK_M) * BK * 2;
   static constexpr int B_BYTES = BLOCK_N * BK * 2;
-  // one persistent CTA per SM: deep rings (A <= 128 KB, B <= 64 KB)
-  static constexpr int SA = 8;
-  static constexpr int SB = (64 * 1024 / (MAX_WSPLIT * B_BYTES)) > 8 ? 8 : (64 * 1024 / (MAX_WSPLIT * B_BYTES));
+  // one persistent CTA per SM: deep rings (A <= 128 KB, B <= 64 KB; 128-channel tiles: A <= 102 KB, B <= 96 KB)
+  static constexpr int SA = BLOCK_N > 64 ? 6 : 8;
+  static constexpr int B_BUDGET = (BLOCK_N > 64 ? 96 : 64) * 1024;
+  static constexpr int SB = (B_BUDGET / (MAX_WSPLIT * B_BYTES)) > 8 ? 8 : (B_BUDGET / (MAX_WSPLIT * B_BYTES));
+  static_assert(SB >= 2, "B ring too shallow");
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + SA * A_BYTES;
   static constexpr int OFF_BAR = OFF_B + SB * MAX_WSPLIT * B_BYTES;
@@ -201,7 +205,8 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Tacc = a.Tx;  // accumulators: one per distinct input time step
-  constexpr uint32_t kBufCols = TMAX * BLOCK_N;     // one accumulator set
+  constexpr int KS = TMAX == 1 ? 2 : 1;             // K-split accumulators of the single-time-step layers
+  constexpr uint32_t kBufCols = KS * TMAX * BLOCK_N;   // one accumulator set
   constexpr uint32_t kCols = 2 * kBufCols <= 32 ? 32 : 2 * kBufCols <= 64 ? 64 : 2 * kBufCols <= 128 ? 128
                              : 2 * kBufCols <= 256 ? 256 : 512;
   static_assert(2 * kBufCols <= 512, "double-buffered accumulators must fit TMEM");
@@ -209,13 +214,15 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   const int taps = a.ksize * a.ksize;
   const int nkb = taps * ncb;
   const int n_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
-  const int n_issuers = Tacc < N_ISSUERS ? Tacc : N_ISSUERS;
+  const bool ks2 = TMAX == 1 && a.ksplit == 2;
+  const int n_issuers = ks2 ? 2 : (Tacc < N_ISSUERS ? Tacc : N_ISSUERS);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
-    for (int i = 0; i < SA; ++i) mbar_init(fullA + i, 1), mbar_init(emptyA + i, 1);
-    for (int i = 0; i < SB; ++i) mbar_init(fullB + i, 1), mbar_init(emptyB + i, n_issuers);
+    // K-split: a B stage belongs to one issuer; in tap-reuse mode both issuers read every A slot
+    for (int i = 0; i < SA; ++i) mbar_init(fullA + i, 1), mbar_init(emptyA + i, (ks2 && REUSE) ? 2 : 1);
+    for (int i = 0; i < SB; ++i) mbar_init(fullB + i, 1), mbar_init(emptyB + i, ks2 ? 1 : n_issuers);
     for (int i = 0; i < 2; ++i) mbar_init(accum_full + i, n_issuers), mbar_init(accum_empty + i, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -241,10 +248,13 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         const uint32_t box_bytes = (uint32_t)((a.TH + 2) * a.TWp * BLOCK_K * 2);
         for (int cb = 0; cb < ncb; ++cb) {
           for (int t = 0; t < Tacc; ++t) {
-            mbar_wait(emptyA + sa, pa ^ 1);
-            mbar_expect_tx(fullA + sa, box_bytes);
-            tma_load_5d(sA + sa * A_BYTES, &xmap, fullA + sa, cb * BLOCK_K, tc.wo0 - 1, tc.ho0 - 1, tc.b0, t);
-            if (++sa == SA) sa = 0, pa ^= 1;
+            for (int i = 0; i < a.n_xsplit; ++i) {
+              mbar_wait(emptyA + sa, pa ^ 1);
+              mbar_expect_tx(fullA + sa, box_bytes);
+              tma_load_5d(sA + sa * A_BYTES, &xmap, fullA + sa, cb * BLOCK_K, tc.wo0 - 1, tc.ho0 - 1, tc.b0,
+                          i * a.Tx + t);
+              if (++sa == SA) sa = 0, pa ^= 1;
+            }
           }
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(emptyB + sb, pb ^ 1);
@@ -283,12 +293,84 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     // (warp-uniform) loop nest so that descriptors live in uniform registers; only its elected lane issues
     // tcgen05.mma / tcgen05.commit.
     const int wi = warp - 1;
-    if (wi < n_issuers) {
+    if (ks2) {
+      // ---- single time step (ANN layers, broadcast first spiking conv): one chain would leave the issue rate of
+      // ONE warp as the bound, so two warps take alternate B stages (K blocks / taps) into their own accumulators,
+      // which the epilogue adds ----
+      if constexpr (TMAX == 1) {
+        if (wi < 2) {
+          const bool leader = elect_one();
+          constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+          const uint64_t a_desc0 = make_kmajor_desc<BK>(smem_u32(sA)), b_desc0 = make_kmajor_desc<BK>(smem_u32(sB));
+          const int nx = a.n_xsplit, nw = a.n_wsplit;
+          int sa = 0, sb = 0;
+          uint32_t pa = 0, pb = 0;
+          int it = 0;
+          for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(accum_empty + buf, ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + (uint32_t)buf * kBufCols + (uint32_t)(wi * BLOCK_N);
+            uint32_t accf = 0;
+            int bcount = 0;
+            const int n_outer = REUSE ? ncb : nkb;
+            for (int kb = 0; kb < n_outer; ++kb) {
+              const int n_taps = REUSE ? 9 : 1;
+              const int first_tap = ((bcount & 1) == wi) ? 0 : 1;
+              const int last_tap = (((bcount + n_taps - 1) & 1) == wi) ? n_taps - 1 : n_taps - 2;
+              for (int tap = 0; tap < n_taps; ++tap, ++bcount) {
+                if ((bcount & 1) == wi) {
+                  mbar_wait(fullB + sb, pb);
+                  const uint64_t bdesc = b_desc0 + (uint64_t)((sb * MAX_WSPLIT * L::B_BYTES) >> 4);
+                  uint32_t shift = 0;
+                  if constexpr (REUSE) {
+                    const int ky = tap / 3, kx = tap - ky * 3;
+                    shift = (uint32_t)(((ky * a.TWp + kx) * BLOCK_K * 2) >> 4);
+                  }
+#pragma unroll
+                  for (int i = 0; i < 2; ++i) {
+                    if (i < nx) {
+                      int st = sa + i;
+                      uint32_t pt = pa;
+                      while (st >= SA) st -= SA, pt ^= 1;
+                      if (!REUSE || tap == first_tap) {
+                        mbar_wait(fullA + st, pt);
+                        tc_fence_after();
+                      }
+                      const uint64_t adesc = a_desc0 + (uint64_t)((st * A_BYTES) >> 4) + (uint64_t)shift;
+                      if (leader) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                          if (j + i < nw) {
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k) {
+                              tc_mma_f16(d0, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(((j * L::B_BYTES) >> 4) + k * 2),
+                                         idesc, accf);
+                              accf = 1u;
+                            }
+                          }
+                        }
+                        if (!REUSE || tap == last_tap) tc_commit(emptyA + st);
+                      }
+                    }
+                  }
+                  if (leader) tc_commit(emptyB + sb);
+                }
+                if (++sb == SB) sb = 0, pb ^= 1;
+              }
+              sa += nx;
+              while (sa >= SA) sa -= SA, pa ^= 1;
+            }
+            if (leader) tc_commit(accum_full + buf);
+          }
+        }
+      }
+    } else if (wi < n_issuers) {
       const bool leader = elect_one();
       // D = f32 (bit 4), A = B = f16 (format fields 0), K-major operands
       constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
       const uint64_t a_desc0 = make_kmajor_desc<BK>(smem_u32(sA)), b_desc0 = make_kmajor_desc<BK>(smem_u32(sB));
-      const int nx = REUSE ? 1 : a.n_xsplit, nw = a.n_wsplit;
+      const int nx = a.n_xsplit, nw = a.n_wsplit;
       const int per_kb = Tacc * nx;           // A slots consumed per K block (per channel block in tap-reuse mode)
       int sa = 0, sb = 0;                     // ring positions at the start of the current K block
       uint32_t pa = 0, pb = 0;
@@ -373,6 +455,8 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       ph = rem / a.TW, pw = rem - ph * a.TW;
     }
     const LifDyn d = make_lif(a.plif_w ? *a.plif_w : 0.0f, a.vth, a.hard_reset, a.vreset, a.decay_input);
+    // the neuron the reference builds (soft reset, decay_input=False, utils_snn.py:44-53): 5 instructions per step
+    const bool fast_lif = a.out_mode == EAS_CONV_OUT_SPIKES && !a.hard_reset && !a.decay_input;
     const int64_t step = (int64_t)a.B * a.Ho * a.Wo;                   // pixels per time step
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -385,8 +469,12 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       // the group's previous tile is done with sBias (every thread passed this barrier after its last read)
       asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
       for (int i = gtid; i < BLOCK_N; i += 128) {
-        sBias[i] = (n0 + i < a.Cout) ? a.bias[n0 + i] : 0.0f;
-        sUnscale[i] = (a.unscale && n0 + i < a.Cout) ? a.unscale[n0 + i] : 1.0f;
+        const float b_ = (n0 + i < a.Cout) ? a.bias[n0 + i] : 0.0f;
+        const float u_ = (a.unscale && n0 + i < a.Cout) ? a.unscale[n0 + i] : 1.0f;
+        // fast neuron path: work in the accumulator's scale.  u_ is a power of two, so dividing the bias and the
+        // threshold by it commutes with every rounding below: bit-identical potentials / spikes, one multiply less
+        sBias[i] = fast_lif ? __fdiv_rn(b_, u_) : b_;
+        sUnscale[i] = fast_lif ? __fdiv_rn(a.vth, u_) : u_;
       }
       const bool res_vec = a.residual != nullptr && valid && a.out_mode == EAS_CONV_OUT_SPIKES &&
                            (a.res_ld & 7) == 0 && (n0 & 7) == 0;
@@ -416,6 +504,16 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
 #pragma unroll
         for (int t = 0; t < TMAX; ++t)
           if (t < Tacc) tmem_ld16(tbase + (uint32_t)(t * BLOCK_N + c16 * 16), acc[t]);
+        if constexpr (TMAX == 1) {
+          if (ks2) {   // K-split: the two partial sums of the single time step
+            uint32_t acc2[16];
+            tmem_ld16(tbase + (uint32_t)(BLOCK_N + c16 * 16), acc2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              acc[0][j] = __float_as_uint(__fadd_rn(__uint_as_float(acc[0][j]), __uint_as_float(acc2[j])));
+          }
+        }
         tmem_ld_wait();
         if (c16 == NCH - 1) {   // last TMEM read of this tile: hand the accumulator buffer back (once per warp)
           tc_fence_before();
@@ -434,12 +532,23 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
             for (int t = 0; t < (TMAX == 1 ? 8 : TMAX); ++t) {
               if (t >= a.T) break;
               float sp[16];
+              if (fast_lif) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float xin = __uint_as_float(TMAX == 1 ? acc[0][j] : (Tacc == 1 ? acc[0][j] : acc[t < TMAX ? t : 0][j]));
-                const float h = lif_charge(d, v[j], __fadd_rn(__fmul_rn(xin, sUnscale[c16 * 16 + j]), sBias[c16 * 16 + j]));
-                sp[j] = lif_fire(d, h);
-                v[j] = lif_reset(d, h, sp[j]);
+                for (int j = 0; j < 16; ++j) {
+                  const float xin = __uint_as_float(TMAX == 1 ? acc[0][j] : (Tacc == 1 ? acc[0][j] : acc[t < TMAX ? t : 0][j]));
+                  const float vth_s = sUnscale[c16 * 16 + j];                       // vth / unscale
+                  const float h = __fadd_rn(__fmul_rn(v[j], d.k), __fadd_rn(xin, sBias[c16 * 16 + j]));
+                  sp[j] = h >= vth_s ? 1.0f : 0.0f;
+                  v[j] = __fmaf_rn(-sp[j], vth_s, h);                               // h - s * vth, one rounding
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float xin = __uint_as_float(TMAX == 1 ? acc[0][j] : (Tacc == 1 ? acc[0][j] : acc[t < TMAX ? t : 0][j]));
+                  const float h = lif_charge(d, v[j], __fadd_rn(__fmul_rn(xin, sUnscale[c16 * 16 + j]), sBias[c16 * 16 + j]));
+                  sp[j] = lif_fire(d, h);
+                  v[j] = lif_reset(d, h, sp[j]);
+                }
               }
               __half* dst = outp + ((int64_t)t * step + pix) * a.out_ld + ch0;
               if (a.residual) {  // SEW add: y = spikes + x (small integers, exact in fp16)
@@ -649,7 +758,10 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
   // 3x3 stride-1 layers on spike inputs: load every haloed input tile once and realise the nine taps as
   // descriptor shifts (9x less activation traffic from L2), when the padded tiles waste < 30 % of the MMA rows
   bool reuse = false;
-  if (c->ksize == 3 && c->stride == 1 && c->n_xsplit == 1 && c->Cin >= 32) {
+  static const bool no_reuse_x2 = getenv("EAS_CONV_NO_REUSE_X2") != nullptr;   // experiment switches
+  static const bool no_n128 = getenv("EAS_CONV_NO_N128") != nullptr;
+  // (every plane of every time step of a channel block must sit in the A ring at once: Tx * n_xsplit <= 6)
+  if (c->ksize == 3 && c->stride == 1 && (c->n_xsplit == 1 || (c->Tx == 1 && !no_reuse_x2)) && c->Cin >= 32) {
     int th = 0, tw = 0;
     if (pick_reuse_tile(Ho, Wo, &th, &tw) >= 0.70) reuse = true, a.NB = 1, a.TH = th, a.TW = tw, a.TWp = tw + 2;
   }
@@ -657,13 +769,22 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
   const int taps_ = c->ksize * c->ksize;
   const int nkb_ = taps_ * (int)eas_ceil_div(c->Cin, BK);
   // 64 output channels per tile; 32 for thin layers and for more than 4 distinct time steps (TMEM)
-  const int BLOCK_N = (c->Cout <= 32 || c->Tx > 4) ? 32 : 64;
+  // a single accumulator (Tx == 1: the ANN layers and the broadcast first spiking conv) leaves TMEM room for 128
+  // (an MMA of N <= 128 costs the same 64 cycles, so half as many of them); kept to grids of >= 1 wave
+  int BLOCK_N = (c->Cout <= 32 || c->Tx > 4) ? 32 : 64;
+  if (c->Tx == 1 && c->Cout > 64 && !no_n128) {
+    const int64_t t128 = eas_ceil_div(Wo, a.TW) * eas_ceil_div(Ho, a.TH) * eas_ceil_div(c->B, a.NB) *
+                         eas_ceil_div(c->Cout, 128);
+    if (t128 >= EAS_NUM_SMS) BLOCK_N = 128;
+  }
   a.tiles_w = (int)eas_ceil_div(Wo, a.TW), a.tiles_h = (int)eas_ceil_div(Ho, a.TH);
   a.tiles_b = (int)eas_ceil_div(c->B, a.NB), a.tiles_n = (int)eas_ceil_div(c->Cout, BLOCK_N);
   a.out_ld = out_ld, a.out_mode = c->out_mode;
   a.residual = (const __half*)c->residual, a.res_ld = c->res_ld ? c->res_ld : c->Cout;
   a.vth = c->v_threshold, a.vreset = c->v_reset, a.hard_reset = c->hard_reset, a.decay_input = c->decay_input;
   a.bias = bias, a.unscale = c->w_unscale, a.plif_w = plif_w, a.out = out;
+  static const bool no_ksplit = getenv("EAS_CONV_NO_KSPLIT") != nullptr;
+  a.ksplit = (c->Tx == 1 && (reuse ? 9 * (int)eas_ceil_div(c->Cin, BK) : nkb_) >= 2 && !no_ksplit) ? 2 : 1;
   const int64_t n_tiles = (int64_t)a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
   EAS_REQUIRE(n_tiles > 0 && n_tiles < (1ll << 31), EAS_E_SHAPE);
   const int64_t grid = n_tiles < EAS_NUM_SMS ? n_tiles : EAS_NUM_SMS;   // persistent: one CTA per SM
@@ -703,6 +824,12 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
   (BK == 64 ? launch_conv_t<BN_, 64>(Tacc, xmap, wmap, a, grid, st)                   \
    : BK == 32 ? launch_conv_t<BN_, 32>(Tacc, xmap, wmap, a, grid, st)                 \
               : launch_conv_t<BN_, 16>(Tacc, xmap, wmap, a, grid, st))
+  if (BLOCK_N == 128) {   // Tacc == 1 only
+    if (reuse) return launch_conv<128, 1, 32, true>(xmap, wmap, a, grid, st);
+    return BK == 64 ? launch_conv<128, 1, 64>(xmap, wmap, a, grid, st)
+           : BK == 32 ? launch_conv<128, 1, 32>(xmap, wmap, a, grid, st)
+                      : launch_conv<128, 1, 16>(xmap, wmap, a, grid, st);
+  }
   if (reuse) return BLOCK_N == 32 ? launch_conv_reuse<32>(Tacc, xmap, wmap, a, grid, st)
                                   : launch_conv_reuse<64>(Tacc, xmap, wmap, a, grid, st);
   if (BLOCK_N == 32) return EAS_CONV_BK(32);

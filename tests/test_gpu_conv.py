@@ -56,6 +56,47 @@ def test_preact_matches_fp32_conv(cuda, shape):
     assert ok, "%s: %s" % (shape, msg)
 
 
+@pytest.mark.parametrize("cfg", [
+    # B, H,  W,  Cin, Cout, k, stride : single-accumulator layers big enough (>= 148 tiles) for 128-channel tiles
+    (8, 64, 80, 64, 192, 3, 1),        # tap-reuse mode with two input planes, N tiles 128 + 64
+    (8, 64, 80, 96, 96, 1, 1),         # 1x1, one 128-wide tile with 96 live channels
+    (8, 64, 80, 64, 144, 3, 2),        # stride 2 (no tap reuse), N tail of 16
+    (16, 32, 40, 192, 200, 3, 1),      # ragged Cout, 6 channel blocks in tap-reuse mode
+])
+def test_ann_layers_wide_tiles_and_split_input_reuse(cuda, cfg):
+    """Real-valued input (two fp16 planes) -> SiLU planes / fp32 pre-activation on the wide-tile kernels."""
+    B, H, W, Cin, Cout, k, stride = cfg
+    g = torch.Generator().manual_seed(sum(cfg))
+    x = torch.randn((1, B, H, W, Cin), generator=g)
+    w = torch.randn((Cout, Cin, k, k), generator=g) / (Cin * k * k) ** 0.5
+    bias = torch.randn(Cout, generator=g) * 0.2
+    xc, bc = x.to(cuda), bias.to(cuda)
+    wp, un = fused.pack_weight(w.to(cuda), 2)
+    want = (F.conv2d(xc[0].permute(0, 3, 1, 2).double(), w.to(cuda).double(), bc.double(), stride, (k - 1) // 2)
+            .permute(0, 2, 3, 1).unsqueeze(0))
+    got = fused.conv_bn_plif(fused.split_f16(xc, 2), wp, bc, None, 1, k, stride, n_xsplit=2,
+                             out_mode=fused.OUT_PREACT, w_unscale=un)
+    K = Cin * k * k
+    ok, msg = close_report(got, want, rtol=3e-6, atol=3e-6 + 2.5e-8 * K)
+    print("wide tile %s: %s" % (cfg, msg))
+    assert ok, msg
+    planes = fused.conv_bn_plif(fused.split_f16(xc, 2), wp, bc, None, 1, k, stride, n_xsplit=2,
+                                out_mode=fused.OUT_SILU2, w_unscale=un)
+    ok, msg = close_report(planes.float().sum(0), F.silu(want).float(), rtol=1e-5, atol=1e-5)
+    assert ok, msg
+    # and as the broadcast first spiking conv: one accumulator, T = 3 LIF steps in the epilogue
+    spikes = fused.conv_bn_plif(fused.split_f16(xc, 2), wp, bc, torch.zeros((), device=cuda), 3, k, stride,
+                                n_xsplit=2, out_mode=fused.OUT_SPIKES, w_unscale=un)
+    pre = want[0].float()
+    v = torch.zeros_like(pre)
+    for t in range(3):
+        v = v * 0.5 + pre
+        s_ = (v >= 1.0).float()
+        v = v - s_
+        mism = (spikes[t].float() != s_).float().mean().item()
+        assert mism <= 1e-4, (t, mism)
+
+
 def test_single_plane_is_fp16_accurate(cuda):
     g = torch.Generator().manual_seed(1)
     x = torch.randint(0, 2, (1, 1, 16, 16, 64), generator=g).float()
