@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libeas_b200.so")
+LIB_PATH = os.environ.get("EAS_B200_LIB") or os.path.join(_HERE, "lib", "libeas_b200.so")
 
 EAS_F32, EAS_I32, EAS_BF16, EAS_U8 = 0, 1, 2, 3
 READOUT = {"sum": 0, "last": 1, "avg": 2}
@@ -75,6 +75,7 @@ SIGNATURES = {
     "eas_time_mean_planes": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, C.c_int, _P, C.c_int, C.c_int64, _P]),
     "eas_upsample2x_planes": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _P,
                                         C.c_int, C.c_int64, _P]),
+    "eas_focus_im2col": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, C.c_int64, _P]),
     "eas_yolox_decode": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P,
                                    C.c_int64, C.c_int64, _P]),
 }

@@ -149,3 +149,66 @@ extern "C" int eas_yolox_decode(const float* preds, int64_t n_images, int H, int
   EAS_LAUNCH_CHECK();
   return EAS_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Focus stem front end (yolox/models/network_blocks.py:191-213): space-to-depth (4 phase planes concatenated on
+// channels: top-left, bottom-left, top-right, bottom-right) followed by the stem's 3x3 conv.  An 8-channel 3x3
+// conv is a poor fit for TMA (nine 32-byte-row boxes per tile), so this kernel writes the im2col rows of the
+// space-to-depth tensor instead -- [pixel][tap (ky, kx)][phase q = dy + 2 dx][c] = 72 values, zero padded to 80 --
+// as two fp16 planes hi + lo, and the stem runs as a 1x1 conv with K = 80 on the tensor cores.
+// One thread per (pixel, tap slot): 8 fp32 reads (L2 resident frames), one 16-byte store per plane.
+namespace {
+
+__global__ void __launch_bounds__(256)
+focus_im2col_kernel(const float* __restrict__ frames, int64_t n_img, int H, int W, __half* __restrict__ out,
+                    int64_t out_plane) {
+  const int H2 = H >> 1, W2 = W >> 1;
+  const int64_t total = n_img * H2 * W2 * 10;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int slot = (int)(i % 10);
+    int64_t r = i / 10;
+    const int w2 = (int)(r % W2);
+    r /= W2;
+    const int h2 = (int)(r % H2);
+    const int64_t img = r / H2;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+    if (slot < 9) {
+      const int ky = slot / 3, kx = slot - ky * 3;
+      const int hs = h2 + ky - 1, ws = w2 + kx - 1;          // pixel of the space-to-depth map (zero padding outside)
+      if (hs >= 0 && hs < H2 && ws >= 0 && ws < W2) {
+        const float* src = frames + (img * 2 * H + 2 * hs) * W + 2 * ws;     // channel 0, row 2 hs, col 2 ws
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float2 r0 = *reinterpret_cast<const float2*>(src + (int64_t)c * H * W);        // dy = 0: dx = 0, 1
+          const float2 r1 = *reinterpret_cast<const float2*>(src + (int64_t)c * H * W + W);    // dy = 1
+          v[0 * 2 + c] = r0.x, v[1 * 2 + c] = r1.x, v[2 * 2 + c] = r0.y, v[3 * 2 + c] = r1.y;  // q = dy + 2 dx
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fminf(fmaxf(v[j], -65504.0f), 65504.0f);
+    uint4 hi, lo;
+    split8(v, &hi, &lo);
+    __half* dst = out + (i / 10) * 80 + slot * 8;
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + out_plane) = lo;
+  }
+}
+
+}  // namespace
+
+extern "C" int eas_focus_im2col(const float* frames, int64_t n_images, int H, int W, void* out,
+                                int64_t out_plane_stride, void* stream) {
+  EAS_REQUIRE(n_images >= 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, EAS_E_SHAPE);
+  EAS_REQUIRE(out_plane_stride % 8 == 0, EAS_E_SHAPE);
+  if (n_images == 0) return EAS_OK;
+  EAS_REQUIRE(frames && out, EAS_E_NULL);
+  EAS_REQUIRE((uintptr_t)frames % 8 == 0 && (uintptr_t)out % 16 == 0, EAS_E_ALIGN);
+  const int64_t total = n_images * (H / 2) * (W / 2) * 10;
+  focus_im2col_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(frames, n_images, H, W, (__half*)out,
+                                                                         out_plane_stride);
+  EAS_LAUNCH_CHECK();
+  return EAS_OK;
+}

@@ -285,9 +285,34 @@ class _Focus(nn.Module):
         m = self.conv
         return m.act(m.bn(m.conv(torch.cat((a, b, c, d), dim=1))))
 
+    def packed_im2col(self):
+        """The stem conv as a 1x1 conv over im2col rows ``[tap][focus channel]`` (72 -> 80 zero padded)."""
+        m = self.conv
+        src = (m.conv.weight, m.bn.weight, m.bn.bias, m.bn.running_mean, m.bn.running_var)
+        key = tuple((t.data_ptr(), t._version) for t in src)
+        if getattr(self, "_cache_i2c", None) is None or self._cache_i2c[0] != key:
+            with torch.no_grad():
+                w, shift = fold_bn(m.conv.weight, m.bn.weight, m.bn.bias, m.bn.running_mean, m.bn.running_var, m.bn.eps)
+                w80 = torch.zeros((w.shape[0], 80, 1, 1), dtype=torch.float32, device=w.device)
+                w80[:, :72, 0, 0] = w.permute(0, 2, 3, 1).reshape(w.shape[0], 72)       # (ky, kx, cin) order
+                wp, unscale = pack_weight(w80, 2)
+                self._cache_i2c = (key, wp, shift.contiguous(), unscale)
+        return self._cache_i2c[1:]
+
     def run(self, frames: torch.Tensor) -> torch.Tensor:
         """frames ``[Tx, B, C, H, W]`` fp32 -> SiLU(BN(conv(space_to_depth))) as 2 fp16 planes
         ``[2, Tx, B, H/2, W/2, cout]`` (network_blocks.py:191-213)."""
+        Tx, B, Cf, H, W = frames.shape
+        if Cf == 2 and self.conv.conv.kernel_size == (3, 3) and H % 2 == 0 and W % 2 == 0:
+            # space-to-depth + im2col + fp16 hi/lo split in one pass, then a K = 80 1x1 conv on the tensor cores
+            fr = frames.float().contiguous()
+            cols = torch.empty((2, Tx, B, H // 2, W // 2, 80), dtype=ACT_DTYPE, device=frames.device)
+            with torch.cuda.device(frames.device):
+                rc = _lib.lib().eas_focus_im2col(_lib.ptr(fr), Tx * B, H, W, _lib.ptr(cols), cols.stride(0),
+                                                 _lib.stream_ptr())
+            _lib.check(rc, "eas_focus_im2col")
+            wp, shift, unscale = self.packed_im2col()
+            return conv_bn_plif(cols, wp, shift, None, Tx, 1, 1, n_xsplit=2, out_mode=OUT_SILU2, w_unscale=unscale)
         a, b = frames[..., ::2, ::2], frames[..., 1::2, ::2]
         c, d = frames[..., ::2, 1::2], frames[..., 1::2, 1::2]
         x = torch.cat((a, b, c, d), dim=2).permute(0, 1, 3, 4, 2).contiguous()      # channels-last fp32

@@ -248,6 +248,12 @@ int eas_upsample2x_planes(const void* in, int n_planes, int64_t in_plane_stride,
  * anchor_offset.  decode = 0 keeps (x, y, w, h) raw (decode_in_inference = False). */
 int eas_yolox_decode(const float* preds, int64_t n_images, int H, int W, int n_ch, int ld, float stride,
                      int decode, float* out, int64_t anchor_offset, int64_t n_anchors_total, void* stream);
+/* Focus stem front end, yolox/models/network_blocks.py:199-213 (space-to-depth of the 2-channel frames) fused with
+ * the im2col of the stem's 3x3 conv: frames f32 [n_images][2][H][W] -> out fp16 planes hi/lo
+ * [n_images][H/2][W/2][80], row = [tap (ky, kx)][phase dy + 2 dx][c] (72 values + 8 zeros), zero padding at the
+ * borders; the stem conv then runs as a 1x1 conv with K = 80 through eas_conv_bn_plif_fwd. */
+int eas_focus_im2col(const float* frames, int64_t n_images, int H, int W, void* out, int64_t out_plane_stride,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -255,3 +255,34 @@ def test_graphed_backbone_replays_the_eager_forward(cuda):
         for k in want:
             assert torch.equal(got[k], want[k]), k
         assert 0.01 < float(want["dark5"].float().mean()) < 0.9
+
+
+def test_focus_im2col_and_stem_match_torch(cuda):
+    """eas_focus_im2col (space-to-depth + 3x3 im2col + fp16 hi/lo split) against torch slicing + unfold, and the
+    stem (Focus conv -> BN -> SiLU, network_blocks.py:191-213) through it against fp32 PyTorch."""
+    from eas_snn_b200 import _lib
+    g = torch.Generator().manual_seed(9)
+    Tx, B, H, W = 1, 3, 20, 28
+    fr = (torch.randn((Tx, B, 2, H, W), generator=g) * 3).to(cuda)
+    cols = torch.empty((2, Tx, B, H // 2, W // 2, 80), dtype=torch.float16, device=cuda)
+    rc = _lib.lib().eas_focus_im2col(_lib.ptr(fr), Tx * B, H, W, _lib.ptr(cols), cols.stride(0), _lib.stream_ptr())
+    assert rc == 0
+    x = fr[0]
+    s2d = torch.cat((x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]), dim=1)   # [B, 8, H/2, W/2]
+    unf = F.unfold(s2d, 3, padding=1).view(B, 8, 9, H // 2, W // 2).permute(0, 3, 4, 2, 1).reshape(B, H // 2, W // 2, 72)
+    got = cols.float().sum(0)[0]
+    assert torch.allclose(got[..., :72], unf, rtol=2.0 ** -21, atol=1e-7)
+    assert not got[..., 72:].any()
+    torch.manual_seed(3)
+    stem = fused._Focus(2, 24, 3).to(cuda).eval()
+    stem.conv.bn.running_mean.normal_(0, 0.2)
+    stem.conv.bn.running_var.uniform_(0.5, 1.5)
+    stem.conv.bn.weight.data.uniform_(0.8, 1.2)
+    with torch.no_grad():
+        want = stem(x.double()) if False else stem.double()(x.double()).float()
+        stem.float()
+        planes = stem.run(fr)
+    gotp = planes.float().sum(0)[0].permute(0, 3, 1, 2)
+    ok, msg = close_report(gotp, want, rtol=1e-5, atol=1e-5)
+    print("stem via im2col:", msg)
+    assert ok, msg
