@@ -43,6 +43,9 @@ WORKLOAD = "gen1_240x304_b64_Tm4_sampler_d2k5_sat_rpd"
 METRIC, UNIT = "Mevents/s sampled+encoded", "Mevents/s"
 
 
+_JSON_LINE: list = []     # the one line main() prints on the real stdout
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -178,7 +181,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _JSON_LINE.append(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -499,7 +502,7 @@ def run_ours(args):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line), flush=True)
+        _JSON_LINE.append(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -541,10 +544,22 @@ def main():
     ap.add_argument("--no-backbone", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE line (the JSON): libraries that write to fd 1 (NCCL prints its version banner
+    # there) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if _JSON_LINE:
+        print(_JSON_LINE[0], flush=True)
 
 
 if __name__ == "__main__":

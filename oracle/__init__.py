@@ -25,4 +25,9 @@ Parity pinning
   ``yolox/utils/model_utils.py:35-77``; the conv/BN arithmetic is PINNED by golden
   vectors from the reference model run through ``oracle/sj_shim`` (so the neuron inside
   is the unpinned restatement above).
+* ``oracle.detector`` follows ``yolox/models/spiking_yolo_pafpn.py:89-120``,
+  ``yolox/models/yolo_head.py:141-250``, ``yolox/models/spiking_yolox.py:38-74``          -- PINNED
+  by ``tests/golden/detector.npz``: the reference's own ``EventExp.get_model()`` (use_spike True,
+  tiny width) run through ``oracle/sj_shim`` from histograms to decoded predictions and its
+  ``postprocess`` detections.
 """
