@@ -41,6 +41,8 @@ struct ConvArgs {
   int T, Tx, B, Ho, Wo, Cin, Cout, ksize, stride, pad;
   int n_wsplit, n_xsplit;
   int NB, TH, TW;
+  int sa_ring;            // A ring slots in use: a multiple of the slots per K block (Tx * n_xsplit), so a group never wraps
+  int a_group;            // 1: ONE TMA box [Tx * n_xsplit planes] per K block into consecutive slots (one full barrier)
   int ksplit;             // single-accumulator layers: 2 = two issuer warps on alternate B stages, two accumulators
   int TWp;                // tap-reuse mode: tile width incl. the 2 halo columns (rows of the tile = TH x TWp)
   int tiles_w, tiles_h, tiles_b, tiles_n;
@@ -85,6 +87,13 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
   asm volatile(
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
@@ -153,7 +162,7 @@ struct SmemLayout {
   static constexpr int A_BYTES = (REUSE ? REUSE_ROWS : BLOCK_M) * BK * 2;
   static constexpr int B_BYTES = BLOCK_N * BK * 2;
   // one persistent CTA per SM: deep rings (A <= 128 KB, B <= 64 KB; 128-channel tiles: A <= 102 KB, B <= 96 KB)
-  static constexpr int SA = BLOCK_N > 64 ? 6 : 8;
+  static constexpr int SA = BLOCK_N > 64 ? 6 : (REUSE ? 8 : 9);   // 9 = three K-block groups of T = 3 time steps
   static constexpr int B_BUDGET = (BLOCK_N > 64 ? 96 : 64) * 1024;
   static constexpr int SB = (B_BUDGET / (MAX_WSPLIT * B_BYTES)) > 8 ? 8 : (B_BUDGET / (MAX_WSPLIT * B_BYTES));
   static_assert(SB >= 2, "B ring too shallow");
@@ -239,29 +248,31 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
+    // The single producer thread is the scarce resource of the short-K layers (ncu: it never waits for a free slot
+    // while the issuers wait for data), so it issues as few TMA instructions as possible: the weight planes hi / lo of
+    // a K block are ONE 4-D box, and the activation tiles of all time steps / input planes of a K block are ONE 5-D
+    // box landing in consecutive ring slots (slot order = plane-major, like the tensor).
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
+    const int per_kb = Tacc * a.n_xsplit;
+    const int SAR = a.sa_ring;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const TileCoord tc = tile_coord(a, tile, BLOCK_N);
       if constexpr (REUSE) {
         // channel block outer: the haloed tile of every time step once, then the nine weight taps
         const uint32_t box_bytes = (uint32_t)((a.TH + 2) * a.TWp * BLOCK_K * 2);
         for (int cb = 0; cb < ncb; ++cb) {
-          for (int t = 0; t < Tacc; ++t) {
-            for (int i = 0; i < a.n_xsplit; ++i) {
-              mbar_wait(emptyA + sa, pa ^ 1);
-              mbar_expect_tx(fullA + sa, box_bytes);
-              tma_load_5d(sA + sa * A_BYTES, &xmap, fullA + sa, cb * BLOCK_K, tc.wo0 - 1, tc.ho0 - 1, tc.b0,
-                          i * a.Tx + t);
-              if (++sa == SA) sa = 0, pa ^= 1;
-            }
+          for (int g = 0; g < per_kb; ++g) {       // slot g = plane g of the tensor (i * Tx + t)
+            mbar_wait(emptyA + sa + g, pa ^ 1);
+            mbar_expect_tx(fullA + sa + g, box_bytes);
+            tma_load_5d(sA + (sa + g) * A_BYTES, &xmap, fullA + sa + g, cb * BLOCK_K, tc.wo0 - 1, tc.ho0 - 1, tc.b0, g);
           }
+          sa += per_kb;
+          if (sa == SAR) sa = 0, pa ^= 1;
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(emptyB + sb, pb ^ 1);
             mbar_expect_tx(fullB + sb, (uint32_t)(a.n_wsplit * L::B_BYTES));
-            for (int j = 0; j < a.n_wsplit; ++j)
-              tma_load_3d(sB + (sb * MAX_WSPLIT + j) * L::B_BYTES, &wmap, fullB + sb, cb * BLOCK_K, tap,
-                          j * a.Cout + tc.n0);
+            tma_load_4d(sB + sb * MAX_WSPLIT * L::B_BYTES, &wmap, fullB + sb, cb * BLOCK_K, tap, tc.n0, 0);
             if (++sb == SB) sb = 0, pb ^= 1;
           }
         }
@@ -272,18 +283,25 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         const int ky = tap / a.ksize, kx = tap - ky * a.ksize;
         mbar_wait(emptyB + sb, pb ^ 1);
         mbar_expect_tx(fullB + sb, (uint32_t)(a.n_wsplit * L::B_BYTES));
-        for (int j = 0; j < a.n_wsplit; ++j)
-          tma_load_3d(sB + (sb * MAX_WSPLIT + j) * L::B_BYTES, &wmap, fullB + sb, cb * BLOCK_K, tap, j * a.Cout + tc.n0);
+        tma_load_4d(sB + sb * MAX_WSPLIT * L::B_BYTES, &wmap, fullB + sb, cb * BLOCK_K, tap, tc.n0, 0);
         if (++sb == SB) sb = 0, pb ^= 1;
-        for (int t = 0; t < Tacc; ++t) {
-          for (int i = 0; i < a.n_xsplit; ++i) {
-            mbar_wait(emptyA + sa, pa ^ 1);
-            mbar_expect_tx(fullA + sa, (uint32_t)A_BYTES);
-            tma_load_5d(sA + sa * A_BYTES, &xmap, fullA + sa, cb * BLOCK_K, tc.wo0 * a.stride + kx - a.pad,
-                        tc.ho0 * a.stride + ky - a.pad, tc.b0, i * a.Tx + t);
-            if (++sa == SA) sa = 0, pa ^= 1;
+        const int cx = tc.wo0 * a.stride + kx - a.pad, cy = tc.ho0 * a.stride + ky - a.pad;
+        if (a.a_group) {
+          for (int g = 0; g < per_kb; ++g) mbar_wait(emptyA + sa + g, pa ^ 1);
+          mbar_expect_tx(fullA + sa, (uint32_t)(per_kb * A_BYTES));
+          tma_load_5d(sA + sa * A_BYTES, &xmap, fullA + sa, cb * BLOCK_K, cx, cy, tc.b0, 0);
+        } else {
+          for (int g = 0; g < per_kb; ++g) {
+            int st = sa + g;
+            uint32_t pt = pa;
+            while (st >= SAR) st -= SAR, pt ^= 1;
+            mbar_wait(emptyA + st, pt ^ 1);
+            mbar_expect_tx(fullA + st, (uint32_t)A_BYTES);
+            tma_load_5d(sA + st * A_BYTES, &xmap, fullA + st, cb * BLOCK_K, cx, cy, tc.b0, g);
           }
         }
+        sa += per_kb;
+        while (sa >= SAR) sa -= SAR, pa ^= 1;
       }
     }
   } else if (warp >= 1 && warp <= N_ISSUERS) {
@@ -330,11 +348,9 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
 #pragma unroll
                   for (int i = 0; i < 2; ++i) {
                     if (i < nx) {
-                      int st = sa + i;
-                      uint32_t pt = pa;
-                      while (st >= SA) st -= SA, pt ^= 1;
+                      const int st = sa + i;                      // (a group never wraps: sa_ring % per_kb == 0)
                       if (!REUSE || tap == first_tap) {
-                        mbar_wait(fullA + st, pt);
+                        mbar_wait(fullA + (a.a_group ? sa : st), pa);   // grouped load: one barrier per K block
                         tc_fence_after();
                       }
                       const uint64_t adesc = a_desc0 + (uint64_t)((st * A_BYTES) >> 4) + (uint64_t)shift;
@@ -359,7 +375,7 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
                 if (++sb == SB) sb = 0, pb ^= 1;
               }
               sa += nx;
-              while (sa >= SA) sa -= SA, pa ^= 1;
+              if (sa == a.sa_ring) sa = 0, pa ^= 1;
             }
             if (leader) tc_commit(accum_full + buf);
           }
@@ -398,11 +414,11 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                   if (i < nx) {
-                    int st = sa + t * nx + i;
+                    int st = sa + i * Tacc + t;                   // plane-major, like the tensor
                     uint32_t pt = pa;
-                    while (st >= SA) st -= SA, pt ^= 1;
+                    while (st >= a.sa_ring) st -= a.sa_ring, pt ^= 1;   // (only the slot-by-slot fall-back wraps)
                     if (tap == 0) {
-                      mbar_wait(fullA + st, pt);
+                      mbar_wait(fullA + (a.a_group ? sa : st), pt);   // grouped load: one barrier per K block
                       tc_fence_after();
                     }
                     const uint64_t adesc = a_desc0 + (uint64_t)((st * A_BYTES) >> 4) + (uint64_t)shift;
@@ -428,7 +444,7 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
             if (++sb == SB) sb = 0, pb ^= 1;
           }
           sa += per_kb;
-          while (sa >= SA) sa -= SA, pa ^= 1;
+          while (sa >= a.sa_ring) sa -= a.sa_ring, pa ^= 1;
         }
         if (leader) tc_commit(accum_full + buf);
       }
@@ -783,6 +799,14 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
   a.residual = (const __half*)c->residual, a.res_ld = c->res_ld ? c->res_ld : c->Cout;
   a.vth = c->v_threshold, a.vreset = c->v_reset, a.hard_reset = c->hard_reset, a.decay_input = c->decay_input;
   a.bias = bias, a.unscale = c->w_unscale, a.plif_w = plif_w, a.out = out;
+  {
+    const int per_kb = c->Tx * c->n_xsplit;
+    const int SA_T = BLOCK_N > 64 ? 6 : (reuse ? 8 : 9);              // SmemLayout::SA of the kernel picked below
+    static const bool no_group = getenv("EAS_CONV_NO_AGROUP") != nullptr;
+    EAS_REQUIRE(!reuse || per_kb <= SA_T, EAS_E_UNSUPPORTED);         // tap reuse keeps every plane of a channel block
+    a.a_group = (!reuse && per_kb <= SA_T && !no_group) ? 1 : 0;      // (more planes than slots: slot-by-slot loads)
+    a.sa_ring = per_kb <= SA_T ? SA_T / per_kb * per_kb : SA_T;       // whole groups, so that a group never wraps
+  }
   static const bool no_ksplit = getenv("EAS_CONV_NO_KSPLIT") != nullptr;
   a.ksplit = (c->Tx == 1 && (reuse ? 9 * (int)eas_ceil_div(c->Cin, BK) : nkb_) >= 2 && !no_ksplit) ? 2 : 1;
   const int64_t n_tiles = (int64_t)a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
@@ -799,7 +823,7 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
     cuuint64_t strides[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)c->W * x_ld * 2, (cuuint64_t)c->H * c->W * x_ld * 2,
                              (cuuint64_t)c->B * c->H * c->W * x_ld * 2};
     cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)(a.TW * c->stride), (cuuint32_t)(a.TH * c->stride),
-                         (cuuint32_t)a.NB, 1};
+                         (cuuint32_t)a.NB, (cuuint32_t)(a.a_group ? c->Tx * c->n_xsplit : 1)};
     if (reuse) box[1] = (cuuint32_t)a.TWp, box[2] = (cuuint32_t)(a.TH + 2);
     cuuint32_t estr[5] = {1, (cuuint32_t)c->stride, (cuuint32_t)c->stride, 1, 1};
     CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
@@ -808,12 +832,14 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
     if (r != CUDA_SUCCESS) return EAS_E_SHAPE;
   }
   {
+    // weights [n_wsplit][Cout][taps][Cin]: the hi / lo planes of an N tile are one box {BK, 1, BLOCK_N, n_wsplit}
     const int taps = c->ksize * c->ksize;
-    cuuint64_t dims[3] = {(cuuint64_t)c->Cin, (cuuint64_t)taps, (cuuint64_t)(c->n_wsplit * c->Cout)};
-    cuuint64_t strides[2] = {(cuuint64_t)c->Cin * 2, (cuuint64_t)taps * c->Cin * 2};
-    cuuint32_t box[3] = {(cuuint32_t)BK, 1, (cuuint32_t)BLOCK_N};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(w_planes), dims, strides, box,
+    cuuint64_t dims[4] = {(cuuint64_t)c->Cin, (cuuint64_t)taps, (cuuint64_t)c->Cout, (cuuint64_t)c->n_wsplit};
+    cuuint64_t strides[3] = {(cuuint64_t)c->Cin * 2, (cuuint64_t)taps * c->Cin * 2,
+                             (cuuint64_t)c->Cout * taps * c->Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, 1, (cuuint32_t)BLOCK_N, (cuuint32_t)c->n_wsplit};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(w_planes), dims, strides, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return EAS_E_SHAPE;
