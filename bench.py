@@ -151,6 +151,38 @@ def cpu_baseline(budget_s: float = 12.0, windows: int = 16):
                       "(1 thread) + torch-CPU sampler (%d threads)" % (windows, BATCH, n, len(times), cores)}
 
 
+def cpu_frames_baseline(budget_s: float = 15.0):
+    """BASELINE config 1 on the host: the oracle port of the reference's SYOLOX-S (use_spike True) forward, batch 1,
+    T=3, one 240x304 window zero-padded to 256x320: events -> bins -> sampler -> detector -> decoded predictions."""
+    from eas_snn_b200 import synth
+    from oracle import detector as odet
+    from oracle.plif import ATan as OATan
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(80)
+    net = odet.OracleSpikingYOLOX(0.33, 0.50, 2, 3, embedding=make_cpu_model(), spike_fn=OATan(2.0)).eval()
+    for mod in net.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.bias.data.fill_(0.6)
+    batch = synth.gen1_batch(1, cfg=2, first_sample=0)      # the window the GPU latency block uses (rank 0, set 0)
+
+    def one():
+        with torch.no_grad():
+            fr = cpu_step(net.embedding, batch)
+            return net.detect_frames(torch.nn.functional.pad(fr, (0, 320 - W, 0, 256 - H)))
+
+    one()
+    times, t_end = [], time.perf_counter() + budget_s
+    while len(times) < 2 or (time.perf_counter() < t_end and len(times) < 20):
+        t0 = time.perf_counter()
+        one()
+        times.append(time.perf_counter() - t0)
+    med = float(np.median(times))
+    return {"value": 1.0 / med, "unit": "frames/s", "ms_per_frame": med * 1e3, "cores": cores, "kind": "port",
+            "sample": "SYOLOX-S, batch 1, T=3, 256x320, %d events: numpy binning + torch-CPU sampler, spiking "
+                      "CSPDarknet, PAFPN, head, decode (%d threads), median of %d passes" % (int(batch[4][-1]), cores, len(times))}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -374,6 +406,43 @@ def run_ours(args):
                "pred_checksum": float(mp.float().abs().mean())}
         del rep
 
+    # ---- secondary metric: batch-1 latency (BASELINE config 1 on the GPU): SYOLOX-S, one window -> predictions ----
+    latency = None
+    if not args.no_backbone:
+        from eas_snn_b200 import fused
+        torch.manual_seed(83)
+        det_s = detector.build_syolox(0.33, 0.50, num_classes=2, T=3, embedding=model).to(dev).eval()   # e_yolox_s.py:13-14
+        for mod in det_s.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.bias.data.fill_(0.6)
+        o1 = devb[0][4][:2]
+        n1 = int(o1[-1])
+        ev1 = tuple(a[:n1] for a in devb[0][:4])
+        fr1 = pad(model(eas.bin_events(*ev1, o1, H, W, TM, dtype=torch.float32))).contiguous()
+        graph = fused.GraphedForward(det_s.detect_frames, fr1)          # ~110 launches replayed by one host call
+        hist1 = torch.empty((1, TM, 2, H, W), dtype=torch.float32, device=dev)
+
+        def lat_step():
+            with torch.no_grad():
+                fr = model(eas.bin_events(*ev1, o1, H, W, TM, out=hist1))
+            return graph(pad(fr))
+
+        for _ in range(5):
+            lat_step()
+        barrier()
+        ts = []
+        for _ in range(30):
+            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0.record()
+            lp = lat_step()
+            l1.record()
+            torch.cuda.synchronize()
+            ts.append(l0.elapsed_time(l1))
+        latency = {"value": float(np.median(ts)), "unit": "ms", "higher_is_better": False,
+                   "what": "SYOLOX-S, batch 1, T=3: %d events of one 50 ms window -> bins -> sampler -> detector (CUDA "
+                           "graph replay) -> decoded predictions [1, 1680, 7]; median of 30" % n1,
+                   "pred_checksum": float(lp.float().abs().mean())}
+
     # ---- secondary metric: SYOLOX-S training step (BASELINE config 4), 8 windows per GPU --------------------
     train = None
     if not args.no_train:
@@ -534,11 +603,15 @@ def run_ours(args):
         line["frames"] = frames
     if mpx is not None:
         line["mpx"] = mpx
+    if latency is not None:
+        line["latency"] = latency
     if train is not None:
         line["train"] = train
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
+            if not args.no_backbone:
+                line["cpu_baseline"]["frames"] = cpu_frames_baseline()
         _JSON_LINE.append(json.dumps(line))
     if world > 1:
         dist.barrier()

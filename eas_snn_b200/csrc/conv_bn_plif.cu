@@ -23,7 +23,6 @@
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
 // Two mbarrier rings: B tiles are loaded once per K block and reused by all T time steps / input
 // planes, A tiles stream through a deeper ring.
-#include <cstdlib>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
@@ -774,10 +773,8 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
   // 3x3 stride-1 layers on spike inputs: load every haloed input tile once and realise the nine taps as
   // descriptor shifts (9x less activation traffic from L2), when the padded tiles waste < 30 % of the MMA rows
   bool reuse = false;
-  static const bool no_reuse_x2 = getenv("EAS_CONV_NO_REUSE_X2") != nullptr;   // experiment switches
-  static const bool no_n128 = getenv("EAS_CONV_NO_N128") != nullptr;
   // (every plane of every time step of a channel block must sit in the A ring at once: Tx * n_xsplit <= 6)
-  if (c->ksize == 3 && c->stride == 1 && (c->n_xsplit == 1 || (c->Tx == 1 && !no_reuse_x2)) && c->Cin >= 32) {
+  if (c->ksize == 3 && c->stride == 1 && (c->n_xsplit == 1 || c->Tx == 1) && c->Cin >= 32) {
     int th = 0, tw = 0;
     if (pick_reuse_tile(Ho, Wo, &th, &tw) >= 0.70) reuse = true, a.NB = 1, a.TH = th, a.TW = tw, a.TWp = tw + 2;
   }
@@ -788,7 +785,7 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
   // a single accumulator (Tx == 1: the ANN layers and the broadcast first spiking conv) leaves TMEM room for 128
   // (an MMA of N <= 128 costs the same 64 cycles, so half as many of them); kept to grids of >= 1 wave
   int BLOCK_N = (c->Cout <= 32 || c->Tx > 4) ? 32 : 64;
-  if (c->Tx == 1 && c->Cout > 64 && !no_n128) {
+  if (c->Tx == 1 && c->Cout > 64) {
     const int64_t t128 = eas_ceil_div(Wo, a.TW) * eas_ceil_div(Ho, a.TH) * eas_ceil_div(c->B, a.NB) *
                          eas_ceil_div(c->Cout, 128);
     if (t128 >= EAS_NUM_SMS) BLOCK_N = 128;
@@ -802,13 +799,11 @@ extern "C" int eas_conv_bn_plif_fwd(const eas_conv_cfg* c, const void* x, const 
   {
     const int per_kb = c->Tx * c->n_xsplit;
     const int SA_T = BLOCK_N > 64 ? 6 : (reuse ? 8 : 9);              // SmemLayout::SA of the kernel picked below
-    static const bool no_group = getenv("EAS_CONV_NO_AGROUP") != nullptr;
     EAS_REQUIRE(!reuse || per_kb <= SA_T, EAS_E_UNSUPPORTED);         // tap reuse keeps every plane of a channel block
-    a.a_group = (!reuse && per_kb <= SA_T && !no_group) ? 1 : 0;      // (more planes than slots: slot-by-slot loads)
+    a.a_group = (!reuse && per_kb <= SA_T) ? 1 : 0;      // (more planes than slots: slot-by-slot loads)
     a.sa_ring = per_kb <= SA_T ? SA_T / per_kb * per_kb : SA_T;       // whole groups, so that a group never wraps
   }
-  static const bool no_ksplit = getenv("EAS_CONV_NO_KSPLIT") != nullptr;
-  a.ksplit = (c->Tx == 1 && (reuse ? 9 * (int)eas_ceil_div(c->Cin, BK) : nkb_) >= 2 && !no_ksplit) ? 2 : 1;
+  a.ksplit = (c->Tx == 1 && (reuse ? 9 * (int)eas_ceil_div(c->Cin, BK) : nkb_) >= 2) ? 2 : 1;
   const int64_t n_tiles = (int64_t)a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
   EAS_REQUIRE(n_tiles > 0 && n_tiles < (1ll << 31), EAS_E_SHAPE);
   const int64_t grid = n_tiles < EAS_NUM_SMS ? n_tiles : EAS_NUM_SMS;   // persistent: one CTA per SM
