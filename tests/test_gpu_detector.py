@@ -160,3 +160,28 @@ def test_detector_s_vs_oracle_from_events(cuda):
     mx, bad = _rel_ok(got, want)
     print("SYOLOX-S predictions vs oracle: max rel err %.2e, beyond 5e-4: %.2e" % (mx, bad))
     assert bad <= 1e-3, (mx, bad)        # a near-threshold spike flip upstream would touch a few anchors
+
+
+def test_detector_m_batch_independence_and_graph_replay(cuda):
+    """Size-independent properties at the BASELINE model size (SYOLOX-M, 256x320, T=3): every window's predictions
+    are the same alone and inside a batch (windows are independent: what lets them shard over GPUs with no
+    collective), and the CUDA-graph replay used for low-latency inference reproduces the eager forward bit for bit."""
+    torch.manual_seed(7)
+    net = detector.build_syolox(0.67, 0.75, 2, 3).to(cuda).eval()
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.bias.data.fill_(0.6)
+    g = torch.Generator(cuda).manual_seed(1)
+    frames = torch.rand((1, 6, 2, 256, 320), device=cuda, generator=g) * 2
+    batch = net.detect_frames(frames)
+    assert batch.shape == (6, 32 * 40 + 16 * 20 + 8 * 10, 7) and bool(torch.isfinite(batch).all())
+    for i in (0, 3, 5):
+        alone = net.detect_frames(frames[:, i:i + 1].contiguous())
+        assert torch.equal(alone[0], batch[i]), "window %d depends on its batch" % i
+    rates = net.backbone.backbone(frames)
+    assert all(0.01 < float(v.float().mean()) < 0.9 for v in rates.values())
+    graph = fused.GraphedForward(net.detect_frames, frames)
+    frames2 = torch.rand((1, 6, 2, 256, 320), device=cuda, generator=g) * 2
+    want = net.detect_frames(frames2).clone()
+    assert torch.equal(graph(frames2), want)
+    assert not torch.equal(want, batch)
