@@ -211,7 +211,9 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_empty + 2);
   float* sBiasAll = reinterpret_cast<float*>(smem + L::OFF_BIAS);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role loops' ring / descriptor
+  // arithmetic on the uniform datapath (no R2UR moves in front of every UTCHMMA)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int Tacc = a.Tx;  // accumulators: one per distinct input time step
   constexpr int KS = TMAX == 1 ? 2 : 1;             // K-split accumulators of the single-time-step layers
   constexpr uint32_t kBufCols = KS * TMAX * BLOCK_N;   // one accumulator set
