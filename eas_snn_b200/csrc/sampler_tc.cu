@@ -272,7 +272,8 @@ sampler_tc_step_kernel(const StepArgs a, const TcGeo g, const uint8_t* __restric
   float* sh_b = reinterpret_cast<float*>(smem + OFF_MISC + 16);  // 12 floats
   const uint32_t sX0 = smem_u32(smem + OFF_X0), sX1 = smem_u32(smem + OFF_X1), sWB = smem_u32(smem);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (through a shuffle: provably warp-uniform, so the role loops' bookkeeping stays on the uniform datapath)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int QPR = g.QPR;
   const bool first = a.t == 0, last = a.t == a.Tm - 1;
   const int tm = a.Tm - 1 - a.t;  // newest micro-bin first (embedding.py:155-156)
