@@ -612,7 +612,8 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
 #pragma unroll
                   for (int j = 0; j < 16; ++j) {
                     const float xv = __fadd_rn(__fmul_rn(__uint_as_float(acc[t][j]), sUnscale[c16 * 16 + j]), sBias[c16 * 16 + j]);
-                    y[j] = fminf(fmaxf(xv * eas_sigmoid(xv), -65504.0f), 65504.0f);
+                    // SiLU = x / (1 + e^-x) on the SFU (ex2.approx + rcp.approx: ~2 ulp, far inside the 22-bit planes)
+                    y[j] = fminf(fmaxf(__fdividef(xv, 1.0f + __expf(-xv)), -65504.0f), 65504.0f);
                   }
                   if (nch == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((plane & 7) == 0)) {
                     uint32_t hi[8], lo[8];
