@@ -485,12 +485,16 @@ sampler_tc_step_kernel(const StepArgs a, const TcGeo g, const uint8_t* __restric
     Seg s;
     int gt = 0;
     while (it.next(s)) {
+      const int nq1 = (s.nrows + 4) * QPR;    // hidden-layer quads this segment needs
       for (int i = 0; i < s.nt1; ++i, ++gt) {
         const int buf = gt & 1, slot = gt % S1;
         const int f = i * TILE + q;
         const int r1 = f / QPR, m = f - r1 * QPR;
         const int y1 = s.ya - 2 + r1, x1 = s.xs - 2 + 4 * m;
-        const bool row_in = (unsigned)y1 < (unsigned)a.H;
+        // quads past nq1 pad the last tile: their windows reach X0 rows nobody wrote in this launch (stale shared
+        // memory), so they are forced to zero like the out-of-image ones -- otherwise garbage there can raise the
+        // fp16-range flag and send a perfectly good forward down the FP32 fall-back
+        const bool row_in = f < nq1 && (unsigned)y1 < (unsigned)a.H;
         mbar_wait(d1_full + buf, (gt >> 1) & 1);
         tc_fence_after();
         // D1 columns: [x*w_hi (16) | x_hi*w_lo (16)] for the input stack, then the same for the gate stack

@@ -90,7 +90,19 @@ def test_forward_dat_equals_forward_events(cuda):
     rec = torch.from_numpy(eas.pack_records(x, y, t, p)).to(cuda)
     ranges = torch.tensor([[off[b], off[b + 1]] for b in range(3)], dtype=torch.int64, device=cuda)
     d = [torch.from_numpy(a).to(cuda) for a in (x, y, t, p, off)]
+    from eas_snn_b200.psee import bin_dat
+    ha = bin_dat(rec, ranges, H, W, 4, dtype=torch.float32)
+    hb = eas.bin_events(*d, H, W, 4, dtype=torch.float32)
+    assert torch.equal(ha, hb), "fp32 histograms differ: %d bins" % int((ha != hb).sum())
     with torch.no_grad():
         a = m.forward_dat(rec, ranges, H, W)
         b = m.forward_events(*d, H, W)
-    assert torch.equal(a, b)
+        b2 = m(hb)
+    assert torch.equal(b, b2), "the sampler is not repeatable on one histogram: %d" % int((b != b2).sum())
+    if not torch.equal(a, b):        # diagnose: is one of them the FP32-pipe fall-back of algo="auto"?
+        m.algo = "fp32"
+        with torch.no_grad():
+            f = m(hb)
+        raise AssertionError("forward_dat vs forward_events: %d elements differ, max |d| %.3e; a == fp32 path: %s, "
+                             "b == fp32 path: %s" % (int((a != b).sum()), float((a - b).abs().max()),
+                                                     bool(torch.equal(a, f)), bool(torch.equal(b, f))))
