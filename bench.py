@@ -554,7 +554,7 @@ def run_ours(args):
         "kernel": "sampler_tc_step_kernel (dominant: %.0f%% of the step)" % (100.0 * t_smp / (t_smp + t_bin)),
         "bound": "tensor", "achieved": smp_flop_launch / smp_launch_ms / 1e9, "peak": tensor_peak, "unit": "TFLOP/s",
         "frac": smp_flop_launch / smp_launch_ms / 1e9 / tensor_peak,
-        "traffic": 372.3e6, "traffic_source": "profiles/r1_ncu_sampler_tc_e.txt (dram read 210.1 MB + write 162.2 MB per launch)",
+        "traffic": 368.7e6, "traffic_source": "profiles/r1_ncu_sampler_tc_f.txt (dram read 209.0 MB + write 159.7 MB per middle-step launch)",
         "peak_source": "measured cuBLAS bf16 burst (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
         "launch_ms": smp_launch_ms,
         "note": "algorithmic FLOPs (2400 per pixel-step, SURVEY 8d) over the dense bf16 GEMM peak; the kernel issues "
