@@ -229,6 +229,8 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    all_cpus = os.sched_getaffinity(0)
+    numa = parallel.bind_to_gpu_numa_node(local)    # before any pinned host buffer is allocated
     peak_gbs, peak_src, sm_max_mhz = load_peaks()
 
     torch.manual_seed(80)
@@ -596,7 +598,7 @@ def run_ours(args):
                     "ms_per_step": e2e_ms / args.steps, "pipeline": "3 streams (H2D / compute / D2H), 2 slots",
                     "input": "raw 8-byte PSEE .dat records + one record range per window (what the reference's loader "
                              "reads from disk); decode, binning and sampling on the GPU via forward_dat",
-                    "checksum": checksum},
+                    "checksum": checksum, "numa": numa},
             "gpu_launches": args.steps * (2 + 1 + 2 * TM),   # bin (2) + weight pack + Tm steps + Tm (no-op) fall-back launches
             "clocks": clk, "roofline": roofline}
     if frames is not None:
@@ -608,6 +610,7 @@ def run_ours(args):
     if train is not None:
         line["train"] = train
     if rank == 0:
+        os.sched_setaffinity(0, all_cpus)           # the CPU baseline gets every host core back
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
             if not args.no_backbone:

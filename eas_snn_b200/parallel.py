@@ -38,6 +38,45 @@ def init_distributed(backend: str | None = None):
     return rank, world, local
 
 
+def _parse_cpulist(text: str) -> set[int]:
+    cpus: set[int] = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(local_rank: int) -> dict:
+    """Pin this process (and so the first-touch placement of its pinned host buffers) to the NUMA node the GPU's
+    PCIe root hangs off.  With one process per GPU the host <-> device copies of N ranks otherwise fight over one
+    socket's memory and the inter-socket links; the staging path is the bound of the end-to-end number.  A no-op
+    (returns why) when the topology files are missing or there is a single node."""
+    info = {"bound": False}
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        info.update(pci=bus, node=node)
+        if node < 0:
+            info["why"] = "no NUMA affinity reported for the device"
+            return info
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            info["why"] = "single node or nothing to narrow"
+            return info
+        os.sched_setaffinity(0, cpus)
+        info.update(bound=True, cpus=len(cpus))
+    except (OSError, ValueError, AttributeError, RuntimeError) as e:   # topology not exposed (containers): stay put
+        info["why"] = "%s: %s" % (type(e).__name__, e)
+    return info
+
+
 def shard_range(n_windows: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous block of windows owned by ``rank`` (remainder spread over the first ranks)."""
     base, rem = divmod(n_windows, world)
