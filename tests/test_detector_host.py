@@ -1,0 +1,74 @@
+"""CPU: host-side logic of the whole-detector modules (no kernels run): the reference checkpoint layout loads key for
+key, the product refuses to run without CUDA, postprocess reproduces the reference's detections on its predictions."""
+import numpy as np
+import pytest
+import torch
+
+import eas_snn_b200 as eas
+from eas_snn_b200 import _lib, detector
+from helpers import detector_case, detector_sampler_kwargs, load_golden
+
+
+def _net():
+    z = load_golden("detector")
+    meta, sd, hist = detector_case(z)
+    emb = eas.AdaptiveRSNNEmbedding(**detector_sampler_kwargs(meta))
+    net = detector.build_syolox(meta["depth"], meta["width"], meta["num_classes"], meta["T"], embedding=emb,
+                                spike_fn=eas.ATan(meta["alpha"]))
+    return z, meta, sd, hist, net
+
+
+def test_reference_state_dict_loads_key_for_key():
+    z, meta, sd, hist, net = _net()
+    assert set(net.state_dict()) == set(sd)                       # same names, nothing extra, nothing missing
+    net.load_state_dict(sd, strict=True)
+    for k, v in net.state_dict().items():
+        assert v.shape == sd[k].shape, k
+    # the names the reference's optimizer grouping and checkpoints rely on (event_yolox_base.py:389-403)
+    for k in ("embedding.gate_conv.0.weight", "backbone.backbone.stem.0.conv.conv.weight",
+              "backbone.backbone.dark2.0.act.w", "backbone.lateral_conv0.bn.running_mean",
+              "backbone.C3_n4.m.0.conv2.conv.weight", "head.stems.2.conv.weight", "head.cls_preds.0.bias",
+              "head.obj_preds.1.weight"):
+        assert k in sd, k
+    assert sum(eas.is_spiking_neuron(m) for m in net.modules()) == sum(k.endswith("act.w") for k in sd)
+
+
+def test_syolox_s_and_m_parameter_counts_match_the_reference_readme():
+    # readme.md model table: e-yolox-s 8.94 M, e-yolox-m 25.28 M parameters (SURVEY 8c probe)
+    for (d, w, want) in ((0.33, 0.50, 8_938_167), (0.67, 0.75, 25_281_000)):
+        emb = eas.AdaptiveRSNNEmbedding(kernel_size=5, depth=2, nb_steps=4, thresh=1, vreset=0)
+        n = sum(p.numel() for p in detector.build_syolox(d, w, 2, 3, embedding=emb).parameters())
+        assert abs(n - want) <= 1000, (d, w, n)
+
+
+def test_detector_refuses_cpu_tensors_and_training_mode():
+    z, meta, sd, hist, net = _net()
+    net.eval()
+    with pytest.raises(_lib.EasError):
+        net(hist)                                  # no CPU fallback anywhere on the path
+    net.train()
+    with pytest.raises(RuntimeError):
+        net(hist)
+
+
+def test_pad_frames_and_postprocess_match_the_reference_detections():
+    z, meta, *_ = _net()
+    f = torch.arange(2 * 3 * 5 * 7, dtype=torch.float32).view(1, 2, 3, 5, 7)
+    p = detector.pad_frames(f)
+    assert p.shape == (1, 2, 3, 32, 32) and torch.equal(p[..., :5, :7], f) and float(p.sum()) == float(f.sum())
+    assert detector.pad_frames(p) is p
+    pred = torch.from_numpy(z["pred"])
+    keep = pred.clone()
+    dets = detector.postprocess(pred, meta["num_classes"], meta["conf_thre"], meta["nms_thre"])
+    assert torch.equal(pred, keep)                 # unlike boxes.py:33-41 the input is left alone
+    n = 0
+    for i, d in enumerate(dets):
+        want = torch.from_numpy(z["dets/%d" % i])
+        got = torch.zeros((0, 7)) if d is None else d
+        assert got.shape == want.shape and torch.allclose(got, want, rtol=0, atol=1e-5), i
+        n += len(want)
+    assert n >= 4
+    # class-agnostic branch and the empty case
+    ag = detector.postprocess(pred, meta["num_classes"], meta["conf_thre"], meta["nms_thre"], class_agnostic=True)
+    assert all(a is not None and len(a) <= len(d) for a, d in zip(ag, dets))
+    assert detector.postprocess(pred, meta["num_classes"], conf_thre=2.0) == [None, None]

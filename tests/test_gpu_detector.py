@@ -185,3 +185,34 @@ def test_detector_m_batch_independence_and_graph_replay(cuda):
     want = net.detect_frames(frames2).clone()
     assert torch.equal(graph(frames2), want)
     assert not torch.equal(want, batch)
+
+
+def test_detector_from_events_with_empty_and_single_event_windows(cuda):
+    """Edge cases the loaders produce (gen1.py:335-337, 356-358: no events -> zero histograms): an empty window and a
+    one-event window (tw == 0 -> all bins empty) between two normal ones, raw events -> predictions, vs the oracle."""
+    from oracle import binning as obin, detector as odet, sampler as osamp
+    from oracle.plif import ATan as OATan
+    from eas_snn_b200 import synth
+    z, meta, net, _ = _golden_model(cuda)
+    H, W = 64, 96
+    rng = np.random.default_rng(5)
+    wins = [synth.make_window(rng, 6000, H, W), tuple(np.zeros(0, dt) for dt in (np.int16, np.int16, np.int64, np.uint8)),
+            tuple(np.asarray(v, dt) for v, dt in (([3], np.int16), ([2], np.int16), ([1000], np.int64), ([1], np.uint8))),
+            synth.make_window(rng, 9000, H, W)]
+    x, y, t, p = (np.concatenate([w[i] for w in wins]) for i in range(4))
+    off = np.cumsum([0] + [len(w[0]) for w in wins]).astype(np.int64)
+    onet = odet.OracleSpikingYOLOX(meta["depth"], meta["width"], meta["num_classes"], meta["T"],
+                                   embedding=osamp.OracleSampler(**detector_sampler_kwargs(meta)),
+                                   spike_fn=OATan(meta["alpha"]))
+    onet.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}, strict=True)
+    onet.eval()
+    hist = torch.from_numpy(obin.micro_sum_batch(x, y, t, p, off, H, W, meta["Tm"])).float()
+    assert not hist[1].any() and not hist[2].any()
+    with torch.no_grad():
+        want = onet(hist)
+    got = net.forward_events(*(torch.from_numpy(a).to(cuda) for a in (x, y, t, p, off)), H, W)
+    assert got.shape == want.shape == (4, 126, 7)
+    mx, bad = _rel_ok(got, want)
+    print("edge windows: max rel err %.2e" % mx)
+    assert bad == 0.0, mx
+    assert torch.equal(got[1], got[2])             # both windows are "no events" to the histogram
