@@ -60,3 +60,49 @@ extern "C" int eas_rvt_event_sum(const uint8_t* repr, int64_t n, int nb, int H, 
   EAS_LAUNCH_CHECK();
   return EAS_OK;
 }
+
+// (f-4) SpikeCountEmbedding (yolox/models/embedding.py:9-24): the micro-bin histograms of a window summed over the Tm
+// micro-bins, `events.transpose(0, 1).sum(axis=0)`: hist [n][Tm][P] (f32 or i32 counts) -> out f32 [n][P], P = 2*H*W.
+// HBM bound: 4*Tm bytes read + 4 written per element; 4 elements per thread, 16 B loads.
+namespace {
+
+template <bool kInt>
+__global__ void __launch_bounds__(256)
+hist_time_sum_kernel(const float* __restrict__ hist, float* __restrict__ out, int64_t n, int Tm, int64_t P) {
+  const int64_t P4 = P >> 2;                       // P % 4 == 0 checked by the caller
+  const int64_t total = n * P4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / P4, q = i - b * P4;
+    const float4* src = reinterpret_cast<const float4*>(hist + b * Tm * P) + q;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < Tm; ++t) {
+      float4 v = ld_stream_f4(src + (int64_t)t * P4);
+      if (kInt) {
+        v.x = (float)__float_as_int(v.x), v.y = (float)__float_as_int(v.y);
+        v.z = (float)__float_as_int(v.z), v.w = (float)__float_as_int(v.w);
+      }
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;     // t ascending, like torch.sum over dim 0
+    }
+    st_stream_f4(reinterpret_cast<float4*>(out + b * P) + q, acc);
+  }
+}
+
+}  // namespace
+
+extern "C" int eas_hist_time_sum(const void* hist, int in_dtype, int64_t n, int Tm, int64_t plane_elems, float* out,
+                                 void* stream) {
+  EAS_REQUIRE(n >= 0 && Tm >= 1 && plane_elems > 0 && plane_elems % 4 == 0, EAS_E_SHAPE);
+  EAS_REQUIRE(in_dtype == EAS_F32 || in_dtype == EAS_I32, EAS_E_UNSUPPORTED);
+  if (n == 0) return EAS_OK;
+  EAS_REQUIRE(hist && out, EAS_E_NULL);
+  EAS_REQUIRE((uintptr_t)hist % 16 == 0 && (uintptr_t)out % 16 == 0, EAS_E_ALIGN);
+  const int64_t total = n * (plane_elems / 4);
+  int64_t g = (total + 255) / 256;
+  if (g > 8 * EAS_NUM_SMS) g = 8 * EAS_NUM_SMS;
+  if (in_dtype == EAS_I32)
+    hist_time_sum_kernel<true><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>((const float*)hist, out, n, Tm, plane_elems);
+  else
+    hist_time_sum_kernel<false><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>((const float*)hist, out, n, Tm, plane_elems);
+  EAS_LAUNCH_CHECK();
+  return EAS_OK;
+}

@@ -197,3 +197,39 @@ class AdaptiveRSNNEmbedding(nn.Module):
         from .psee import bin_dat
         hist = bin_dat(records, ranges, H, W, self.nb_steps, strategy=strategy, dtype=torch.float32)
         return self.forward(hist)
+
+
+class SpikeCountEmbedding(nn.Module):
+    """``SpikeCountEmbedding`` (yolox/models/embedding.py:9-24; ``embedding: count`` in event_yolox_base.py:160): the
+    micro-bin histograms of each window summed over the Tm micro-bins -- the plain event-count frame the adaptive
+    sampler is compared against.  ``forward(events)`` takes what the reference takes: 5-D ``[B, Tm, 2, H, W]`` ->
+    ``[B, 2, H, W]``, 6-D ``[B, Tl, Tm, 2, H, W]`` -> ``[B*Tl, 2, H, W]``, and < 5-D (a single frame) ->
+    ``nb_steps`` copies summed = ``nb_steps * events``.  No parameters."""
+
+    def __init__(self, nb_steps):
+        super().__init__()
+        self.nb_steps = nb_steps
+
+    def forward(self, events: torch.Tensor) -> torch.Tensor:
+        _lib.require_cuda(events)
+        if events.dim() < 5:                       # embedding.py:15-16: broadcast over nb_steps, then sum
+            return events.float() * float(self.nb_steps)
+        ev = events.flatten(end_dim=-5) if events.dim() > 5 else events
+        if ev.dtype not in (torch.float32, torch.int32):
+            ev = ev.float()
+        ev = ev.contiguous()
+        n, Tm = ev.shape[0], ev.shape[1]
+        plane = ev[0, 0].numel()
+        if plane % 4 != 0:
+            return ev.float().sum(dim=1)           # ragged planes: not worth a kernel
+        out = torch.empty(ev.shape[:1] + ev.shape[2:], dtype=torch.float32, device=ev.device)
+        in_dtype = _lib.EAS_I32 if ev.dtype == torch.int32 else _lib.EAS_F32
+        with torch.cuda.device(ev.device):
+            rc = _lib.lib().eas_hist_time_sum(_lib.ptr(ev), in_dtype, n, Tm, plane, _lib.ptr(out), _lib.stream_ptr())
+        _lib.check(rc, "eas_hist_time_sum")
+        return out
+
+    def forward_events(self, x, y, t, p, offsets, H: int, W: int):
+        """Raw windows -> count frames ``[B, 2, H, W]``: binning (gen1.py:313-360) + the sum over micro-bins."""
+        from .binning import bin_events
+        return self.forward(bin_events(x, y, t, p, offsets, H, W, self.nb_steps))

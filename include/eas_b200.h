@@ -254,6 +254,11 @@ int eas_yolox_decode(const float* preds, int64_t n_images, int H, int W, int n_c
  * borders; the stem conv then runs as a 1x1 conv with K = 80 through eas_conv_bn_plif_fwd. */
 int eas_focus_im2col(const float* frames, int64_t n_images, int H, int W, void* out, int64_t out_plane_stride,
                      void* stream);
+/* (f-4) SpikeCountEmbedding.forward, yolox/models/embedding.py:9-24: micro-bin histograms summed over the Tm
+ * micro-bins (`events.transpose(0, 1).sum(axis=0)`).  hist: [n][Tm][plane_elems] f32 or i32 counts (in_dtype),
+ * out: f32 [n][plane_elems]; plane_elems = 2*H*W, a multiple of 4. */
+int eas_hist_time_sum(const void* hist, int in_dtype, int64_t n, int Tm, int64_t plane_elems, float* out,
+                      void* stream);
 
 #ifdef __cplusplus
 }

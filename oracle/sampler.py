@@ -167,3 +167,16 @@ class OracleSampler(nn.Module):
         return sampler_forward(events, iw, ib, gw, gb, Ts=self.Ts, thresh=self.thresh, vreset=self.vreset,
                                readout=self.readout, spike_attach=self.spike_attach,
                                write_zero=self.write_zero, use_abs=self.abs)
+
+
+def spike_count(events: torch.Tensor, nb_steps: int) -> torch.Tensor:
+    """``SpikeCountEmbedding.forward`` (``yolox/models/embedding.py:14-24``): micro-bin histograms summed over the
+    micro-bin axis; a single frame (< 5-D) is broadcast ``nb_steps`` times first (:15-16).  Pinned by
+    ``tests/golden/count.npz`` (the reference class run on 5-D, 6-D and 4-D inputs)."""
+    if events.dim() < 5:
+        events = events.unsqueeze(0).expand((nb_steps,) + tuple(events.shape))
+    elif events.dim() > 5:
+        events = events.flatten(end_dim=-5).transpose(0, 1)
+    else:
+        events = events.transpose(0, 1)
+    return events.sum(dim=0)

@@ -2,7 +2,7 @@
 
     python tests/golden/make_golden.py          # needs /root/reference (read-only)
 
-Outputs (small, committed): tests/golden/binning.npz, sampler.npz, backbone.npz, psee.npz, detector.npz.
+Outputs (small, committed): tests/golden/binning.npz, sampler.npz, backbone.npz, psee.npz, detector.npz, count.npz.
 The reference is imported in place through ``oracle/ref_loader.py``; nothing is copied from it.
 ``/root/reference`` does not exist on the GPU box, so tests only ever read the .npz files.
 """
@@ -124,6 +124,19 @@ def make_sampler(emb, act):
     out["names"] = np.array(names)
     np.savez_compressed(os.path.join(HERE, "sampler.npz"), **out)
     print("sampler.npz:", len(names), "cases")
+
+
+def make_count(emb):
+    """(f-4) The reference's SpikeCountEmbedding (embedding.py:9-24) on 5-D, 6-D and single-frame inputs."""
+    m = emb.SpikeCountEmbedding(4)
+    g = torch.Generator().manual_seed(21)
+    x5 = torch.poisson(torch.full((3, 4, 2, 24, 32), 0.8), generator=g)
+    x6 = torch.poisson(torch.full((2, 2, 4, 2, 24, 32), 0.8), generator=g)
+    x4 = torch.poisson(torch.full((3, 2, 24, 32), 0.8), generator=g)
+    out = {"x5": x5.numpy().astype(np.uint8), "y5": m(x5).numpy(), "x6": x6.numpy().astype(np.uint8),
+           "y6": m(x6).numpy(), "x4": x4.numpy().astype(np.uint8), "y4": m(x4).numpy()}
+    np.savez_compressed(os.path.join(HERE, "count.npz"), **out)
+    print("count.npz:", {k: v.shape for k, v in out.items() if k.startswith("y")})
 
 
 def make_backbone():
@@ -314,6 +327,7 @@ if __name__ == "__main__":
         sys.exit(0)
     make_binning(gen1)
     make_sampler(emb, act)
+    make_count(emb)
     make_backbone()
     make_psee(gen1)
     make_detector()

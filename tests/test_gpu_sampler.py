@@ -223,3 +223,22 @@ def test_1mpx_rvt_layout_event_sum_and_sampler(cuda):
         print(algo, msg)
         assert ok, algo + ": " + msg
     assert (want != 0).float().mean().item() > 0.01
+
+
+def test_spike_count_embedding_golden_and_events(cuda):
+    """(f-4) SpikeCountEmbedding: the reference class's outputs (tests/golden/count.npz), int32 histograms, and
+    raw events -> count frames = total events per pixel and polarity inside the Tm micro-bins (bit-exact)."""
+    from helpers import load_golden
+    from oracle import binning as ob
+    z = load_golden("count")
+    m = eas.SpikeCountEmbedding(4)
+    assert not list(m.parameters())
+    for k in ("5", "6", "4"):
+        x = torch.from_numpy(z["x" + k].astype(np.float32)).to(cuda)
+        assert torch.equal(m(x).cpu(), torch.from_numpy(z["y" + k])), k
+    xi = torch.from_numpy(z["x5"].astype(np.int32)).to(cuda)
+    assert torch.equal(m(xi).cpu(), torch.from_numpy(z["y5"]))
+    x, y, t, p, off = synth.make_batch(4, 5, 240, 304, 2e4, 6e4)
+    got = m.forward_events(*(torch.from_numpy(a).to(cuda) for a in (x, y, t, p, off)), 240, 304)
+    want = ob.micro_sum_batch(x, y, t, p, off, 240, 304, 4).sum(axis=1)
+    assert got.shape == (5, 2, 240, 304) and np.array_equal(got.cpu().numpy(), want.astype(np.float32))

@@ -114,3 +114,10 @@ def test_detector_golden():
         raw = net.head(pyr, decode=False)
     assert torch.allclose(pred, torch.from_numpy(z["pred"]), rtol=1e-5, atol=1e-5)
     assert torch.allclose(raw, torch.from_numpy(z["raw"]), rtol=1e-5, atol=1e-5)
+
+
+def test_spike_count_golden():
+    z = load_golden("count")
+    for k in ("5", "6", "4"):
+        x = torch.from_numpy(z["x" + k].astype(np.float32))
+        assert torch.equal(sampler.spike_count(x, 4), torch.from_numpy(z["y" + k])), k
