@@ -495,13 +495,14 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       }
       const bool res_vec = a.residual != nullptr && valid && a.out_mode == EAS_CONV_OUT_SPIKES &&
                            (a.res_ld & 7) == 0 && (n0 & 7) == 0;
-      constexpr int RT = TMAX == 4 ? 4 : 1;   // time steps whose shortcut is prefetched (T <= 4 layers)
+      constexpr bool kPrefRes = TMAX == 3 || TMAX == 4;   // the shortcut of every time step is prefetched (T <= 4 layers)
+      constexpr int RT = kPrefRes ? TMAX : 1;
       uint4 rres[RT][2];
       auto load_res = [&](int c16, uint4 (&r)[RT][2]) {
         const int ch0 = n0 + c16 * 16;
 #pragma unroll
         for (int t = 0; t < RT; ++t) {
-          if (TMAX == 4 && t < a.T && res_vec && ch0 + 16 <= a.Cout) {
+          if (kPrefRes && t < a.T && res_vec && ch0 + 16 <= a.Cout) {
             const uint4* rp = reinterpret_cast<const uint4*>(a.residual + ((int64_t)t * step + pix) * a.res_ld + ch0);
             r[t][0] = ld_stream_u4(rp), r[t][1] = ld_stream_u4(rp + 1);
           }
@@ -569,7 +570,7 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
               }
               __half* dst = outp + ((int64_t)t * step + pix) * a.out_ld + ch0;
               if (a.residual) {  // SEW add: y = spikes + x (small integers, exact in fp16)
-                if (TMAX == 4 && res_vec && nch == 16) {
+                if (kPrefRes && res_vec && nch == 16) {
                   const __half* rb0 = reinterpret_cast<const __half*>(&rres[t < RT ? t : 0][0]);
                   const __half* rb1 = reinterpret_cast<const __half*>(&rres[t < RT ? t : 0][1]);
 #pragma unroll
@@ -712,6 +713,9 @@ int launch_conv_t(int Tacc, const CUtensorMap& xmap, const CUtensorMap& wmap, co
                   cudaStream_t st) {
   // two accumulator sets of Tacc x BLOCK_N columns must fit the 512 TMEM columns
   if (Tacc <= 1) return launch_conv<BLOCK_N, 1, BK>(xmap, wmap, a, grid, st);
+  // T = 3 is the reference configuration: its own instantiation keeps 16 accumulator + 8 shortcut registers less live
+  // than the T <= 4 one (the epilogue sits at the 168-register cap of a 384-thread CTA, and spills cost more than MMAs)
+  if (Tacc <= 3) return launch_conv<BLOCK_N, 3, BK>(xmap, wmap, a, grid, st);
   if (Tacc <= 4) return launch_conv<BLOCK_N, 4, BK>(xmap, wmap, a, grid, st);
   if constexpr (BLOCK_N <= 32) return launch_conv<BLOCK_N, 8, BK>(xmap, wmap, a, grid, st);
   return EAS_E_UNSUPPORTED;
@@ -721,6 +725,7 @@ template <int BLOCK_N>
 int launch_conv_reuse(int Tacc, const CUtensorMap& xmap, const CUtensorMap& wmap, const ConvArgs& a, int64_t grid,
                       cudaStream_t st) {
   if (Tacc <= 1) return launch_conv<BLOCK_N, 1, 32, true>(xmap, wmap, a, grid, st);
+  if (Tacc <= 3) return launch_conv<BLOCK_N, 3, 32, true>(xmap, wmap, a, grid, st);
   if (Tacc <= 4) return launch_conv<BLOCK_N, 4, 32, true>(xmap, wmap, a, grid, st);
   if constexpr (BLOCK_N <= 32) return launch_conv<BLOCK_N, 8, 32, true>(xmap, wmap, a, grid, st);
   return EAS_E_UNSUPPORTED;
