@@ -75,6 +75,8 @@ SIGNATURES = {
     "eas_time_mean_planes": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, C.c_int, _P, C.c_int, C.c_int64, _P]),
     "eas_upsample2x_planes": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _P,
                                         C.c_int, C.c_int64, _P]),
+    "eas_letterbox_bilinear": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, _P, C.c_int, C.c_int, _P]),
     "eas_hist_time_sum": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, C.c_int64, _P, _P]),
     "eas_focus_im2col": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, C.c_int64, _P]),
     "eas_yolox_decode": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P,

@@ -90,3 +90,56 @@ def rvt_event_sum(repr_u8: torch.Tensor, n_bins: int = 10) -> torch.Tensor:
         rc = _lib.lib().eas_rvt_event_sum(_lib.ptr(repr_u8), n, n_bins, H, W, _lib.ptr(out), _lib.stream_ptr())
     _lib.check(rc, "eas_rvt_event_sum")
     return out
+
+
+_TAPS: dict = {}
+
+
+def _linear_taps(n_out: int, n_in: int, device):
+    """cv2.INTER_LINEAR taps of one axis (half-pixel centres in float32, taps clamped to the image): source index
+    and float32 weight of the second tap, cached per (n_out, n_in, device)."""
+    key = (n_out, n_in, str(device))
+    if key not in _TAPS:
+        scale = 1.0 / (float(n_out) / float(n_in))
+        f = ((np.arange(n_out, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+        i0 = np.floor(f).astype(np.int64)
+        f = (f - i0.astype(np.float32)).astype(np.float32)
+        f[i0 < 0] = 0.0
+        i0[i0 < 0] = 0
+        f[i0 >= n_in - 1] = 0.0
+        i0[i0 >= n_in - 1] = n_in - 1
+        _TAPS[key] = (torch.from_numpy(i0.astype(np.int32)).to(device), torch.from_numpy(f).to(device))
+    return _TAPS[key]
+
+
+def letterbox_frames(frames: torch.Tensor, size, letterbox: bool = True, center: bool = False) -> torch.Tensor:
+    """Letterbox + bilinear resize of micro-frames on the GPU: what ``GEN1Dataset.get_random_data(random=False)``
+    (``yolox/data/datasets/gen1.py:433-483``) does on the host with ``cv2.resize(INTER_LINEAR)`` -- every
+    ``[ih, iw]`` plane of ``frames [..., ih, iw]`` (fp32 or int32 counts) scaled by ``min(w/iw, h/ih)``, pasted
+    top-left (``center``: centred) into a zero ``[h, w]`` canvas; ``letterbox=False`` stretches to ``(h, w)``.
+    Counts become fractional, so this sits outside the bit-exact histogram contract (optional stage)."""
+    _lib.require_cuda(frames)
+    h, w = int(size[0]), int(size[1])
+    ih, iw = frames.shape[-2:]
+    if frames.dtype not in (torch.float32, torch.int32):
+        frames = frames.float()
+    frames = frames.contiguous()
+    if letterbox:
+        scale = min(w / iw, h / ih)
+        nw, nh = int(iw * scale), int(ih * scale)
+        dy, dx = ((h - nh) // 2, (w - nw) // 2) if center else (0, 0)
+    else:
+        nh, nw, dy, dx = h, w, 0, 0
+    if w % 4 != 0:
+        raise ValueError("letterbox_frames: the output width must be a multiple of 4")
+    x0, fx = _linear_taps(nw, iw, frames.device)
+    y0, fy = _linear_taps(nh, ih, frames.device)
+    out = torch.empty(frames.shape[:-2] + (h, w), dtype=torch.float32, device=frames.device)
+    n_planes = frames.numel() // (ih * iw)
+    in_dtype = _lib.EAS_I32 if frames.dtype == torch.int32 else _lib.EAS_F32
+    with torch.cuda.device(frames.device):
+        rc = _lib.lib().eas_letterbox_bilinear(_lib.ptr(frames), in_dtype, n_planes, ih, iw, _lib.ptr(x0), _lib.ptr(fx),
+                                               _lib.ptr(y0), _lib.ptr(fy), nh, nw, dy, dx, _lib.ptr(out), h, w,
+                                               _lib.stream_ptr())
+    _lib.check(rc, "eas_letterbox_bilinear")
+    return out

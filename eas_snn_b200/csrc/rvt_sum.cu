@@ -106,3 +106,76 @@ extern "C" int eas_hist_time_sum(const void* hist, int in_dtype, int64_t n, int 
   EAS_LAUNCH_CHECK();
   return EAS_OK;
 }
+
+// (f-3) Letterbox + bilinear resize of micro-frames: GEN1Dataset.get_random_data with random=False
+// (yolox/data/datasets/gen1.py:433-483): cv2.resize(INTER_LINEAR) of every [ih][iw] plane to [nh][nw], pasted at
+// (dy, dx) into a zero canvas [oh][ow].  The tap tables (source index and float32 weight per output column / row:
+// cv2's half-pixel rule, built on the host) make the kernel a pure gather: 4 output pixels per thread, 16 B stores;
+// HBM bound on the write (4 B per output pixel).
+namespace {
+
+template <bool kInt>
+__global__ void __launch_bounds__(256)
+letterbox_bilinear_kernel(const float* __restrict__ in, int64_t n_planes, int ih, int iw, const int* __restrict__ x0t,
+                          const float* __restrict__ fxt, const int* __restrict__ y0t, const float* __restrict__ fyt,
+                          int nh, int nw, int dy, int dx, float* __restrict__ out, int oh, int ow) {
+  const int ow4 = ow >> 2;                               // ow % 4 == 0 checked by the caller
+  const int64_t total = n_planes * oh * ow4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % ow4);
+    int64_t r = i / ow4;
+    const int oy = (int)(r % oh);
+    const int64_t pl = r / oh;
+    float4 res = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int y = oy - dy;
+    if (y >= 0 && y < nh) {
+      const int ya = y0t[y], yb = min(ya + 1, ih - 1);
+      const float fy = fyt[y], gy = 1.0f - fy;
+      const float* ra = in + (pl * ih + ya) * iw;
+      const float* rb = in + (pl * ih + yb) * iw;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int x = q * 4 + j - dx;
+        v[j] = 0.0f;
+        if (x >= 0 && x < nw) {
+          const int xa = x0t[x], xb = min(xa + 1, iw - 1);
+          const float fx = fxt[x], gx = 1.0f - fx;
+          float a0 = ra[xa], a1 = ra[xb], b0 = rb[xa], b1 = rb[xb];
+          if (kInt) {
+            a0 = (float)__float_as_int(a0), a1 = (float)__float_as_int(a1);
+            b0 = (float)__float_as_int(b0), b1 = (float)__float_as_int(b1);
+          }
+          // horizontal pass then vertical pass, like cv2 (weights are float32 there too)
+          v[j] = (a0 * gx + a1 * fx) * gy + (b0 * gx + b1 * fx) * fy;
+        }
+      }
+      res = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    st_stream_f4(reinterpret_cast<float4*>(out + (pl * oh + oy) * ow) + q, res);
+  }
+}
+
+}  // namespace
+
+extern "C" int eas_letterbox_bilinear(const void* in, int in_dtype, int64_t n_planes, int ih, int iw, const int32_t* x0,
+                                      const float* fx, const int32_t* y0, const float* fy, int nh, int nw, int dy,
+                                      int dx, float* out, int oh, int ow, void* stream) {
+  EAS_REQUIRE(n_planes >= 0 && ih >= 1 && iw >= 1 && nh >= 1 && nw >= 1 && oh >= 1 && ow >= 4 && ow % 4 == 0, EAS_E_SHAPE);
+  EAS_REQUIRE(dy >= 0 && dx >= 0 && dy + nh <= oh && dx + nw <= ow, EAS_E_SHAPE);
+  EAS_REQUIRE(in_dtype == EAS_F32 || in_dtype == EAS_I32, EAS_E_UNSUPPORTED);
+  if (n_planes == 0) return EAS_OK;
+  EAS_REQUIRE(in && out && x0 && fx && y0 && fy, EAS_E_NULL);
+  EAS_REQUIRE((uintptr_t)out % 16 == 0, EAS_E_ALIGN);
+  const int64_t total = n_planes * oh * (ow / 4);
+  int64_t g = (total + 255) / 256;
+  if (g > 8 * EAS_NUM_SMS) g = 8 * EAS_NUM_SMS;
+  if (in_dtype == EAS_I32)
+    letterbox_bilinear_kernel<true><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(
+        (const float*)in, n_planes, ih, iw, x0, fx, y0, fy, nh, nw, dy, dx, out, oh, ow);
+  else
+    letterbox_bilinear_kernel<false><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(
+        (const float*)in, n_planes, ih, iw, x0, fx, y0, fy, nh, nw, dy, dx, out, oh, ow);
+  EAS_LAUNCH_CHECK();
+  return EAS_OK;
+}

@@ -259,6 +259,14 @@ int eas_focus_im2col(const float* frames, int64_t n_images, int H, int W, void* 
  * out: f32 [n][plane_elems]; plane_elems = 2*H*W, a multiple of 4. */
 int eas_hist_time_sum(const void* hist, int in_dtype, int64_t n, int Tm, int64_t plane_elems, float* out,
                       void* stream);
+/* (f-3) Letterbox + bilinear resize of micro-frames: GEN1Dataset.get_random_data(random=False),
+ * yolox/data/datasets/gen1.py:433-483 (cv2.resize INTER_LINEAR of every plane to [nh][nw], pasted at (dy, dx) into a
+ * zero canvas [oh][ow]).  in: [n_planes][ih][iw] f32 or i32 counts; x0 / fx ([nw]) and y0 / fy ([nh]): source tap and
+ * float32 weight of the second tap per output column / row (cv2's half-pixel rule; the second tap is min(tap+1, last));
+ * out: f32 [n_planes][oh][ow], ow % 4 == 0, written completely. */
+int eas_letterbox_bilinear(const void* in, int in_dtype, int64_t n_planes, int ih, int iw, const int32_t* x0,
+                           const float* fx, const int32_t* y0, const float* fy, int nh, int nw, int dy, int dx,
+                           float* out, int oh, int ow, void* stream);
 
 #ifdef __cplusplus
 }

@@ -30,4 +30,7 @@ Parity pinning
   by ``tests/golden/detector.npz``: the reference's own ``EventExp.get_model()`` (use_spike True,
   tiny width) run through ``oracle/sj_shim`` from histograms to decoded predictions and its
   ``postprocess`` detections.
+* ``oracle.letterbox`` follows ``yolox/data/datasets/gen1.py:423-483`` (letterbox geometry + paste) and restates
+  ``cv2.resize(INTER_LINEAR)`` (third-party opencv-python, present in the authoring container)      -- PINNED
+  by ``tests/golden/letterbox.npz``: the reference method (and so cv2) run on synthetic frames; identical in float64.
 """

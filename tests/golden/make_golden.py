@@ -2,7 +2,7 @@
 
     python tests/golden/make_golden.py          # needs /root/reference (read-only)
 
-Outputs (small, committed): tests/golden/binning.npz, sampler.npz, backbone.npz, psee.npz, detector.npz, count.npz.
+Outputs (small, committed): tests/golden/binning.npz, sampler.npz, backbone.npz, psee.npz, detector.npz, count.npz, letterbox.npz.
 The reference is imported in place through ``oracle/ref_loader.py``; nothing is copied from it.
 ``/root/reference`` does not exist on the GPU box, so tests only ever read the .npz files.
 """
@@ -137,6 +137,36 @@ def make_count(emb):
            "y6": m(x6).numpy(), "x4": x4.numpy().astype(np.uint8), "y4": m(x4).numpy()}
     np.savez_compressed(os.path.join(HERE, "count.npz"), **out)
     print("count.npz:", {k: v.shape for k, v in out.items() if k.startswith("y")})
+
+
+LETTERBOX_CASES = [  # ih, iw, h, w, center, letterbox
+    (240, 304, 640, 640, False, True),     # the reference's default input_size
+    (240, 304, 256, 320, False, True),
+    (240, 304, 512, 640, True, True),
+    (64, 96, 48, 72, True, True),          # down-scaling
+    (37, 53, 128, 96, False, True),        # odd source size
+    (240, 304, 320, 320, False, False),    # no letterbox: stretched
+    (40, 48, 40, 48, False, True),         # identity
+]
+
+
+def make_letterbox(gen1):
+    """(f-3) The reference's own GEN1Dataset.get_random_data(random=False) (gen1.py:433-483; cv2.resize INTER_LINEAR
+    per micro-frame + paste into a zero canvas) on synthetic count frames.  Inputs are regenerated from the seed by the
+    tests; the fixture keeps a strided sample of every output plus its checksum."""
+    out = {}
+    for i, (ih, iw, h, w, center, lb) in enumerate(LETTERBOX_CASES):
+        rng = np.random.default_rng(100 + i)
+        fr = rng.poisson(0.7, (3, 2, ih, iw)).astype(np.float64)
+        ds = object.__new__(gen1.GEN1Dataset)
+        ds.letterbox_image = lb
+        ref, _ = ds.get_random_data(fr, np.zeros((0, 5)), (h, w), random=False, center=center)
+        assert ref.shape == (3, 2, h, w)
+        out["%d/cfg" % i] = np.array([ih, iw, h, w, int(center), int(lb)], np.int64)
+        out["%d/sample" % i] = ref[:, :, ::3, ::5].astype(np.float64)
+        out["%d/sum" % i] = np.array([ref.sum(), np.abs(ref).max(), float((ref != 0).mean())])
+    np.savez_compressed(os.path.join(HERE, "letterbox.npz"), **out)
+    print("letterbox.npz:", len(LETTERBOX_CASES), "cases")
 
 
 def make_backbone():
@@ -321,6 +351,9 @@ if __name__ == "__main__":
         make_psee(gen1)
         print("psee.npz", os.path.getsize(os.path.join(HERE, "psee.npz")) // 1024, "KiB")
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "letterbox":
+        make_letterbox(gen1)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "detector":
         make_detector()
         print("detector.npz", os.path.getsize(os.path.join(HERE, "detector.npz")) // 1024, "KiB")
@@ -328,6 +361,7 @@ if __name__ == "__main__":
     make_binning(gen1)
     make_sampler(emb, act)
     make_count(emb)
+    make_letterbox(gen1)
     make_backbone()
     make_psee(gen1)
     make_detector()

@@ -60,3 +60,14 @@ def detector_sampler_kwargs(meta):
                 write_zero=meta["write_zero"], abs=meta["abs"], depth=meta["emb_depth"], nb_steps=meta["Tm"],
                 vreset=meta["vreset"], thresh=meta["thresh"], embedding="arsnn", Ts=meta["Ts"],
                 spike_attach=meta["spike_attach"])
+
+
+def letterbox_cases(z):
+    """(cfg tuple, regenerated input frames, golden strided sample, golden [sum, max, nonzero fraction]) per case."""
+    i = 0
+    while "%d/cfg" % i in z.files:
+        ih, iw, h, w, center, lb = (int(v) for v in z["%d/cfg" % i])
+        rng = np.random.default_rng(100 + i)
+        fr = rng.poisson(0.7, (3, 2, ih, iw)).astype(np.float64)
+        yield (ih, iw, h, w, bool(center), bool(lb)), fr, z["%d/sample" % i], z["%d/sum" % i]
+        i += 1

@@ -95,3 +95,24 @@ def test_out_of_range_events_are_ignored(cuda):
     for s in ("reds", "tiles"):
         got = eas.bin_events(*_dev((x, y, t, p, off), cuda), 8, 8, 4, strategy=s)
         assert int(got.sum()) == 2 and int(got[0, 0, 1, 0, 0]) == 1 and int(got[0, 1, 0, 5, 5]) == 1
+
+
+def test_letterbox_frames_match_the_reference_resize(cuda):
+    """(f-3) eas_letterbox_bilinear vs the reference's get_random_data(random=False) outputs (golden sample + checksum)
+    and the full oracle restatement: fp32 arithmetic against cv2's float64 -> 1e-6 relative."""
+    from helpers import letterbox_cases, load_golden
+    from oracle import letterbox as ol
+    for (ih, iw, h, w, center, lb), fr, sample, chk in letterbox_cases(load_golden("letterbox")):
+        want = ol.letterbox_frames(fr, (h, w), lb, center)
+        for dt in (torch.float32, torch.int32):
+            got = eas.letterbox_frames(torch.from_numpy(fr).to(cuda).to(dt), (h, w), letterbox=lb, center=center)
+            assert got.shape == (3, 2, h, w) and got.dtype == torch.float32
+            g = got.cpu().double().numpy()
+            err = np.abs(g - want) / np.maximum(1.0, np.abs(want))
+            assert err.max() <= 1e-6, ((ih, iw, h, w), err.max())
+            assert np.abs(g[:, :, ::3, ::5] - sample).max() <= 1e-5
+            assert abs(g.sum() - chk[0]) <= 1e-6 * chk[0]
+    # 5-D histograms keep their leading dims; the canvas outside the pasted image is zero
+    hist = torch.poisson(torch.full((2, 4, 2, 240, 304), 0.5)).to(cuda)
+    out = eas.letterbox_frames(hist, (640, 640))
+    assert out.shape == (2, 4, 2, 640, 640) and not out[..., 505:, :].any() and out[..., :505, :].any()

@@ -121,3 +121,18 @@ def test_spike_count_golden():
     for k in ("5", "6", "4"):
         x = torch.from_numpy(z["x" + k].astype(np.float32))
         assert torch.equal(sampler.spike_count(x, 4), torch.from_numpy(z["y" + k])), k
+
+
+def test_letterbox_golden():
+    """(f-3) oracle.letterbox (cv2 INTER_LINEAR restated + the paste of gen1.py:433-483) against the reference method's
+    own outputs: identical in float64."""
+    from oracle import letterbox as ol
+    from helpers import letterbox_cases
+    n = 0
+    for (ih, iw, h, w, center, lb), fr, sample, chk in letterbox_cases(load_golden("letterbox")):
+        got = ol.letterbox_frames(fr, (h, w), lb, center)
+        assert got.shape == (3, 2, h, w)
+        assert np.array_equal(got[:, :, ::3, ::5], sample), (ih, iw, h, w)
+        assert got.sum() == chk[0] and np.abs(got).max() == chk[1]
+        n += 1
+    assert n == 7
