@@ -52,6 +52,34 @@ def test_host_side_argument_checks_need_no_gpu():
     assert L.eas_plif_fwd(C.byref(pc), None, None, None, None, None, None) == -2
 
 
+def test_host_side_checks_of_the_detector_and_representation_entry_points():
+    """Shape / NULL / alignment contract violations come back as negative codes before anything is launched."""
+    L = _lib.lib()
+    E_NULL, E_SHAPE, E_UNSUP = -1, -2, -3
+    assert L.eas_time_mean_planes(None, 3, 10, 12, 12, None, 12, 120, None) == E_SHAPE      # C % 8 != 0
+    assert L.eas_time_mean_planes(None, 3, 10, 16, 16, None, 16, 160, None) == E_NULL
+    assert L.eas_time_mean_planes(None, 3, 0, 16, 16, None, 16, 0, None) == 0               # nothing to do
+    assert L.eas_upsample2x_planes(None, 2, 64, 1, 2, 2, 8, 4, None, 8, 256, None) == E_SHAPE   # in_ld < C
+    assert L.eas_upsample2x_planes(None, 2, 64, 1, 2, 2, 8, 8, None, 8, 256, None) == E_NULL
+    assert L.eas_yolox_decode(None, 1, 2, 3, 4, 4, 8.0, 1, None, 0, 6, None) == E_SHAPE       # n_ch < 5
+    assert L.eas_yolox_decode(None, 1, 2, 3, 7, 7, 8.0, 1, None, 4, 6, None) == E_SHAPE       # anchors overflow
+    assert L.eas_yolox_decode(None, 1, 2, 3, 7, 7, 8.0, 1, None, 0, 6, None) == E_NULL
+    assert L.eas_focus_im2col(None, 1, 3, 4, None, 0, None) == E_SHAPE                        # odd height
+    assert L.eas_focus_im2col(None, 1, 4, 4, None, 0, None) == E_NULL
+    assert L.eas_hist_time_sum(None, 0, 2, 4, 10, None, None) == E_SHAPE                      # plane % 4 != 0
+    assert L.eas_hist_time_sum(None, 2, 2, 4, 8, None, None) == E_UNSUP                       # bf16 histograms
+    assert L.eas_hist_time_sum(None, 0, 2, 4, 8, None, None) == E_NULL
+    assert L.eas_letterbox_bilinear(None, 0, 1, 4, 4, None, None, None, None, 8, 8, 0, 0, None, 8, 6, None) == E_SHAPE
+    assert L.eas_letterbox_bilinear(None, 0, 1, 4, 4, None, None, None, None, 8, 8, 1, 0, None, 8, 8, None) == E_SHAPE
+    assert L.eas_letterbox_bilinear(None, 0, 1, 4, 4, None, None, None, None, 8, 8, 0, 0, None, 8, 8, None) == E_NULL
+    cc = _lib.ConvCfg(T=3, Tx=3, B=1, H=8, W=8, Cin=12, Cout=16, ksize=3, stride=1, n_wsplit=2, n_xsplit=1)
+    assert L.eas_conv_bn_plif_fwd(C.byref(cc), None, None, None, None, None, None, 0, None) == E_SHAPE   # Cin % 8
+    cc.Cin, cc.ksize = 16, 5
+    assert L.eas_conv_bn_plif_fwd(C.byref(cc), None, None, None, None, None, None, 0, None) == E_UNSUP
+    cc.ksize = 3
+    assert L.eas_conv_bn_plif_fwd(C.byref(cc), None, None, None, None, None, None, 0, None) == E_NULL
+
+
 def test_no_cpu_fallback():
     z16 = torch.zeros(4, dtype=torch.int16)
     with pytest.raises(_lib.EasError):
