@@ -84,6 +84,7 @@ class AnnBaseConv(nn.Module):
         self.bn = nn.BatchNorm2d(cout, eps=1e-3, momentum=0.03)       # init_yolo, event_yolox_base.py:179-183
         self.act = nn.SiLU()
         self.ksize, self.stride = ksize, stride
+        self.fp16_inputs = False      # True: read only the hi plane of the input (see SpikingYOLOX.set_ann_precision)
         self._cache = None
 
     def packed(self):
@@ -99,6 +100,9 @@ class AnnBaseConv(nn.Module):
 
     def run(self, xp: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         wp, shift, unscale = self.packed()
+        if self.fp16_inputs:          # fp16 activations x fp32-equivalent weights: two product terms instead of three
+            return conv_bn_plif(xp[:1], wp, shift, None, 1, self.ksize, self.stride, n_xsplit=1, out=out,
+                                out_mode=OUT_SILU2, w_unscale=unscale)
         return conv_bn_plif(xp, wp, shift, None, 1, self.ksize, self.stride, n_xsplit=2, out=out, out_mode=OUT_SILU2,
                             w_unscale=unscale)
 
@@ -225,6 +229,7 @@ class YOLOXHead(nn.Module):
         self.reg_preds = nn.ModuleList(nn.Conv2d(hid, 4, 1, 1, 0) for _ in in_channels)
         self.obj_preds = nn.ModuleList(nn.Conv2d(hid, 1, 1, 1, 0) for _ in in_channels)
         self._pred_cache = {}
+        self.fp16_inputs = False
 
     def initialize_biases(self, prior_prob):                    # yolo_head.py:130-140
         for conv in list(self.cls_preds) + list(self.obj_preds):
@@ -266,10 +271,11 @@ class YOLOXHead(nn.Module):
             reg_feat = self.reg_convs[k][1].run(self.reg_convs[k][0].run(x))
             (w_ro, u_ro, b_ro), (w_c, u_c, b_c) = self._packed_preds(k)
             preds = torch.empty((1, B, H, W, n_ch), dtype=torch.float32, device=dev)
-            conv_bn_plif(reg_feat, w_ro, b_ro, None, 1, 1, 1, n_xsplit=2, out=preds[..., :5], out_mode=OUT_PREACT,
-                         w_unscale=u_ro)
-            conv_bn_plif(cls_feat, w_c, b_c, None, 1, 1, 1, n_xsplit=2, out=preds[..., 5:], out_mode=OUT_PREACT,
-                         w_unscale=u_c)
+            nx = 1 if self.fp16_inputs else 2
+            conv_bn_plif(reg_feat[:nx], w_ro, b_ro, None, 1, 1, 1, n_xsplit=nx, out=preds[..., :5],
+                         out_mode=OUT_PREACT, w_unscale=u_ro)
+            conv_bn_plif(cls_feat[:nx], w_c, b_c, None, 1, 1, 1, n_xsplit=nx, out=preds[..., 5:],
+                         out_mode=OUT_PREACT, w_unscale=u_c)
             with torch.cuda.device(dev):
                 rc = L.eas_yolox_decode(_lib.ptr(preds), B, H, W, n_ch, n_ch, float(self.strides[k]),
                                         int(self.decode_in_inference), _lib.ptr(out), a_off, A, _lib.stream_ptr())
@@ -302,6 +308,20 @@ class SpikingYOLOX(nn.Module):
         self.head = head
         if backbone.backbone.T != T:
             raise ValueError("backbone was built for T=%d" % backbone.backbone.T)
+
+    def set_ann_precision(self, precision: str = "fp32"):
+        """Arithmetic of the ANN pyramid / head (the spiking backbone is unaffected: its inputs are exact in fp16).
+        ``"fp32"`` (default): activations and weights as fp16 hi + lo planes, three product terms = fp32-equivalent,
+        the reference's default evaluation.  ``"fp16"``: activations rounded to fp16 on their way into every conv
+        (one input plane, two product terms, fp32 accumulation) -- what the reference computes under ``--fp16``
+        autocast (tools/eval_event.py, yolox/evaluators/event_evaluator.py:180-190); predictions then agree with the
+        fp32 ones to ~1e-2 relative, the reduced-precision bar of the parity contract."""
+        if precision not in ("fp32", "fp16"):
+            raise ValueError("ann precision must be 'fp32' or 'fp16'")
+        for m in list(self.backbone.modules()) + list(self.head.modules()):
+            if isinstance(m, (AnnBaseConv, YOLOXHead)):
+                m.fp16_inputs = precision == "fp16"
+        return self
 
     def embed(self, x):
         """spiking_yolox.py:41-57 up to the broadcast (which the backbone does implicitly for Ts == 1)."""

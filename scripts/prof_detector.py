@@ -9,6 +9,8 @@ net = detector.build_syolox(0.67, 0.75, 2, 3).to(dev).eval()
 for m in net.modules():
     if isinstance(m, torch.nn.BatchNorm2d):
         m.bias.data.fill_(0.6)
+if os.environ.get("ANN") == "fp16":
+    net.set_ann_precision("fp16")
 B = int(os.environ.get("B", 64))
 x = torch.rand(1, B, 2, 256, 320, device=dev) * 2
 for _ in range(2):

@@ -216,3 +216,18 @@ def test_detector_from_events_with_empty_and_single_event_windows(cuda):
     print("edge windows: max rel err %.2e" % mx)
     assert bad == 0.0, mx
     assert torch.equal(got[1], got[2])             # both windows are "no events" to the histogram
+
+
+def test_detector_fp16_activation_mode(cuda):
+    """The reduced-precision tier of the parity contract (1e-2 relative): ANN pyramid / head with fp16 activations
+    (what the reference's --fp16 evaluation computes) against the fp32 golden predictions of the reference model."""
+    z, meta, net, hist = _golden_model(cuda)
+    full = net(hist)
+    net.set_ann_precision("fp16")
+    half = net(hist)
+    mx, bad = _rel_ok(half, torch.from_numpy(z["pred"]), tol=1e-2)
+    print("fp16-activation ANN part: max rel err %.2e vs the reference fp32 predictions" % mx)
+    assert bad == 0.0, mx
+    assert not torch.equal(half, full)
+    net.set_ann_precision("fp32")
+    assert torch.equal(net(hist), full)
