@@ -362,7 +362,7 @@ def run_ours(args):
         det16_ms, _ = time_frames(lambda db: det.detect_frames(pad(step(db))), fsteps)
         det.set_ann_precision("fp32")
         n_spk = sum(1 for mod in bb.modules() if isinstance(mod, fused.FusedConvBNPLIF)) + 1
-        n_ann = sum(1 for mod in det.modules() if isinstance(mod, detector.AnnBaseConv)) + 6
+        n_ann = sum(1 for mod in det.modules() if isinstance(mod, fused.AnnBaseConv)) - 1 + 6   # (- stem, + predictors)
         gflop_bb = 6.61 * 3 * BATCH                                          # M@256x320, per sample-step
         frames = {"value": world * BATCH / det_ms * 1e3, "unit": "frames/s", "ms_per_batch": det_ms,
                   "what": "events -> bin -> sampler -> SYOLOX-M forward (T=3, 256x320): spiking CSPDarknet (%d tcgen05 "

@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .fused import (ACT_DTYPE, OUT_PREACT, OUT_SILU2, SpikingCSPDarknet, conv_bn_plif, fold_bn, pack_weight)
+from .fused import (ACT_DTYPE, OUT_PREACT, AnnBaseConv, SpikingCSPDarknet, conv_bn_plif, pack_weight)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -75,38 +75,6 @@ def _new_planes(B, H, W, C, device):
 # ------------------------------------------------------------------------------------------------
 # ANN blocks on planes (network_blocks.py:31-56, 81-104, 150-188 with act = SiLU)
 # ------------------------------------------------------------------------------------------------
-class AnnBaseConv(nn.Module):
-    """``BaseConv``: conv -> BN -> SiLU (network_blocks.py:31-56); keys ``conv.weight``, ``bn.*``."""
-
-    def __init__(self, cin, cout, ksize, stride):
-        super().__init__()
-        self.conv = nn.Conv2d(cin, cout, ksize, stride, (ksize - 1) // 2, bias=False)
-        self.bn = nn.BatchNorm2d(cout, eps=1e-3, momentum=0.03)       # init_yolo, event_yolox_base.py:179-183
-        self.act = nn.SiLU()
-        self.ksize, self.stride = ksize, stride
-        self.fp16_inputs = False      # True: read only the hi plane of the input (see SpikingYOLOX.set_ann_precision)
-        self._cache = None
-
-    def packed(self):
-        src = (self.conv.weight, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var)
-        key = tuple((t.data_ptr(), t._version) for t in src)
-        if self._cache is None or self._cache[0] != key:
-            with torch.no_grad():
-                w, shift = fold_bn(self.conv.weight, self.bn.weight, self.bn.bias, self.bn.running_mean,
-                                   self.bn.running_var, self.bn.eps)
-                wp, unscale = pack_weight(w, 2)
-                self._cache = (key, wp, shift.contiguous(), unscale)
-        return self._cache[1], self._cache[2], self._cache[3]
-
-    def run(self, xp: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
-        wp, shift, unscale = self.packed()
-        if self.fp16_inputs:          # fp16 activations x fp32-equivalent weights: two product terms instead of three
-            return conv_bn_plif(xp[:1], wp, shift, None, 1, self.ksize, self.stride, n_xsplit=1, out=out,
-                                out_mode=OUT_SILU2, w_unscale=unscale)
-        return conv_bn_plif(xp, wp, shift, None, 1, self.ksize, self.stride, n_xsplit=2, out=out, out_mode=OUT_SILU2,
-                            w_unscale=unscale)
-
-
 class _AnnBottleneck(nn.Module):
     def __init__(self, cin, cout, shortcut, expansion=0.5):
         super().__init__()

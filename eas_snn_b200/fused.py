@@ -251,14 +251,18 @@ class FusedConvBNPLIF(nn.Module):
 # ------------------------------------------------------------------------------------------------
 # the spiking CSPDarknet on channels-last buffers
 # ------------------------------------------------------------------------------------------------
-class _AnnStemConv(nn.Module):
-    """The stem's inner ``BaseConv`` (conv -> BN -> SiLU); the reference keeps it ANN (utils_snn.py:23-24)."""
+class AnnBaseConv(nn.Module):
+    """The reference's ANN ``BaseConv``: conv -> BN -> SiLU (network_blocks.py:31-56); keys ``conv.weight``, ``bn.*``.
+    Used for the stem's inner conv (``Focus`` stays ANN, utils_snn.py:23-24) and for every layer of the ANN pyramid /
+    head (``eas_snn_b200.detector``).  ``run`` works on two-plane activations ``[2, 1, B, H, W, C]``."""
 
-    def __init__(self, cin, cout, k):
+    def __init__(self, cin, cout, ksize, stride=1):
         super().__init__()
-        self.conv = nn.Conv2d(cin, cout, k, 1, (k - 1) // 2, bias=False)
-        self.bn = nn.BatchNorm2d(cout, eps=1e-3, momentum=0.03)
+        self.conv = nn.Conv2d(cin, cout, ksize, stride, (ksize - 1) // 2, bias=False)
+        self.bn = nn.BatchNorm2d(cout, eps=1e-3, momentum=0.03)       # init_yolo, event_yolox_base.py:179-183
         self.act = nn.SiLU()
+        self.ksize, self.stride = ksize, stride
+        self.fp16_inputs = False      # True: read only the hi plane of the input (SpikingYOLOX.set_ann_precision)
         self._cache = None
 
     def packed(self):
@@ -272,11 +276,19 @@ class _AnnStemConv(nn.Module):
                 self._cache = (key, wp, shift.contiguous(), unscale)
         return self._cache[1], self._cache[2], self._cache[3]
 
+    def run(self, xp: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        wp, shift, unscale = self.packed()
+        if self.fp16_inputs:          # fp16 activations x fp32-equivalent weights: two product terms instead of three
+            return conv_bn_plif(xp[:1], wp, shift, None, 1, self.ksize, self.stride, n_xsplit=1, out=out,
+                                out_mode=OUT_SILU2, w_unscale=unscale)
+        return conv_bn_plif(xp, wp, shift, None, 1, self.ksize, self.stride, n_xsplit=2, out=out, out_mode=OUT_SILU2,
+                            w_unscale=unscale)
+
 
 class _Focus(nn.Module):
     def __init__(self, cin, cout, k):
         super().__init__()
-        self.conv = _AnnStemConv(cin * 4, cout, k)
+        self.conv = AnnBaseConv(cin * 4, cout, k, 1)
 
     def forward(self, x):
         """PyTorch path (training: batch statistics + autograd), ``[N, C, H, W]`` (network_blocks.py:199-213)."""
