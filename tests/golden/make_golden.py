@@ -362,8 +362,8 @@ if __name__ == "__main__":
     make_sampler(emb, act)
     make_count(emb)
     make_letterbox(gen1)
+    make_psee(gen1)          # (before the two below: load_full_model re-imports yolox without the package stubs)
     make_backbone()
-    make_psee(gen1)
     make_detector()
-    for f in ("binning.npz", "sampler.npz", "backbone.npz", "psee.npz", "detector.npz"):
+    for f in ("binning.npz", "sampler.npz", "count.npz", "letterbox.npz", "backbone.npz", "psee.npz", "detector.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
