@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # a fresh checkout has no built library (binaries stay out of history): build it once, like __graft_entry__.build()
+    from eas_snn_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from eas_snn_b200.build import build_library
+        build_library()
 
 
 @pytest.fixture(scope="session")
