@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("EAS_B200_LIB") or os.path.join(_HERE, "lib", "libeas_
 
 EAS_F32, EAS_I32, EAS_BF16, EAS_U8 = 0, 1, 2, 3
 READOUT = {"sum": 0, "last": 1, "avg": 2}
-SAMPLER_ALGO = {"auto": 0, "fp32": 1, "tensor": 2}
+SAMPLER_ALGO = {"auto": 0, "fp32": 1, "tensor": 2, "tensor_split": 3}
 SURROGATE = {"atan": 0, "sigmoid": 1, "rect": 2}
 
 

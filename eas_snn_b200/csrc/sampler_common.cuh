@@ -36,6 +36,17 @@ bool eas_sampler_tc_supported(const eas_sampler_cfg* c, const void* events, cons
                               const float* gate_seq);
 int eas_sampler_tc_run(const eas_sampler_cfg* cfg, StepArgs a, float* s0, float* s1, void* wimg, cudaStream_t st);
 
+// Row-folded tensor-core path (sampler_tc2.cu): depth 2, k 5, inputs exact in one fp16 plane (event
+// counts).  Compact state: meta8 = B*2*H*W bytes, sb0 / sb1 = B*2*H*W/4 spike bytes each; vm / acc as in
+// StepArgs.  The flag is raised when an input is not exactly representable or a magnitude leaves the
+// fp16 range: the caller then recomputes the forward on another kernel.
+size_t eas_sampler_tc2_wimg_bytes();
+const int* eas_sampler_tc2_flag(const void* wimg);
+bool eas_sampler_tc2_supported(const eas_sampler_cfg* c, const void* events, const float* out, const float* v_seq,
+                               const float* gate_seq);
+int eas_sampler_tc2_run(const eas_sampler_cfg* cfg, StepArgs a, uint8_t* meta8, uint8_t* sb0, uint8_t* sb1, void* wimg,
+                        cudaStream_t st);
+
 __device__ __forceinline__ void cp_async_16(void* smem, const void* g, bool pred) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   const int sz = pred ? 16 : 0;

@@ -422,7 +422,7 @@ int check(const eas_sampler_cfg* c) {
   EAS_REQUIRE(c->ksize == 3 || c->ksize == 5 || c->ksize == 7, EAS_E_UNSUPPORTED);
   EAS_REQUIRE(c->readout >= EAS_READOUT_SUM && c->readout <= EAS_READOUT_AVG, EAS_E_UNSUPPORTED);
   EAS_REQUIRE(c->in_dtype == EAS_F32 || c->in_dtype == EAS_I32, EAS_E_UNSUPPORTED);
-  EAS_REQUIRE(c->algo >= EAS_SAMPLER_AUTO && c->algo <= EAS_SAMPLER_TENSOR, EAS_E_UNSUPPORTED);
+  EAS_REQUIRE(c->algo >= EAS_SAMPLER_AUTO && c->algo <= EAS_SAMPLER_TENSOR_SPLIT, EAS_E_UNSUPPORTED);
   return EAS_OK;
 }
 
@@ -433,8 +433,9 @@ extern "C" size_t eas_sampler_fwd_ws_bytes(const eas_sampler_cfg* c) {
   const size_t n = (size_t)c->B * 2 * c->H * c->W;
   // vm, acc, s0, s1 (f32) + meta (u16), each segment 256 B aligned
   // + the packed weight tiles of the tensor-core path
-  return 4 * eas_align_up(n * 4, 256) + eas_align_up(n * 2, 256) + 256 +
-         eas_align_up(eas_sampler_tc_wimg_bytes(), 256);
+  const size_t wimg = eas_sampler_tc_wimg_bytes() > eas_sampler_tc2_wimg_bytes() ? eas_sampler_tc_wimg_bytes()
+                                                                               : eas_sampler_tc2_wimg_bytes();
+  return 4 * eas_align_up(n * 4, 256) + eas_align_up(n * 2, 256) + 256 + eas_align_up(wimg, 256);
 }
 
 extern "C" int eas_sampler_fwd(const eas_sampler_cfg* c, const void* events, const eas_sampler_weights* w,
@@ -472,14 +473,25 @@ extern "C" int eas_sampler_fwd(const eas_sampler_cfg* c, const void* events, con
   a.readout = c->readout, a.hard_reset = c->hard_reset, a.write_zero = c->write_zero, a.use_abs = c->use_abs;
   a.vreset = c->vreset, a.thresh = c->thresh;
   cudaStream_t st = (cudaStream_t)stream;
-  // depth 2, k 5 (the published configuration): tensor-core kernel (sampler_tc.cu)
-  const bool tc_ok = eas_sampler_tc_supported(c, events, out, v_seq, gate_seq);
-  if (c->algo == EAS_SAMPLER_TENSOR) EAS_REQUIRE(tc_ok, EAS_E_UNSUPPORTED);
-  if (tc_ok && c->algo != EAS_SAMPLER_FP32) {
-    rc = eas_sampler_tc_run(c, a, s0, s1, wimg, st);
+  // depth 2, k 5 (the published configuration): tensor-core kernels.
+  //   TENSOR / AUTO : row-folded kernel (sampler_tc2.cu; inputs exact in one fp16 plane = event counts)
+  //   TENSOR_SPLIT  : first kernel (sampler_tc.cu; hi + lo input planes = real-valued inputs such as
+  //                   letterboxed frames), also what AUTO uses when only it supports the shape
+  // AUTO: inputs the kernel cannot hold exactly (or magnitudes beyond the fp16 range, never seen on event
+  // data) raise a device flag; the FP32-pipe launches below then recompute the whole step sequence,
+  // otherwise they exit at once.
+  const bool tc2_ok = eas_sampler_tc2_supported(c, events, out, v_seq, gate_seq);
+  const bool tc1_ok = eas_sampler_tc_supported(c, events, out, v_seq, gate_seq);
+  if (c->algo == EAS_SAMPLER_TENSOR) EAS_REQUIRE(tc2_ok, EAS_E_UNSUPPORTED);
+  if (c->algo == EAS_SAMPLER_TENSOR_SPLIT) EAS_REQUIRE(tc1_ok, EAS_E_UNSUPPORTED);
+  if (tc2_ok && (c->algo == EAS_SAMPLER_AUTO || c->algo == EAS_SAMPLER_TENSOR)) {
+    // the compact state lives in the same workspace segments: spike bytes in s0 / s1, one meta byte per element
+    rc = eas_sampler_tc2_run(c, a, (uint8_t*)a.meta, (uint8_t*)s0, (uint8_t*)s1, wimg, st);
     if (rc != EAS_OK || c->algo == EAS_SAMPLER_TENSOR) return rc;
-    // AUTO: operands beyond the fp16 range (never seen on event data) raise a device flag; the
-    // FP32-pipe launches below then recompute the whole step sequence, otherwise they exit at once.
+    a.run_if = eas_sampler_tc2_flag(wimg);
+  } else if (tc1_ok && c->algo != EAS_SAMPLER_FP32) {
+    rc = eas_sampler_tc_run(c, a, s0, s1, wimg, st);
+    if (rc != EAS_OK || c->algo == EAS_SAMPLER_TENSOR_SPLIT) return rc;
     a.run_if = eas_sampler_tc_flag(wimg);
   }
   // 16-byte vector path: rows must keep 16 B alignment (W % 4 == 0) and so must every base pointer

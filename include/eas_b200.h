@@ -113,11 +113,15 @@ typedef struct {
   int32_t write_zero;   /* RPD: residual potential of silent pixels dropped      */
   int32_t use_abs;      /* relu on the aggregated frames                         */
   int32_t in_dtype;     /* EAS_F32 or EAS_I32                                    */
-  int32_t algo;         /* EAS_SAMPLER_* (forward only): AUTO picks the tensor-core kernel for
-                           depth 2, k 5, W % 4 == 0, 16 B aligned buffers, else the FP32-pipe kernel */
+  int32_t algo;         /* EAS_SAMPLER_* (forward only): AUTO picks the row-folded tensor-core kernel for
+                           depth 2, k 5, W % 4 == 0, 16 B aligned buffers (and re-runs on the FP32-pipe
+                           kernel when an input is not exact in fp16), else the FP32-pipe kernel */
 } eas_sampler_cfg;
 
-enum { EAS_SAMPLER_AUTO = 0, EAS_SAMPLER_FP32 = 1, EAS_SAMPLER_TENSOR = 2 };
+/* TENSOR: row-folded tcgen05 kernel, inputs must be exact in one fp16 plane (event counts <= 2048; the
+ * result is undefined otherwise -- AUTO checks).  TENSOR_SPLIT: tcgen05 kernel with hi + lo input planes
+ * (real-valued inputs, e.g. letterboxed frames). */
+enum { EAS_SAMPLER_AUTO = 0, EAS_SAMPLER_FP32 = 1, EAS_SAMPLER_TENSOR = 2, EAS_SAMPLER_TENSOR_SPLIT = 3 };
 
 typedef struct {
   const float *in_w0, *in_b0, *in_w1, *in_b1;

@@ -9,7 +9,7 @@ model = eas.AdaptiveRSNNEmbedding(**bench.SAMPLER_KW).to(dev).eval()
 b = [torch.from_numpy(a).to(dev) for a in bench.host_batches(0, bench.BATCH)[0]]
 for dt in (torch.float32, torch.int32):
     hist = eas.bin_events(*b, bench.H, bench.W, bench.TM, dtype=dt)
-    for algo in ("auto", "tensor", "fp32"):
+    for algo in ("auto", "tensor", "tensor_split", "fp32"):
         model.algo = algo
         ts = []
         with torch.no_grad():

@@ -30,7 +30,9 @@ def _compare(out_gpu, out_ref, budget=1e-4):
     return frac <= budget, frac, msg
 
 
-ALGOS = ["fp32", "tensor"]
+# "tensor" = row-folded tcgen05 kernel (inputs exact in one fp16 plane: event counts), "tensor_split" = the
+# tcgen05 kernel with hi + lo input planes (real-valued inputs), "fp32" = FP32-pipe kernel
+ALGOS = ["fp32", "tensor", "tensor_split"]
 
 
 def _tc_capable(cfg_or_kw, W):
@@ -43,7 +45,7 @@ def _tc_capable(cfg_or_kw, W):
 def test_forward_golden(cuda, name, algo):
     z = load_golden("sampler")
     cfg, params, grads, x, y = sampler_case(z, name)
-    if algo == "tensor" and not _tc_capable(cfg, cfg["W"]):
+    if algo != "fp32" and not _tc_capable(cfg, cfg["W"]):
         pytest.skip("the tensor-core kernel covers depth 2 / k 5 / W % 4 == 0")
     m = eas.AdaptiveRSNNEmbedding(**sampler_kwargs(cfg)).to(cuda)
     m.algo = algo
@@ -134,22 +136,29 @@ def test_tensor_kernel_vs_oracle_shapes(cuda, shape, flags):
     g = torch.Generator().manual_seed(B * 1000 + H)
     x = torch.poisson(torch.full((B, Tm, 2, H, W), 1.0), generator=g)
     x[0, 0, 0, H // 2, W // 2] = 300.0            # a count that is not exact in one bf16 plane
-    if H % 2 == 1:                                # real-valued micro-frames (resized inputs): all 3 planes
+    real = H % 2 == 1
+    if real:                                      # real-valued micro-frames (resized inputs): hi + lo input planes
         x = x * (0.5 + torch.rand(x.shape, generator=g))
     with torch.no_grad():
         want = ref(x)
     m = eas.AdaptiveRSNNEmbedding(**kw).to(cuda)
     m.load_state_dict(ref.state_dict())
     outs = {}
-    for algo in ALGOS:
+    # real-valued inputs are not exact in one fp16 plane: "auto" must notice and recompute on the FP32 kernel
+    for algo in (["fp32", "auto", "tensor_split"] if real else ALGOS):
         m.algo = algo
         with torch.no_grad():
             outs[algo] = m(x.to(cuda))
         ok, frac, msg = _compare(outs[algo], want, budget=2e-3 if want.numel() < 20000 else 2e-4)
         print(algo, shape, msg)
         assert ok, algo + ": " + msg
-    ok, frac, msg = _compare(outs["tensor"], outs["fp32"].cpu(), budget=2e-3 if want.numel() < 20000 else 2e-4)
-    assert ok, "tensor vs fp32: " + msg
+    if real:
+        assert torch.equal(outs["auto"], outs["fp32"])
+    else:
+        ok, frac, msg = _compare(outs["tensor"], outs["fp32"].cpu(), budget=2e-3 if want.numel() < 20000 else 2e-4)
+        assert ok, "tensor vs fp32: " + msg
+    ok, frac, msg = _compare(outs["tensor_split"], outs["fp32"].cpu(), budget=2e-3 if want.numel() < 20000 else 2e-4)
+    assert ok, "tensor_split vs fp32: " + msg
     assert (want != 0).float().mean().item() > 0.01
 
 
@@ -166,22 +175,24 @@ def test_tensor_kernel_saves_same_sequences_for_backward(cuda):
         out = m(x)
         (out * torch.linspace(0.5, 1.5, out.numel(), device=cuda).view_as(out)).sum().backward()
         grads[algo] = [p.grad.clone() for p in m.parameters()]
-    for a, b in zip(grads["tensor"], grads["fp32"]):
-        scale = b.abs().max().item() + 1e-12
-        assert (a - b).abs().max().item() <= 2e-3 * scale, ((a - b).abs().max().item(), scale)
+    for algo in ALGOS[1:]:
+        for a, b in zip(grads[algo], grads["fp32"]):
+            scale = b.abs().max().item() + 1e-12
+            assert (a - b).abs().max().item() <= 2e-3 * scale, (algo, (a - b).abs().max().item(), scale)
 
 
 def test_auto_falls_back_beyond_fp16_range(cuda):
-    """The tensor-core kernel holds operands as fp16 hi+lo pairs; a magnitude >= 65504 raises its
-    device flag and algo="auto" recomputes on the FP32-pipe kernel: bit-identical to algo="fp32"."""
+    """The tensor-core kernels hold operands as fp16 planes; a count that is not exact in fp16 (row-folded kernel) or a
+    magnitude >= 65504 raises the device flag and algo="auto" recomputes on the FP32-pipe kernel: bit-identical to
+    algo="fp32"."""
     torch.manual_seed(5)
     kw = dict(kernel_size=5, depth=2, nb_steps=4, thresh=1, vreset=0, Ts=1, write_zero=True, spike_attach=True)
     m = eas.AdaptiveRSNNEmbedding(**kw).to(cuda)
     x = torch.poisson(torch.full((2, 4, 2, 40, 64), 1.0)).to(cuda)
     outs = {}
-    for big in (False, True):
+    for big in (0.0, 2049.0, 0.3, 70000.0):
         if big:
-            x[1, 2, 0, 17, 33] = 70000.0
+            x[1, 2, 0, 17, 33] = big
         for algo in ("auto", "fp32"):
             m.algo = algo
             with torch.no_grad():
