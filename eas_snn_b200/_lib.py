@@ -21,7 +21,8 @@ class SamplerCfg(C.Structure):
     _fields_ = [("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Tm", C.c_int32), ("Ts", C.c_int32),
                 ("ksize", C.c_int32), ("depth", C.c_int32), ("readout", C.c_int32), ("hard_reset", C.c_int32),
                 ("vreset", C.c_float), ("thresh", C.c_float), ("spike_attach", C.c_int32),
-                ("write_zero", C.c_int32), ("use_abs", C.c_int32), ("in_dtype", C.c_int32), ("algo", C.c_int32)]
+                ("write_zero", C.c_int32), ("use_abs", C.c_int32), ("in_dtype", C.c_int32), ("algo", C.c_int32),
+                ("surr_alpha", C.c_float)]
 
 
 class SamplerPtrs(C.Structure):

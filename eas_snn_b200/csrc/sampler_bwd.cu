@@ -36,6 +36,7 @@ struct BwdArgs {
   int B, H, W, Tm, Ts, t;
   int readout, hard_reset, write_zero, use_abs, spike_attach, in_is_int;
   float vreset, thresh;
+  float surr_alpha, surr_half;  // Rectangle: grad * alpha inside |v - thresh| < 0.5 / alpha
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(256) sampler_bwd_point_kernel(const BwdArgs a)
     d_s -= a.thresh * d_vm;
   }
   d_v += d_accp;                                                 // acc' = acc + v
-  if (fabsf(__fsub_rn(v, a.thresh)) < 0.5f) d_v += d_s;          // Rectangle surrogate
+  if (fabsf(__fsub_rn(v, a.thresh)) < a.surr_half) d_v += d_s * a.surr_alpha;   // Rectangle surrogate (activation.py:26-30)
   const float gate = a.gate_seq[(int64_t)t * n + e];
   // v = gate*vm_prev + cur
   const float d_gate = d_v * vm_prev;
@@ -550,6 +551,8 @@ extern "C" int eas_sampler_bwd(const eas_sampler_cfg* c, const void* events, con
   a.B = c->B, a.H = c->H, a.W = c->W, a.Tm = c->Tm, a.Ts = c->Ts;
   a.readout = c->readout, a.hard_reset = c->hard_reset, a.write_zero = c->write_zero, a.use_abs = c->use_abs;
   a.spike_attach = c->spike_attach, a.vreset = c->vreset, a.thresh = c->thresh;
+  a.surr_alpha = c->surr_alpha > 0.0f ? c->surr_alpha : 1.0f;
+  a.surr_half = 0.5f / a.surr_alpha;
   if (c->in_dtype == EAS_F32) return dispatch_bwd<float>(c, a, st);
   return dispatch_bwd<int32_t>(c, a, st);
 }

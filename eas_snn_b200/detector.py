@@ -24,7 +24,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .fused import (ACT_DTYPE, OUT_PREACT, AnnBaseConv, SpikingCSPDarknet, conv_bn_plif, pack_weight)
+from .fused import (ACT_DTYPE, OUT_PREACT, AnnBaseConv, FusedConvBNPLIF, SeqToANNContainer, SpikingCSPDarknet, _CSPLayer,
+                    conv_bn_plif, pack_weight)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -171,6 +172,94 @@ class SpikingYOLOPAFPN(nn.Module):
         return tuple(planes_to_nchw(p) for p in self.run(frames))
 
 
+def upsample2x_spikes(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """``SeqToANNContainer(nn.Upsample(scale_factor=2, mode='nearest'))`` (utils_snn.py:25-27) on channels-last
+    fp16 spikes ``[T, B, H, W, C]`` into ``out [T, B, 2H, 2W, C]`` (a channel slice of a concatenation buffer)."""
+    _lib.require_cuda(x, out)
+    T, B, H, W, C = x.shape
+    if tuple(out.shape) != (T, B, 2 * H, 2 * W, C) or x.dtype != ACT_DTYPE or out.dtype != ACT_DTYPE or not x.is_contiguous():
+        raise ValueError("upsample2x_spikes: x [T,B,H,W,C] fp16 contiguous, out [T,B,2H,2W,C]")
+    ld = out.stride(-2)
+    if out.stride(-1) != 1 or out.stride(-3) != 2 * W * ld or out.stride(1) != 4 * H * W * ld or \
+            (T > 1 and out.stride(0) != B * 4 * H * W * ld):
+        raise ValueError("upsample2x_spikes: out must be a channel slice of a contiguous [T,B,2H,2W,C'] buffer")
+    with torch.cuda.device(x.device):   # (T, B) is one batch axis for the kernel: one plane
+        rc = _lib.lib().eas_upsample2x_planes(_lib.ptr(x), 1, 0, T * B, H, W, C, C, _lib.ptr(out), ld, 0,
+                                              _lib.stream_ptr())
+    _lib.check(rc, "eas_upsample2x_planes")
+    return out
+
+
+class FullSpikeYOLOPAFPN(nn.Module):
+    """``convert_to_spiking(YOLOPAFPN(...))`` -- the backbone of ``use_spike full_spike / full_spike_v2``
+    (event_yolox_base.py:207-208; yolo_pafpn.py:16-116 through utils_snn.py:16-58): the spiking CSPDarknet AND a
+    spiking pyramid.  Every ``BaseConv`` is conv -> BN -> PLIF over the T steps on spike inputs (one fp16 plane, two
+    weight planes: fewer product terms than the ANN pyramid and the LIF in the conv epilogue), the upsampling and the
+    concatenations (``torch.cat(.., -3)``, :103-116) act per time step.  Returns the three spike tensors
+    ``(pan_out2, pan_out1, pan_out0)``; reference child names, so its ``state_dict`` loads with ``strict=True``."""
+
+    def __init__(self, depth=1.0, width=1.0, in_features=("dark3", "dark4", "dark5"), in_channels=(256, 512, 1024),
+                 in_dim=2, spike_fn=None, T=3):
+        super().__init__()
+        self.backbone = SpikingCSPDarknet(depth, width, in_dim=in_dim, spike_fn=spike_fn, T=T,
+                                          out_features=tuple(in_features))
+        self.in_features = tuple(in_features)
+        c0, c1, c2 = (int(c * width) for c in in_channels)
+        n = round(3 * depth)
+        self.upsample = SeqToANNContainer(nn.Upsample(scale_factor=2, mode="nearest"))
+        self.lateral_conv0 = FusedConvBNPLIF(c2, c1, 1, 1, spike_fn)
+        self.C3_p4 = _CSPLayer(2 * c1, c1, n, False, spike_fn)
+        self.reduce_conv1 = FusedConvBNPLIF(c1, c0, 1, 1, spike_fn)
+        self.C3_p3 = _CSPLayer(2 * c0, c0, n, False, spike_fn)
+        self.bu_conv2 = FusedConvBNPLIF(c0, c0, 3, 2, spike_fn)
+        self.C3_n3 = _CSPLayer(2 * c0, c1, n, False, spike_fn)
+        self.bu_conv1 = FusedConvBNPLIF(c1, c1, 3, 2, spike_fn)
+        self.C3_n4 = _CSPLayer(2 * c1, c2, n, False, spike_fn)
+        self.channels = (c0, c1, c2)
+
+    @torch.no_grad()
+    def run(self, frames: torch.Tensor):
+        """frames ``[Ts or T, B, in_dim, H, W]`` -> spikes ``[T, B, H/s, W/s, C]`` (fp16, channels-last) at s = 8, 16, 32."""
+        if self.training:
+            raise RuntimeError("FullSpikeYOLOPAFPN (fused) is the inference path; call .eval()")
+        T = self.backbone.T
+        c0, c1, c2 = self.channels
+        dev = frames.device
+        cats = {}
+
+        def buf(name, T_, B, H, W, ctot):
+            cats[name] = torch.empty((T_, B, H, W, ctot), dtype=ACT_DTYPE, device=dev)
+            return cats[name]
+
+        # dark4 / dark3 write straight into the second halves of the top-down concatenations (:102-108)
+        feats = self.backbone.run_cl(frames, into={
+            "dark4": lambda T_, B, H, W, C: buf("p4", T_, B, H, W, 2 * c1)[..., c1:],
+            "dark3": lambda T_, B, H, W, C: buf("p3", T_, B, H, W, 2 * c0)[..., c0:]})
+        s0 = feats[self.in_features[2]]
+        _, B, H0, W0, _ = s0.shape
+        cat_p4, cat_p3 = cats["p4"], cats["p3"]
+        H1, W1, H2, W2 = cat_p4.shape[2], cat_p4.shape[3], cat_p3.shape[2], cat_p3.shape[3]
+        if (H1, W1) != (2 * H0, 2 * W0) or (H2, W2) != (2 * H1, 2 * W1):
+            raise ValueError("input height and width must be multiples of 32 (event_yolox_base.py:556-559)")
+        cat_n3 = torch.empty((T, B, H1, W1, 2 * c0), dtype=ACT_DTYPE, device=dev)    # [bu_conv2(pan_out2), fpn_out1]
+        cat_n4 = torch.empty((T, B, H0, W0, 2 * c1), dtype=ACT_DTYPE, device=dev)    # [bu_conv1(pan_out1), fpn_out0]
+        fpn_out0 = self.lateral_conv0.run(s0, T, out=cat_n4[..., c1:])
+        upsample2x_spikes(fpn_out0.contiguous() if not fpn_out0.is_contiguous() else fpn_out0, cat_p4[..., :c1])
+        f_out0 = self.C3_p4.run(cat_p4, T)
+        fpn_out1 = self.reduce_conv1.run(f_out0, T, out=cat_n3[..., c0:])
+        upsample2x_spikes(fpn_out1.contiguous() if not fpn_out1.is_contiguous() else fpn_out1, cat_p3[..., :c0])
+        pan_out2 = self.C3_p3.run(cat_p3, T)
+        self.bu_conv2.run(pan_out2, T, out=cat_n3[..., :c0])
+        pan_out1 = self.C3_n3.run(cat_n3, T)
+        self.bu_conv1.run(pan_out1, T, out=cat_n4[..., :c1])
+        pan_out0 = self.C3_n4.run(cat_n4, T)
+        return pan_out2, pan_out1, pan_out0
+
+    def forward(self, frames: torch.Tensor):
+        """Reference-shaped: spike tensors as logical ``[T, B, C, H, W]`` views."""
+        return tuple(p.permute(0, 1, 4, 2, 3) for p in self.run(frames))
+
+
 def planes_to_nchw(p: torch.Tensor) -> torch.Tensor:
     """planes ``[2, 1, B, H, W, C]`` -> fp32 ``[B, C, H, W]`` (hi + lo)."""
     return (p[0, 0].float() + p[1, 0].float()).permute(0, 3, 1, 2)
@@ -200,43 +289,53 @@ class YOLOXHead(nn.Module):
         self.fp16_inputs = False
 
     def initialize_biases(self, prior_prob):                    # yolo_head.py:130-140
-        for conv in list(self.cls_preds) + list(self.obj_preds):
-            conv.bias.data.fill_(-math.log((1 - prior_prob) / prior_prob))
+        for k in range(len(self.cls_preds)):
+            for name in ("cls_preds", "obj_preds"):
+                self._pred(name, k).bias.data.fill_(-math.log((1 - prior_prob) / prior_prob))
 
     def _packed_preds(self, k):
         """(reg | obj) as one 5-channel 1x1 conv (both read reg_feat), cls as another; no BN, conv bias kept."""
-        src = [m[k].weight for m in (self.reg_preds, self.obj_preds, self.cls_preds)] + \
-              [m[k].bias for m in (self.reg_preds, self.obj_preds, self.cls_preds)]
+        reg, obj, cls = (self._pred(n, k) for n in ("reg_preds", "obj_preds", "cls_preds"))
+        src = [reg.weight, obj.weight, cls.weight, reg.bias, obj.bias, cls.bias]
         key = tuple((t.data_ptr(), t._version) for t in src)
         hit = self._pred_cache.get(k)
         if hit is None or hit[0] != key:
             with torch.no_grad():
-                w_ro = torch.cat((self.reg_preds[k].weight, self.obj_preds[k].weight), 0)
-                b_ro = torch.cat((self.reg_preds[k].bias, self.obj_preds[k].bias), 0).float().contiguous()
-                hit = (key, pack_weight(w_ro, 2) + (b_ro,),
-                       pack_weight(self.cls_preds[k].weight, 2) + (self.cls_preds[k].bias.float().contiguous(),))
+                w_ro = torch.cat((reg.weight, obj.weight), 0)
+                b_ro = torch.cat((reg.bias, obj.bias), 0).float().contiguous()
+                hit = (key, pack_weight(w_ro, 2) + (b_ro,), pack_weight(cls.weight, 2) + (cls.bias.float().contiguous(),))
                 self._pred_cache[k] = hit
         return hit[1], hit[2]
+
+    def _pred(self, name, k) -> nn.Conv2d:
+        return getattr(self, name)[k]
 
     @torch.no_grad()
     def run(self, feats):
         """feats: planes ``[2, 1, B, H, W, C]`` per level -> ``[B, n_anchors, 5 + num_classes]`` fp32."""
         if self.training:
             raise RuntimeError("YOLOXHead (fused) is the inference path; call .eval()")
+        towers = []
+        for k, xp in enumerate(feats):
+            x = self.stems[k].run(xp)
+            towers.append((self.cls_convs[k][1].run(self.cls_convs[k][0].run(x)),
+                           self.reg_convs[k][1].run(self.reg_convs[k][0].run(x))))
+        return self._predict_and_decode(towers)
+
+    @torch.no_grad()
+    def _predict_and_decode(self, towers):
+        """(cls_feat, reg_feat) planes per level -> 1x1 predictors -> sigmoid / grid decode -> ``[B, A, 5 + classes]``."""
         n_ch = 5 + self.num_classes
-        B = feats[0].shape[2]
-        dev = feats[0].device
-        hw = [tuple(f.shape[3:5]) for f in feats]
+        B = towers[0][0].shape[2]
+        dev = towers[0][0].device
+        hw = [tuple(c.shape[3:5]) for c, _ in towers]
         self.hw = hw
         A = sum(h * w for h, w in hw)
         out = torch.empty((B, A, n_ch), dtype=torch.float32, device=dev)
         a_off = 0
         L = _lib.lib()
-        for k, xp in enumerate(feats):
+        for k, (cls_feat, reg_feat) in enumerate(towers):
             H, W = hw[k]
-            x = self.stems[k].run(xp)
-            cls_feat = self.cls_convs[k][1].run(self.cls_convs[k][0].run(x))
-            reg_feat = self.reg_convs[k][1].run(self.reg_convs[k][0].run(x))
             (w_ro, u_ro, b_ro), (w_c, u_c, b_c) = self._packed_preds(k)
             preds = torch.empty((1, B, H, W, n_ch), dtype=torch.float32, device=dev)
             nx = 1 if self.fp16_inputs else 2
@@ -256,6 +355,70 @@ class YOLOXHead(nn.Module):
         return self.run([nchw_to_planes(x) for x in xin])
 
 
+class SpikingYOLOXHead(YOLOXHead):
+    """``SpikingYOLOXHead`` (spiking_yolo_head.py:18-230), inference branch, on the spike tensors of
+    :class:`FullSpikeYOLOPAFPN`.
+
+    ``full_spike=False`` (``use_spike full_spike``): the head itself stays ANN; every level is averaged over the T
+    steps first (``x.mean(axis=0)``, :159-160) -- :class:`YOLOXHead` on firing rates.
+    ``full_spike=True`` (``full_spike_v2``): stems and towers are conv -> BN -> PLIF over the T steps
+    (``convert_to_spiking(self)``, :125-127), the 1x1 predictors run per step and their outputs are averaged over T
+    (:173-178).  The predictors are linear, so the average is taken on the tower spikes instead (firing rates k/T, then
+    ONE predictor pass): the same number up to fp32 rounding, a third of the work.  State-dict keys as the reference's
+    (``stems.0.conv.0.weight``, ``stems.0.act.w``, ``cls_preds.0.0.weight``)."""
+
+    def __init__(self, num_classes, width=1.0, strides=(8, 16, 32), in_channels=(256, 512, 1024), spike_fn=None,
+                 full_spike=False, T=3):
+        super().__init__(num_classes, width, strides, in_channels)
+        self.full_spike = bool(full_spike)
+        self.T = T
+        if self.full_spike:
+            hid = int(256 * width)
+            self.stems = nn.ModuleList(FusedConvBNPLIF(int(c * width), hid, 1, 1, spike_fn) for c in in_channels)
+            self.cls_convs = nn.ModuleList(nn.Sequential(FusedConvBNPLIF(hid, hid, 3, 1, spike_fn),
+                                                         FusedConvBNPLIF(hid, hid, 3, 1, spike_fn)) for _ in in_channels)
+            self.reg_convs = nn.ModuleList(nn.Sequential(FusedConvBNPLIF(hid, hid, 3, 1, spike_fn),
+                                                         FusedConvBNPLIF(hid, hid, 3, 1, spike_fn)) for _ in in_channels)
+            for name in ("cls_preds", "reg_preds", "obj_preds"):      # lone Conv2d -> SeqToANNContainer (utils_snn.py:25-27)
+                setattr(self, name, nn.ModuleList(SeqToANNContainer(m) for m in getattr(self, name)))
+
+    def _pred(self, name, k) -> nn.Conv2d:
+        m = getattr(self, name)[k]
+        return m[0] if isinstance(m, SeqToANNContainer) else m
+
+    def initialize_biases(self, prior_prob):                    # spiking_yolo_head.py:135-146
+        for k in range(len(self.cls_preds)):
+            for name in ("cls_preds", "obj_preds"):
+                self._pred(name, k).bias.data.fill_(-math.log((1 - prior_prob) / prior_prob))
+
+    @torch.no_grad()
+    def run(self, feats):
+        """feats: spikes ``[T, B, H, W, C]`` fp16 per level -> ``[B, n_anchors, 5 + num_classes]`` fp32."""
+        if self.training:
+            raise RuntimeError("SpikingYOLOXHead (fused) is the inference path; call .eval()")
+        dev = feats[0].device
+        if not self.full_spike:
+            rates = []
+            for f in feats:
+                _, B, H, W, C = f.shape
+                rates.append(time_mean_planes(f.contiguous(), _new_planes(B, H, W, C, dev)))
+            return super().run(rates)
+        T = feats[0].shape[0]
+        towers = []
+        for k, f in enumerate(feats):
+            x = self.stems[k].run(f.contiguous(), T)
+            cls_feat = self.cls_convs[k][1].run(self.cls_convs[k][0].run(x, T), T)
+            reg_feat = self.reg_convs[k][1].run(self.reg_convs[k][0].run(x, T), T)
+            _, B, H, W, C = cls_feat.shape
+            towers.append((time_mean_planes(cls_feat, _new_planes(B, H, W, C, dev)),
+                           time_mean_planes(reg_feat, _new_planes(B, H, W, C, dev))))
+        return self._predict_and_decode(towers)
+
+    def forward(self, xin, labels=None, imgs=None):
+        """Reference-shaped entry: ``xin`` = spikes ``[T, B, C, H, W]`` per level."""
+        return self.run([x.permute(0, 1, 3, 4, 2).to(ACT_DTYPE).contiguous() for x in xin])
+
+
 def nchw_to_planes(x: torch.Tensor) -> torch.Tensor:
     from .fused import split_f16
     return split_f16(x.permute(0, 2, 3, 1).contiguous().unsqueeze(0), 2)
@@ -268,7 +431,7 @@ class SpikingYOLOX(nn.Module):
     """``SpikingYOLOX`` (spiking_yolox.py:23-74), inference: ``forward(x)`` with ``x`` the micro-bin histograms
     ``[B, Tm, 2, H, W]`` (or whatever the embedding takes) returns ``[B, n_anchors, 5 + num_classes]``."""
 
-    def __init__(self, backbone: SpikingYOLOPAFPN, head: YOLOXHead, embedding=None, T=4):
+    def __init__(self, backbone, head: YOLOXHead, embedding=None, T=4):
         super().__init__()
         self.nb_steps = T
         self.embedding = embedding
@@ -291,16 +454,19 @@ class SpikingYOLOX(nn.Module):
                 m.fp16_inputs = precision == "fp16"
         return self
 
-    def embed(self, x):
-        """spiking_yolox.py:41-57 up to the broadcast (which the backbone does implicitly for Ts == 1)."""
+    def embed(self, x, sampler=None):
+        """spiking_yolox.py:41-57 up to the broadcast (which the backbone does implicitly for Ts == 1).  ``sampler``
+        replaces the call of the sampler module (the raw-event front doors pass ``m.forward_events(...)``); the
+        ``exp.norm`` variant ``ModuleList([embedding, BatchNorm2d(2)])`` (event_yolox_base.py:188-192) goes the same way."""
+        call = sampler if sampler is not None else (lambda m: m(x))
         if isinstance(self.embedding, nn.ModuleList):
-            x = self.embedding[0](x)
+            x = call(self.embedding[0])
             if x.dim() > 4:
                 x = x[0]
             if len(self.embedding) > 1:
                 x = self.embedding[1](x)
         elif self.embedding is not None:
-            x = self.embedding(x)
+            x = call(self.embedding)
             if x.dim() > 5:
                 x = x[0]
         if x.dim() == 4:
@@ -324,7 +490,7 @@ class SpikingYOLOX(nn.Module):
     def forward_events(self, x, y, t, p, offsets, H: int, W: int, pad_to=None):
         """raw events -> detections: binning + sampler (``AdaptiveRSNNEmbedding.forward_events``), zero padding of
         the frames to ``pad_to = (H', W')`` (multiples of 32), detector."""
-        frames = self.embedding.forward_events(x, y, t, p, offsets, H, W)
+        frames = self.embed(None, sampler=lambda m: m.forward_events(x, y, t, p, offsets, H, W))
         return self.detect_frames(pad_frames(frames, pad_to))
 
 
@@ -338,11 +504,22 @@ def pad_frames(frames: torch.Tensor, size=None) -> torch.Tensor:
     return torch.nn.functional.pad(frames, (0, Wp - W, 0, Hp - H))
 
 
-def build_syolox(depth, width, num_classes=2, T=3, embedding=None, spike_fn=None, in_channels=(256, 512, 1024)):
-    """The model of ``EventExp.get_model`` for ``use_spike True`` (event_yolox_base.py:188-207); e-yolox-s =
-    (0.33, 0.50), e-yolox-m = (0.67, 0.75) (exps/default/e_yolox_s.py:13-14, e_yolox_m.py:13-14)."""
-    backbone = SpikingYOLOPAFPN(depth, width, in_channels=in_channels, in_dim=2, spike_fn=spike_fn, T=T)
-    head = YOLOXHead(num_classes, width, in_channels=in_channels)
+def build_syolox(depth, width, num_classes=2, T=3, embedding=None, spike_fn=None, in_channels=(256, 512, 1024),
+                 use_spike=True):
+    """The model of ``EventExp.get_model`` (event_yolox_base.py:188-218); e-yolox-s = (0.33, 0.50), e-yolox-m =
+    (0.67, 0.75) (exps/default/e_yolox_s.py:13-14, e_yolox_m.py:13-14).  ``use_spike``: ``True`` (spiking backbone, ANN
+    pyramid + head, :197-206), ``"full_spike"`` (spiking backbone + pyramid, ANN head on firing rates, :207-211) or
+    ``"full_spike_v2"`` (spiking head towers too) -- the README trains and evaluates SYOLOX-M with ``full_spike``
+    (readme.md:136-160)."""
+    if use_spike is True or use_spike == "True":
+        backbone = SpikingYOLOPAFPN(depth, width, in_channels=in_channels, in_dim=2, spike_fn=spike_fn, T=T)
+        head = YOLOXHead(num_classes, width, in_channels=in_channels)
+    elif isinstance(use_spike, str) and "full_spike" in use_spike:
+        backbone = FullSpikeYOLOPAFPN(depth, width, in_channels=in_channels, in_dim=2, spike_fn=spike_fn, T=T)
+        head = SpikingYOLOXHead(num_classes, width, in_channels=in_channels, spike_fn=spike_fn,
+                                full_spike="v2" in use_spike, T=T)
+    else:
+        raise NotImplementedError("use_spike=%r: the fused detector covers True, 'full_spike', 'full_spike_v2'" % (use_spike,))
     model = SpikingYOLOX(backbone, head, embedding, T=T)
     head.initialize_biases(1e-2)
     return model

@@ -26,7 +26,8 @@ def _cfg(B, H, W, Tm, mod, in_dtype):
                            vreset=0.0 if mod.vreset is None else float(mod.vreset), thresh=float(mod.thresh),
                            spike_attach=int(bool(mod.spike_attach)), write_zero=int(bool(mod.write_zero)),
                            use_abs=int(bool(mod.abs)), in_dtype=in_dtype,
-                           algo=_lib.SAMPLER_ALGO[getattr(mod, "algo", "auto")])
+                           algo=_lib.SAMPLER_ALGO[getattr(mod, "algo", "auto")],
+                           surr_alpha=float(getattr(mod.kwargs_spikes.get("spike_fn", None), "alpha", 1.0)))
 
 
 def _pack_ptrs(tensors):

@@ -214,7 +214,8 @@ class FusedConvBNPLIF(nn.Module):
         return (self.conv[0].weight, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var)
 
     def packed(self):
-        key = tuple((t.data_ptr(), t._version) for t in self._sources()) + (self.n_wsplit,)
+        # (bn.eps is part of the key: init_yolo rewrites it after construction, event_yolox_base.py:179-183)
+        key = tuple((t.data_ptr(), t._version) for t in self._sources()) + (self.n_wsplit, float(self.bn.eps))
         if self._cache is None or self._cache[0] != key:
             with torch.no_grad():
                 w, shift = fold_bn(self.conv[0].weight, self.bn.weight, self.bn.bias, self.bn.running_mean,
@@ -267,7 +268,7 @@ class AnnBaseConv(nn.Module):
 
     def packed(self):
         src = (self.conv.weight, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var)
-        key = tuple((t.data_ptr(), t._version) for t in src)
+        key = tuple((t.data_ptr(), t._version) for t in src) + (float(self.bn.eps),)
         if self._cache is None or self._cache[0] != key:
             with torch.no_grad():
                 w, shift = fold_bn(self.conv.weight, self.bn.weight, self.bn.bias, self.bn.running_mean,
@@ -301,7 +302,7 @@ class _Focus(nn.Module):
         """The stem conv as a 1x1 conv over im2col rows ``[tap][focus channel]`` (72 -> 80 zero padded)."""
         m = self.conv
         src = (m.conv.weight, m.bn.weight, m.bn.bias, m.bn.running_mean, m.bn.running_var)
-        key = tuple((t.data_ptr(), t._version) for t in src)
+        key = tuple((t.data_ptr(), t._version) for t in src) + (float(m.bn.eps),)
         if getattr(self, "_cache_i2c", None) is None or self._cache_i2c[0] != key:
             with torch.no_grad():
                 w, shift = fold_bn(m.conv.weight, m.bn.weight, m.bn.bias, m.bn.running_mean, m.bn.running_var, m.bn.eps)
@@ -390,16 +391,16 @@ class _CSPLayer(nn.Module):
         self.conv3 = FusedConvBNPLIF(2 * hid, cout, 1, 1, spike_fn)
         self.m = nn.Sequential(*[_Bottleneck(hid, hid, shortcut, 1.0, spike_fn) for _ in range(n)])
 
-    def run(self, x, T):
+    def run(self, x, T, out=None):
         Tn, B, H, W, _ = x.shape
         hid = self.conv1.conv[0].out_channels
         cat = torch.empty((T, B, H, W, 2 * hid), dtype=ACT_DTYPE, device=x.device)
         self.conv2.run(x, T, out=cat[..., hid:])
-        y = self.conv1.run(x, T)
         blocks = list(self.m)
+        y = self.conv1.run(x, T, out=None if blocks else cat[..., :hid])
         for i, blk in enumerate(blocks):
             y = blk.run(y, T, out=cat[..., :hid] if i == len(blocks) - 1 else None)
-        return self.conv3.run(cat, T)
+        return self.conv3.run(cat, T, out=out)
 
     def forward(self, x):
         return self.conv3(torch.cat((self.m(self.conv1(x)), self.conv2(x)), dim=-3))
@@ -432,8 +433,10 @@ class SpikingCSPDarknet(nn.Module):
                                    _CSPLayer(c * 16, c * 16, d, False, spike_fn))
 
     @torch.no_grad()
-    def run_cl(self, frames: torch.Tensor) -> dict:
-        """All stage outputs as channels-last fp16 spike tensors ``[T, B, H, W, C]`` (what the fused FPN reads)."""
+    def run_cl(self, frames: torch.Tensor, into: dict | None = None) -> dict:
+        """All stage outputs as channels-last fp16 spike tensors ``[T, B, H, W, C]`` (what the fused FPN reads).
+        ``into[name]`` (optional) = a function ``(T, B, H, W, C) -> tensor`` giving the buffer (e.g. a channel slice of
+        a concatenation buffer of the pyramid) that stage ``name`` writes its output into."""
         if self.training:
             raise RuntimeError("run_cl is the fused inference path; call .eval() (training: forward())")
         _lib.require_cuda(frames)
@@ -448,8 +451,13 @@ class SpikingCSPDarknet(nn.Module):
         for name in ("dark3", "dark4", "dark5"):
             seq = getattr(self, name)
             x = seq[0].run(x, T)
-            for blk in list(seq)[1:]:
-                x = blk.run(x, T)
+            blocks = list(seq)[1:]
+            for i, blk in enumerate(blocks):
+                if i == len(blocks) - 1 and into is not None and name in into:
+                    _, B, H, W, _ = x.shape
+                    x = blk.run(x, T, out=into[name](T, B, H, W, blk.conv3.conv[0].out_channels))
+                else:
+                    x = blk.run(x, T)
             outs[name] = x
         return outs
 

@@ -57,8 +57,10 @@ class Rect(_Surrogate):
 
 
 def surrogate_kind(fn) -> tuple[int, float]:
-    """Duck-typed: works for our carriers and for spikingjelly's ``surrogate.ATan/Sigmoid`` objects."""
-    name = getattr(fn, "kind", None) or type(fn).__name__
+    """Duck-typed: works for our carriers, for spikingjelly's ``surrogate.ATan/Sigmoid`` objects and for the
+    reference's ``Rectangle`` autograd.Function CLASS (what ``spike_fn='rect'`` hands over,
+    ``yolox/exp/event_yolox_base.py:146``; its ``alpha`` is a class attribute, activation.py:18)."""
+    name = getattr(fn, "kind", None) or (fn.__name__ if isinstance(fn, type) else type(fn).__name__)
     name = name.lower()
     if name == "rectangle":
         name = "rect"
@@ -122,6 +124,12 @@ def plif_multistep(x_seq, w, node, v0=None, want_v=False):
         x_seq = x_seq.float()
     x_seq = x_seq.contiguous()
     if v0 is not None:
+        # the kernels index v0[i] for every element of one time step: a state carried over from another batch
+        # size / resolution (no reset_net in between) must not be read out of bounds or applied to other neurons
+        if tuple(v0.shape) != tuple(x_seq.shape[1:]) or v0.device != x_seq.device:
+            raise ValueError("membrane state of shape %s on %s does not match the input %s on %s: call reset() "
+                             "(functional.reset_net) before changing the batch size or resolution"
+                             % (tuple(v0.shape), v0.device, tuple(x_seq.shape[1:]), x_seq.device))
         v0 = v0.float().contiguous()
     return _PlifFn.apply(x_seq, w, v0, node, want_v)
 
@@ -156,6 +164,11 @@ class ParametricLIFNode(nn.Module):
     def forward(self, x):
         seq = x if self.step_mode == "m" else x.unsqueeze(0)
         v0 = self.v if isinstance(self.v, torch.Tensor) else None
+        if v0 is not None and torch.is_grad_enabled() and (x.requires_grad or self.w.requires_grad):
+            # the carried potential is a plain buffer (grad_v0 is not produced): BPTT across separate calls
+            # would be silently truncated.  The reference resets after every batch (trainer.py:115-117).
+            raise RuntimeError("ParametricLIFNode: state carried across calls under autograd is not differentiable here; "
+                               "use step_mode='m' over the whole sequence and reset_net() between batches")
         spikes, v_out = plif_multistep(seq, self.w, self, v0=v0, want_v=self.keep_v)
         if self.keep_v:
             self.v = v_out

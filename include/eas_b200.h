@@ -116,6 +116,8 @@ typedef struct {
   int32_t algo;         /* EAS_SAMPLER_* (forward only): AUTO picks the row-folded tensor-core kernel for
                            depth 2, k 5, W % 4 == 0, 16 B aligned buffers (and re-runs on the FP32-pipe
                            kernel when an input is not exact in fp16), else the FP32-pipe kernel */
+  float surr_alpha;     /* Rectangle.alpha (a class attribute, activation.py:18-30): the backward passes
+                           grad * alpha inside |v - thresh| < 0.5 / alpha.  0 is read as 1 (the reference's value) */
 } eas_sampler_cfg;
 
 /* TENSOR: row-folded tcgen05 kernel, inputs must be exact in one fp16 plane (event counts <= 2048; the

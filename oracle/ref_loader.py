@@ -57,7 +57,13 @@ def load_full_model(name="e-yolox-s", opts=()):
         for k in [k for k in sys.modules if k == "yolox" or k.startswith("yolox.")]:
             del sys.modules[k]
     root = os.path.dirname(_HERE)
-    for p in (root, os.path.join(_HERE, "sj_shim"), REF):
+    # the real spikingjelly wins when it is installed; the shim (our restatement) is only the stand-in
+    try:
+        import spikingjelly.activation_based.neuron  # noqa: F401
+        paths = (root, REF)
+    except ImportError:
+        paths = (root, os.path.join(_HERE, "sj_shim"), REF)
+    for p in paths:
         if p not in sys.path:
             sys.path.insert(0, p)
     from yolox.exp import get_exp  # type: ignore
@@ -65,3 +71,12 @@ def load_full_model(name="e-yolox-s", opts=()):
     exp.merge(list(opts))
     model = exp.get_model()
     return exp, model
+
+
+def spikingjelly_origin() -> str:
+    """'shim' when the neuron / BN / container classes come from oracle/sj_shim, else the real package's version."""
+    import spikingjelly
+    f = getattr(spikingjelly, "__file__", "") or ""
+    if "sj_shim" in f:
+        return "shim"
+    return "spikingjelly " + str(getattr(spikingjelly, "__version__", "unknown"))

@@ -10,11 +10,16 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    # a fresh checkout has no built library (binaries stay out of history): build it once, like __graft_entry__.build()
+    # a fresh checkout has no built library (binaries stay out of history): build it once, like
+    # __graft_entry__.build().  Without nvcc (a plain CPU box) the oracle / golden / gloo tests still run; the tests
+    # that load the library fail on their own with the loader's message.
     from eas_snn_b200 import _lib
     if not os.path.exists(_lib.LIB_PATH):
-        from eas_snn_b200.build import build_library
-        build_library()
+        try:
+            from eas_snn_b200.build import build_library
+            build_library()
+        except (OSError, RuntimeError) as e:
+            sys.stderr.write("conftest: could not build libeas_b200.so (%s)\n" % e)
 
 
 @pytest.fixture(scope="session")

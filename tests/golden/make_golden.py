@@ -2,7 +2,8 @@
 
     python tests/golden/make_golden.py          # needs /root/reference (read-only)
 
-Outputs (small, committed): tests/golden/binning.npz, sampler.npz, backbone.npz, psee.npz, detector.npz, count.npz, letterbox.npz.
+Outputs (small, committed): tests/golden/binning.npz, sampler.npz, backbone.npz, psee.npz, detector.npz,
+detector_full_spike.npz, detector_full_spike_v2.npz, count.npz, letterbox.npz.
 The reference is imported in place through ``oracle/ref_loader.py``; nothing is copied from it.
 ``/root/reference`` does not exist on the GPU box, so tests only ever read the .npz files.
 """
@@ -208,15 +209,20 @@ def make_backbone():
     print("backbone.npz written, params:", sum(p.numel() for p in bb.parameters()))
 
 
-def make_detector():
-    """(f-2) The reference's whole model for ``use_spike True`` -- ``EventExp.get_model()`` = SpikingYOLOX(
-    SpikingYOLOPAFPN, YOLOXHead, AdaptiveRSNNEmbedding) -- at a tiny width, run unmodified through the
+def make_detector(use_spike=True):
+    """(f-2) The reference's whole model -- ``EventExp.get_model()`` -- at a tiny width, run unmodified through the
     spikingjelly shim: micro-bin histograms in, decoded predictions out, plus the pyramid features, the sampler
-    frames and the reference's own ``postprocess`` (boxes.py:33-77) on those predictions."""
+    frames and the reference's own ``postprocess`` (boxes.py:33-77) on those predictions.
+      use_spike True            : SpikingYOLOX(SpikingYOLOPAFPN, YOLOXHead, ...)               -> detector.npz
+      use_spike 'full_spike'    : SpikingYOLOX(convert_to_spiking(YOLOPAFPN), SpikingYOLOXHead(full_spike=False))
+                                  (event_yolox_base.py:207-211; what readme.md:136-160 trains / evaluates) -> detector_full_spike.npz
+      use_spike 'full_spike_v2' : ... SpikingYOLOXHead(full_spike=True): spiking towers, time mean of the predictor
+                                  outputs (spiking_yolo_head.py:125-127, 159-178)                -> detector_full_spike_v2.npz"""
+    tag = "" if use_spike is True else "_" + use_spike
     exp, model = ref_loader.load_full_model("e-yolox-s", ["T", 3, "embedding", "arsnn", "embedding_depth", 2,
                                                           "embedding_ksize", 5, "spike_attach", True,
                                                           "write_zero", True, "spike_fn", "atan",
-                                                          "use_spike", True, "num_classes", 2,
+                                                          "use_spike", use_spike, "num_classes", 2,
                                                           "width", 0.125, "depth", 0.33])
     from spikingjelly.activation_based import functional
     from oracle.backbone import calibrate_bn
@@ -237,18 +243,40 @@ def make_detector():
     with torch.no_grad():
         frames = model.embedding(hist)                                   # [Ts=1, B, 2, H, W]
     nz = float((frames != 0).float().mean())
-    print(" detector sampler frames", tuple(frames.shape), "non-zero %.3f" % nz)
+    print(" detector%s sampler frames" % tag, tuple(frames.shape), "non-zero %.3f" % nz)
     assert frames.shape == (1, B, 2, H, W) and 0.01 < nz < 0.9
     x = frames.expand(3, -1, -1, -1, -1).contiguous()
-    calibrate_bn(model.backbone, x, seed=3)                              # spiking backbone + ANN pyramid BNs
+    calibrate_bn(model.backbone, x, seed=3)                              # every BN of the backbone + pyramid
     gg = torch.Generator().manual_seed(4)
-    for m in model.head.modules():                                       # head BNs: non-trivial running stats
-        if isinstance(m, nn.BatchNorm2d):
-            m.weight.data = torch.empty_like(m.weight).uniform_(0.8, 1.2, generator=gg)
-            m.bias.data = torch.empty_like(m.bias).normal_(0.0, 0.1, generator=gg)
+    head_bns = [m for m in model.head.modules() if isinstance(m, nn.BatchNorm2d)]
+    for m in head_bns:                                                   # head BNs: non-trivial affine parameters
+        m.weight.data = torch.empty_like(m.weight).uniform_(0.8, 1.2, generator=gg)
+        m.bias.data = torch.empty_like(m.bias).normal_(0.0, 0.1, generator=gg)
+        if use_spike != "full_spike_v2":                                 # ANN head: any running statistics will do
             m.running_mean.data = torch.empty_like(m.running_mean).normal_(0.0, 0.2, generator=gg)
             m.running_var.data = torch.empty_like(m.running_var).uniform_(0.5, 1.5, generator=gg)
-    for conv in list(model.head.cls_preds) + list(model.head.reg_preds) + list(model.head.obj_preds):
+    if use_spike == "full_spike_v2":
+        # spiking towers: running statistics calibrated on their own inputs (random ones leave the towers dead or
+        # saturated -- the vacuous-parity hazard of SURVEY 7.8); two train-mode passes with momentum 1
+        old = [m.momentum for m in head_bns]
+        for m in head_bns:
+            m.momentum = 1.0
+        model.eval()
+        with torch.no_grad():
+            feats = model.backbone(x)
+            functional.reset_net(model)
+            model.head.train()
+            for _ in range(2):
+                for k, f in enumerate(feats):
+                    y = model.head.stems[k](f)
+                    model.head.cls_convs[k](y)
+                    model.head.reg_convs[k](y)
+                functional.reset_net(model)
+        for m, o in zip(head_bns, old):
+            m.momentum = o
+    preds_convs = [m for ml in (model.head.cls_preds, model.head.reg_preds, model.head.obj_preds) for mm in ml
+                   for m in mm.modules() if isinstance(m, nn.Conv2d)]
+    for conv in preds_convs:
         # (the 1e-2 prior of initialize_biases would put every score below any useful threshold)
         conv.bias.data = torch.empty_like(conv.bias).normal_(0.0, 0.7, generator=gg)
         conv.weight.data *= 0.3
@@ -270,8 +298,26 @@ def make_detector():
     for k, v in model.state_dict().items():
         out["sd/" + k] = v.numpy()
     for i, f in enumerate(pyramid):
-        out["pyramid/%d" % i] = f.numpy()
-        print(" detector pyramid", i, tuple(f.shape), "mean |x| %.3f" % float(f.abs().mean()))
+        if f.dim() == 5:                                                 # spiking pyramid: [T, B, C, H, W] spikes
+            rate = float(f.mean())
+            assert 0.01 < rate < 0.9, ("pyramid level %d is dead or saturated" % i, rate)
+            assert bool(((f == 0) | (f == 1)).all())
+            out["pyramid/%d" % i] = f.numpy().astype(np.uint8)
+            print(" detector%s pyramid" % tag, i, tuple(f.shape), "rate %.3f" % rate)
+        else:
+            out["pyramid/%d" % i] = f.numpy()
+            print(" detector%s pyramid" % tag, i, tuple(f.shape), "mean |x| %.3f" % float(f.abs().mean()))
+    if use_spike == "full_spike_v2":                                     # firing rates inside the spiking towers
+        with torch.no_grad():
+            for k, f in enumerate(pyramid):
+                y = model.head.stems[k](f)
+                c, r = model.head.cls_convs[k](y), model.head.reg_convs[k](y)
+                for nm, v in (("stem", y), ("cls", c), ("reg", r)):
+                    rate = float(v.mean())
+                    assert 0.005 < rate < 0.95, (nm, k, rate)
+                out["tower/%d/cls" % k] = c.numpy().astype(np.uint8)
+                out["tower/%d/reg" % k] = r.numpy().astype(np.uint8)
+            functional.reset_net(model)
     n_det = 0
     for i, d in enumerate(dets):
         out["dets/%d" % i] = np.zeros((0, 7), np.float32) if d is None else d.numpy()
@@ -280,9 +326,10 @@ def make_detector():
     out["meta"] = np.array([repr(dict(depth=0.33, width=0.125, num_classes=2, T=3, Tm=Tm, Ts=1, ksize=5,
                                       emb_depth=2, readout=exp.readout, vreset=exp.reset, thresh=exp.thresh,
                                       spike_attach=True, write_zero=True, abs=bool(exp.abs), alpha=float(exp.alpha),
-                                      conf_thre=0.3, nms_thre=0.45))])
-    np.savez_compressed(os.path.join(HERE, "detector.npz"), **out)
-    print("detector.npz written: pred", tuple(pred.shape), "detections", n_det,
+                                      conf_thre=0.3, nms_thre=0.45, use_spike=use_spike,
+                                      spikingjelly=ref_loader.spikingjelly_origin()))])
+    np.savez_compressed(os.path.join(HERE, "detector%s.npz" % tag), **out)
+    print("detector%s.npz written: pred" % tag, tuple(pred.shape), "detections", n_det,
           "obj range %.3f..%.3f" % (float(pred[..., 4].min()), float(pred[..., 4].max())))
 
 
@@ -358,6 +405,10 @@ if __name__ == "__main__":
         make_detector()
         print("detector.npz", os.path.getsize(os.path.join(HERE, "detector.npz")) // 1024, "KiB")
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "full_spike":
+        make_detector("full_spike")
+        make_detector("full_spike_v2")
+        sys.exit(0)
     make_binning(gen1)
     make_sampler(emb, act)
     make_count(emb)
@@ -365,5 +416,8 @@ if __name__ == "__main__":
     make_psee(gen1)          # (before the two below: load_full_model re-imports yolox without the package stubs)
     make_backbone()
     make_detector()
-    for f in ("binning.npz", "sampler.npz", "count.npz", "letterbox.npz", "backbone.npz", "psee.npz", "detector.npz"):
+    make_detector("full_spike")
+    make_detector("full_spike_v2")
+    for f in ("binning.npz", "sampler.npz", "count.npz", "letterbox.npz", "backbone.npz", "psee.npz", "detector.npz",
+              "detector_full_spike.npz", "detector_full_spike_v2.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

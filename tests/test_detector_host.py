@@ -33,6 +33,35 @@ def test_reference_state_dict_loads_key_for_key():
     assert sum(eas.is_spiking_neuron(m) for m in net.modules()) == sum(k.endswith("act.w") for k in sd)
 
 
+@pytest.mark.parametrize("mode", ["full_spike", "full_spike_v2"])
+def test_full_spike_state_dicts_load_key_for_key(mode):
+    """The reference's ``use_spike full_spike / full_spike_v2`` checkpoints (event_yolox_base.py:207-211): converted
+    pyramid (``lateral_conv0.conv.0.weight``, ``...act.w``) and, for v2, converted head (``stems.0.conv.0.weight``,
+    ``cls_preds.0.0.bias``) -- same names, nothing extra, nothing missing."""
+    z = load_golden("detector_" + mode)
+    meta, sd, hist = detector_case(z)
+    emb = eas.AdaptiveRSNNEmbedding(**detector_sampler_kwargs(meta))
+    net = detector.build_syolox(meta["depth"], meta["width"], meta["num_classes"], meta["T"], embedding=emb,
+                                spike_fn=eas.ATan(meta["alpha"]), use_spike=mode)
+    assert set(net.state_dict()) == set(sd)
+    net.load_state_dict(sd, strict=True)
+    want = ["backbone.lateral_conv0.conv.0.weight", "backbone.C3_p4.m.0.conv2.act.w", "backbone.bu_conv1.bn.running_var"]
+    want += ["head.stems.0.conv.0.weight", "head.cls_convs.1.0.act.w", "head.cls_preds.0.0.bias"] if mode.endswith("v2") \
+        else ["head.stems.0.conv.weight", "head.cls_preds.0.bias"]
+    for k in want:
+        assert k in sd, k
+    n_plif = sum(eas.is_spiking_neuron(m) for m in net.modules())
+    assert n_plif == sum(k.endswith("act.w") for k in sd)
+    # SURVEY 8a-4: the M-sized models have 82 / 97 neurons; the S-sized fixture 58 / 73 (34 backbone + 24 pyramid [+ 15 head])
+    assert n_plif == (73 if mode.endswith("v2") else 58), n_plif
+
+
+def test_syolox_m_full_spike_neuron_counts():
+    for mode, want in (("full_spike", 82), ("full_spike_v2", 97)):       # SURVEY 8a-4 [probe]
+        net = detector.build_syolox(0.67, 0.75, 2, 3, use_spike=mode)
+        assert sum(eas.is_spiking_neuron(m) for m in net.modules()) == want, mode
+
+
 def test_syolox_s_and_m_parameter_counts_match_the_reference_readme():
     # readme.md model table: e-yolox-s 8.94 M, e-yolox-m 25.28 M parameters (SURVEY 8c probe)
     for (d, w, want) in ((0.33, 0.50, 8_938_167), (0.67, 0.75, 25_281_000)):

@@ -132,6 +132,70 @@ def test_postprocess_matches_reference_detections(cuda):
         assert torch.allclose(d.cpu(), torch.from_numpy(z["dets/%d" % i]), rtol=0, atol=1e-5)
 
 
+@pytest.mark.parametrize("mode", ["full_spike", "full_spike_v2"])
+def test_full_spike_detector_golden(cuda, mode):
+    """The configuration the README trains / evaluates SYOLOX-M with (readme.md:136-160): the reference's own
+    ``EventExp.get_model()`` for ``use_spike full_spike`` / ``full_spike_v2`` (event_yolox_base.py:207-211) -- spiking
+    CSPDarknet AND spiking pyramid, ``SpikingYOLOXHead`` -- loaded key for key; the pyramid is compared as spikes
+    (mismatch budget 2e-3 like the backbone golden; measured 0), predictions at the 5e-4 bar of the ANN path."""
+    z = load_golden("detector_" + mode)
+    meta, sd, hist = detector_case(z)
+    assert meta["use_spike"] == mode
+    emb = eas.AdaptiveRSNNEmbedding(**detector_sampler_kwargs(meta))
+    net = detector.build_syolox(meta["depth"], meta["width"], meta["num_classes"], meta["T"], embedding=emb,
+                                spike_fn=eas.ATan(meta["alpha"]), use_spike=mode)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(cuda).eval()
+    hist = hist.to(cuda)
+    frames = net.embed(hist)
+    ok, msg = close_report(frames.cpu(), torch.from_numpy(z["frames"]), rtol=1e-5, atol=1e-5)
+    assert ok, "sampler frames: " + msg
+    pyr = net.backbone(frames)                                     # spikes, logical [T, B, C, H, W]
+    for i, f in enumerate(pyr):
+        want = torch.from_numpy(z["pyramid/%d" % i].astype(np.float32))
+        assert f.shape == want.shape, (f.shape, want.shape)
+        mism = float((f.float().cpu() != want).float().mean())
+        print("%s pyramid %d: spike mismatch %.2e (rate %.3f)" % (mode, i, mism, float(want.mean())))
+        assert mism <= 2e-3, (i, mism)
+    if mode == "full_spike_v2":                                    # spiking towers of the head
+        feats = net.backbone.run(frames)
+        for k, f in enumerate(feats):
+            x = net.head.stems[k].run(f.contiguous(), f.shape[0])
+            c = net.head.cls_convs[k][1].run(net.head.cls_convs[k][0].run(x, f.shape[0]), f.shape[0])
+            want = torch.from_numpy(z["tower/%d/cls" % k].astype(np.float32))
+            mism = float((c.permute(0, 1, 4, 2, 3).float().cpu() != want).float().mean())
+            assert mism <= 2e-3, (k, mism)
+    pred = net(hist)
+    mx, bad = _rel_ok(pred, torch.from_numpy(z["pred"]))
+    print("%s decoded predictions: max rel err %.2e, beyond 5e-4: %.2e" % (mode, mx, bad))
+    assert pred.shape == z["pred"].shape and bad == 0.0, mx
+    net.head.decode_in_inference = False
+    mx, bad = _rel_ok(net(hist), torch.from_numpy(z["raw"]))
+    assert bad == 0.0, mx
+    net.head.decode_in_inference = True
+    # the reference-shaped head entry: spikes [T, B, C, H, W] per level
+    mx, bad = _rel_ok(net.head([torch.from_numpy(z["pyramid/%d" % i].astype(np.float32)).to(cuda) for i in range(3)]),
+                      torch.from_numpy(z["pred"]))
+    assert bad == 0.0, mx
+    dets = detector.postprocess(pred, meta["num_classes"], conf_thre=meta["conf_thre"], nms_thre=meta["nms_thre"])
+    for i, d in enumerate(dets):
+        want = torch.from_numpy(z["dets/%d" % i])
+        got = torch.zeros((0, 7)) if d is None else d.cpu()
+        assert got.shape == want.shape, (i, got.shape, want.shape)
+        ok, msg = close_report(got, want, rtol=1e-3, atol=1e-3)
+        assert ok, msg
+
+
+def test_upsample2x_spikes_into_slice(cuda):
+    g = torch.Generator().manual_seed(5)
+    T, B, H, W, C = 3, 2, 4, 5, 16
+    src = (torch.rand((T, B, H, W, C), generator=g) < 0.3).half().to(cuda)
+    dst = torch.full((T, B, 2 * H, 2 * W, 2 * C), -3.0, dtype=torch.float16, device=cuda)
+    detector.upsample2x_spikes(src, dst[..., :C])
+    want = src.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+    assert torch.equal(dst[..., :C], want) and bool((dst[..., C:] == -3).all())
+
+
 def test_detector_s_vs_oracle_from_events(cuda):
     """SYOLOX-S on one Gen1-shaped window (240x304 events, frames zero-padded to 256x320): raw events -> bins ->
     sampler -> detector through the product API vs the oracle restatement with the same weights."""
