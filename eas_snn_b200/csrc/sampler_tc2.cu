@@ -87,6 +87,12 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifdef EAS_TC2_DIAG
+// Development aid (-DEAS_TC2_DIAG): a wait that times out records (barrier offset, parity, warp, block) and releases
+// every other wait, so that a dead-locked launch ends and eas_debug_tc2_diag() can tell who was stuck.
+__device__ unsigned int g_diag[64];
+__device__ volatile int g_abort;
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0, spins = 0;
@@ -99,7 +105,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (ok) break;
+#ifdef EAS_TC2_DIAG
+    if (g_abort) break;
+    if (++spins > (1u << 18)) {
+      if ((threadIdx.x & 31) == 0) {
+        const unsigned int slot = atomicAdd(&g_diag[0], 1u);
+        if (slot < 20) {
+          g_diag[1 + 3 * slot] = addr & 0xfff;          // barrier offset inside the barrier block
+          g_diag[2 + 3 * slot] = (parity << 16) | (threadIdx.x >> 5);
+          g_diag[3 + 3 * slot] = blockIdx.x;
+        }
+      }
+      g_abort = 1;
+      break;
+    }
+#else
     if (++spins > SPIN_LIMIT) __trap();  // watchdog: trap instead of hanging the GPU
+#endif
   }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -523,12 +545,14 @@ sampler_tc2_step_kernel(const StepArgs a, const Tc2State st, const Tc2Geo g, con
       if (leader) {
         tc_commit(d1_full + buf);
         tc_commit(x0_empty + slot);
-        if (k == s1.nt1 - 1)
-          for (int kk = s1.nt1; kk < s1.nt0; ++kk) tc_commit(x0_empty + ((g0 + kk) & 1));
       }
       if (++k1 == s1.nt1) {
-        // chunks of trailing X0 tiles that no hidden tile waited for
+        // A trailing X0 tile (only its first chunk was an operand) is freed here -- but only once ALL its chunks
+        // have been written: a producer that has not yet passed its wait for this slot would otherwise see the
+        // slot's barrier two phases ahead (parity aliasing) and wait forever.
         while (w0 < (g0 + s1.nt0) * 4) mbar_wait(x0_full + (w0 & 7), (w0 >> 3) & 1), ++w0;
+        if (leader)
+          for (int kk = s1.nt1; kk < s1.nt0; ++kk) tc_commit(x0_empty + ((g0 + kk) & 1));
         g0 += s1.nt0, g1a += s1.nt1, k1 = 0;
         more1 = it1.next(s1);
       }
@@ -574,11 +598,12 @@ sampler_tc2_step_kernel(const StepArgs a, const Tc2State st, const Tc2Geo g, con
         if (leader) {
           tc_commit(d2_full + buf);
           tc_commit(x1_empty + slot);
-          if (k == s2.nt2 - 1)
-            for (int kk = s2.nt2; kk < s2.nt1; ++kk) tc_commit(x1_empty + ((g1b + kk) & 1));
         }
         if (++k2 == s2.nt2) {
+          // trailing X1 tile: freed only after all of its chunks were written (see the X0 ring above)
           while (w1 < (g1b + s2.nt1) * 4) mbar_wait(x1_full + (w1 & 7), (w1 >> 3) & 1), ++w1;
+          if (leader)
+            for (int kk = s2.nt2; kk < s2.nt1; ++kk) tc_commit(x1_empty + ((g1b + kk) & 1));
           g1b += s2.nt1, g2 += s2.nt2, k2 = 0;
           more2 = it2.next(s2);
         }
@@ -717,7 +742,7 @@ sampler_tc2_step_kernel(const StepArgs a, const Tc2State st, const Tc2Geo g, con
       mbar_wait(d2_full + buf, (gk >> 1) & 1);
       if (warp == 0) TC2_TRACE(4, 1, gk);
       tc_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (int d = 0; d < 2; ++d) {
         const int dy = 2 * hf + d;
         float pre[8];  // [px][gate, current], still x 2^8
@@ -905,6 +930,19 @@ int eas_sampler_tc2_run(const eas_sampler_cfg* cfg, StepArgs a, uint8_t* meta8, 
 }
 
 }  // namespace eas_sampler
+
+#ifdef EAS_TC2_DIAG
+extern "C" int eas_debug_tc2_diag(unsigned int* out) {
+  using namespace eas_sampler;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_diag, sizeof(unsigned int) * 64);
+  unsigned int zero[64] = {0};
+  int z = 0;
+  cudaMemcpyToSymbol(g_diag, zero, sizeof(zero));
+  cudaMemcpyToSymbol(g_abort, &z, sizeof(int));
+  return (int)(OFF_BAR & 0xfff);
+}
+#endif
 
 #ifdef EAS_TC2_TRACE
 // development aid: copies the trace (5 roles x TRACE_PER_ROLE records, then 5 counts) to the host and resets it

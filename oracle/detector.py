@@ -1,4 +1,5 @@
-"""Oracle (TEST INFRASTRUCTURE): the whole SYOLOX detector of ``use_spike True``, PyTorch fp32 restatement.
+"""Oracle (TEST INFRASTRUCTURE): the whole SYOLOX detector (``use_spike True`` and the two ``full_spike`` variants),
+PyTorch fp32 restatement.
 
 Follows, with the reference's child names (so its ``state_dict`` loads with ``strict=True``):
   * ``SpikingYOLOPAFPN.forward`` (``yolox/models/spiking_yolo_pafpn.py:89-120``): spiking CSPDarknet
@@ -8,6 +9,10 @@ Follows, with the reference's child names (so its ``state_dict`` loads with ``st
   * ``SpikingYOLOX.forward`` (``yolox/models/spiking_yolox.py:38-74``);
   * ``postprocess`` (``yolox/utils/boxes.py:33-77``) lives in the product (torchvision NMS) and is compared on
     identical predictions.
+  * ``use_spike full_spike / full_spike_v2`` (``yolox/exp/event_yolox_base.py:207-211``): the whole ``YOLOPAFPN``
+    (``yolo_pafpn.py:16-116``) converted by ``convert_to_spiking`` (``utils_snn.py:16-58``) and ``SpikingYOLOXHead``
+    (``spiking_yolo_head.py:18-230``): time mean in front of an ANN head, or spiking towers with the time mean after
+    the 1x1 predictors (:159-178).  PINNED by ``tests/golden/detector_full_spike{,_v2}.npz``.
 PINNED by ``tests/golden/detector.npz``: the reference's own ``EventExp.get_model()`` (tiny width) run through
 ``oracle/sj_shim`` (the neuron inside stays the unpinned spikingjelly restatement, see ``oracle/plif.py``).
 """
@@ -18,7 +23,7 @@ import math
 import torch
 import torch.nn as nn
 
-from .backbone import SpikingCSPDarknet, _AnnBaseConv, reset_net
+from .backbone import SpikingBaseConv, SpikingCSPDarknet, SpikingCSPLayer, _AnnBaseConv, _Seq, reset_net
 
 
 class _Bottleneck(nn.Module):
@@ -110,15 +115,93 @@ class OracleYOLOXHead(nn.Module):
         return torch.cat([(out[..., 0:2] + g) * s, torch.exp(out[..., 2:4]) * s, out[..., 4:]], dim=-1)
 
 
+class OracleFullSpikeYOLOPAFPN(nn.Module):
+    """``convert_to_spiking(YOLOPAFPN(...))``: every BaseConv is conv -> BN -> PLIF on [T, B, C, H, W] (cat on dim -3)."""
+
+    def __init__(self, depth, width, in_features=("dark3", "dark4", "dark5"), in_channels=(256, 512, 1024), in_dim=2,
+                 spike_fn=None):
+        super().__init__()
+        self.backbone = SpikingCSPDarknet(depth, width, in_dim=in_dim, spike_fn=spike_fn, out_features=in_features)
+        self.in_features = in_features
+        c0, c1, c2 = (int(c * width) for c in in_channels)
+        n = round(3 * depth)
+        self.upsample = _Seq(nn.Upsample(scale_factor=2, mode="nearest"))
+        self.lateral_conv0 = SpikingBaseConv(c2, c1, 1, 1, spike_fn)
+        self.C3_p4 = SpikingCSPLayer(2 * c1, c1, n, False, spike_fn)
+        self.reduce_conv1 = SpikingBaseConv(c1, c0, 1, 1, spike_fn)
+        self.C3_p3 = SpikingCSPLayer(2 * c0, c0, n, False, spike_fn)
+        self.bu_conv2 = SpikingBaseConv(c0, c0, 3, 2, spike_fn)
+        self.C3_n3 = SpikingCSPLayer(2 * c0, c1, n, False, spike_fn)
+        self.bu_conv1 = SpikingBaseConv(c1, c1, 3, 2, spike_fn)
+        self.C3_n4 = SpikingCSPLayer(2 * c1, c2, n, False, spike_fn)
+
+    def forward(self, x_seq):
+        outs = self.backbone(x_seq)
+        x2, x1, x0 = (outs[f] for f in self.in_features)
+        fpn_out0 = self.lateral_conv0(x0)
+        f_out0 = self.C3_p4(torch.cat([self.upsample(fpn_out0), x1], -3))
+        fpn_out1 = self.reduce_conv1(f_out0)
+        pan_out2 = self.C3_p3(torch.cat([self.upsample(fpn_out1), x2], -3))
+        pan_out1 = self.C3_n3(torch.cat([self.bu_conv2(pan_out2), fpn_out1], -3))
+        pan_out0 = self.C3_n4(torch.cat([self.bu_conv1(pan_out1), fpn_out0], -3))
+        return pan_out2, pan_out1, pan_out0
+
+
+class OracleSpikingYOLOXHead(OracleYOLOXHead):
+    """``SpikingYOLOXHead``: ``full_spike=False`` averages every level over T in front of the ANN head
+    (spiking_yolo_head.py:159-160); ``full_spike=True`` converts stems / towers to conv -> BN -> PLIF, wraps the 1x1
+    predictors per time step and averages their outputs over T (:125-127, :173-178)."""
+
+    def __init__(self, num_classes, width=1.0, strides=(8, 16, 32), in_channels=(256, 512, 1024), spike_fn=None,
+                 full_spike=False):
+        super().__init__(num_classes, width, strides, in_channels)
+        self.full_spike = full_spike
+        if full_spike:
+            hid = int(256 * width)
+            self.stems = nn.ModuleList(SpikingBaseConv(int(c * width), hid, 1, 1, spike_fn) for c in in_channels)
+            self.cls_convs = nn.ModuleList(nn.Sequential(SpikingBaseConv(hid, hid, 3, 1, spike_fn),
+                                                         SpikingBaseConv(hid, hid, 3, 1, spike_fn)) for _ in in_channels)
+            self.reg_convs = nn.ModuleList(nn.Sequential(SpikingBaseConv(hid, hid, 3, 1, spike_fn),
+                                                         SpikingBaseConv(hid, hid, 3, 1, spike_fn)) for _ in in_channels)
+            for name in ("cls_preds", "reg_preds", "obj_preds"):
+                setattr(self, name, nn.ModuleList(_Seq(m) for m in getattr(self, name)))
+
+    def forward(self, xin, decode=True):
+        if not self.full_spike:
+            return super().forward([x.mean(axis=0) for x in xin], decode)
+        outs, grids, strides = [], [], []
+        for k, x in enumerate(xin):
+            x = self.stems[k](x)
+            cls_feat, reg_feat = self.cls_convs[k](x), self.reg_convs[k](x)
+            o = torch.cat([self.reg_preds[k](reg_feat).mean(axis=0), self.obj_preds[k](reg_feat).mean(axis=0).sigmoid(),
+                           self.cls_preds[k](cls_feat).mean(axis=0).sigmoid()], 1)
+            h, w = o.shape[-2:]
+            yv, xv = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+            grids.append(torch.stack((xv, yv), 2).view(1, -1, 2).float())
+            strides.append(torch.full((1, h * w, 1), float(self.strides[k])))
+            outs.append(o.flatten(start_dim=2))
+        out = torch.cat(outs, dim=2).permute(0, 2, 1)
+        if not decode:
+            return out
+        g, s = torch.cat(grids, 1), torch.cat(strides, 1)
+        return torch.cat([(out[..., 0:2] + g) * s, torch.exp(out[..., 2:4]) * s, out[..., 4:]], dim=-1)
+
+
 class OracleSpikingYOLOX(nn.Module):
-    def __init__(self, depth, width, num_classes, T, embedding=None, spike_fn=None):
+    def __init__(self, depth, width, num_classes, T, embedding=None, spike_fn=None, use_spike=True):
         super().__init__()
         self.nb_steps = T
         self.embedding = embedding
-        self.backbone = OracleSpikingYOLOPAFPN(depth, width, spike_fn=spike_fn)
-        self.head = OracleYOLOXHead(num_classes, width)
-        for conv in list(self.head.cls_preds) + list(self.head.obj_preds):
-            conv.bias.data.fill_(-math.log((1 - 1e-2) / 1e-2))
+        if use_spike is True:
+            self.backbone = OracleSpikingYOLOPAFPN(depth, width, spike_fn=spike_fn)
+            self.head = OracleYOLOXHead(num_classes, width)
+        else:
+            self.backbone = OracleFullSpikeYOLOPAFPN(depth, width, spike_fn=spike_fn)
+            self.head = OracleSpikingYOLOXHead(num_classes, width, spike_fn=spike_fn, full_spike="v2" in use_spike)
+        for ml in (self.head.cls_preds, self.head.obj_preds):
+            for m in ml.modules():
+                if isinstance(m, nn.Conv2d):
+                    m.bias.data.fill_(-math.log((1 - 1e-2) / 1e-2))
 
     def detect_frames(self, frames):
         """frames [Ts or T, B, 2, H, W] -> decoded predictions [B, A, 5 + nc]."""

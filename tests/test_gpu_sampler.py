@@ -204,6 +204,26 @@ def test_auto_falls_back_beyond_fp16_range(cuda):
             assert ok, msg
 
 
+def test_back_to_back_forwards_are_deterministic_and_do_not_stall(cuda):
+    """Stress: hundreds of forwards queued without a host sync in between (the way bench.py and a serving loop drive the
+    kernel).  The warp-specialised kernels hand tiles over through mbarriers; an ordering bug there shows up as a
+    watchdog trap (launch failure) or as run-to-run differences only under this kind of back-to-back load -- a
+    trailing-tile parity aliasing in the row-folded kernel was found exactly this way."""
+    torch.manual_seed(11)
+    kw = dict(kernel_size=5, depth=2, nb_steps=4, thresh=1, vreset=0, Ts=1, write_zero=True, spike_attach=True)
+    m = eas.AdaptiveRSNNEmbedding(**kw).to(cuda)
+    for shape in ((64, 4, 240, 304), (7, 4, 61, 100), (16, 4, 360, 640)):
+        x = torch.poisson(torch.full(shape[:2] + (2,) + shape[2:], 0.8)).to(cuda)
+        for algo in ("tensor", "tensor_split"):
+            m.algo = algo
+            with torch.no_grad():
+                first = m(x).clone()
+                for _ in range(150):
+                    out = m(x)
+            torch.cuda.synchronize()
+            assert torch.equal(out, first), (shape, algo)
+
+
 def test_1mpx_rvt_layout_event_sum_and_sampler(cuda):
     """BASELINE config 3: RVT-preprocessed uint8 [n, 20, 360, 640] -> 'event_sum' counts (rvt_gen4.py:120-122,
     bit-exact vs numpy) -> Tm consecutive slices as the sampler's steps at 360x640 (6 strips of the

@@ -116,6 +116,32 @@ def test_detector_golden():
     assert torch.allclose(raw, torch.from_numpy(z["raw"]), rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("mode", ["full_spike", "full_spike_v2"])
+def test_full_spike_detector_golden(mode):
+    """oracle.detector's restatement of ``use_spike full_spike / full_spike_v2`` (event_yolox_base.py:207-211) loads the
+    reference model's state_dict key for key and reproduces its spiking pyramid bit for bit and its predictions."""
+    from oracle import detector
+    from helpers import detector_case, detector_sampler_kwargs
+    z = load_golden("detector_" + mode)
+    meta, sd, hist = detector_case(z)
+    emb = sampler.OracleSampler(**detector_sampler_kwargs(meta))
+    net = detector.OracleSpikingYOLOX(meta["depth"], meta["width"], meta["num_classes"], meta["T"], embedding=emb,
+                                      spike_fn=ATan(meta["alpha"]), use_spike=mode)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    with torch.no_grad():
+        frames = net.embedding(hist)
+        assert torch.equal(frames, torch.from_numpy(z["frames"]))
+        pyr = net.backbone(frames.expand(meta["T"], -1, -1, -1, -1).contiguous())
+        for i, f in enumerate(pyr):
+            assert torch.equal(f, torch.from_numpy(z["pyramid/%d" % i].astype(np.float32))), i
+        raw = net.head(pyr, decode=False)
+        backbone.reset_net(net)
+        pred = net(hist)
+    assert torch.allclose(pred, torch.from_numpy(z["pred"]), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(raw, torch.from_numpy(z["raw"]), rtol=1e-5, atol=1e-5)
+
+
 def test_spike_count_golden():
     z = load_golden("count")
     for k in ("5", "6", "4"):
