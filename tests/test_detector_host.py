@@ -101,3 +101,22 @@ def test_pad_frames_and_postprocess_match_the_reference_detections():
     ag = detector.postprocess(pred, meta["num_classes"], meta["conf_thre"], meta["nms_thre"], class_agnostic=True)
     assert all(a is not None and len(a) <= len(d) for a, d in zip(ag, dets))
     assert detector.postprocess(pred, meta["num_classes"], conf_thre=2.0) == [None, None]
+
+
+def test_convert_to_spiking_gives_the_reference_checkpoint_layout():
+    """``fused.convert_to_spiking`` (the seam INTEGRATION.md Level 1 names; utils_snn.py:16-58) on a plain ANN
+    CSPDarknet: every BaseConv becomes the fused conv+BN+PLIF layer, Focus is wrapped whole and stays ANN, lone
+    MaxPool2d are wrapped -- and the result carries exactly the keys of the REFERENCE's converted backbone
+    (tests/golden/backbone.npz, produced by the reference's own convert_to_spiking)."""
+    from eas_snn_b200 import fused
+    from helpers import AnnCSPDarknet
+    z = load_golden("backbone")
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    net = fused.convert_to_spiking(AnnCSPDarknet(0.33, 0.125, in_dim=2), eas.ATan(2.0))
+    assert set(net.state_dict()) == set(sd)
+    net.load_state_dict(sd, strict=True)
+    assert isinstance(net.stem, fused.SeqToANNContainer) and type(net.stem[0]).__name__ == "Focus"
+    assert isinstance(net.stem[0].conv.act, torch.nn.SiLU)                  # the stem stays ANN (utils_snn.py:23-24)
+    n_fused = sum(isinstance(m, fused.FusedConvBNPLIF) for m in net.modules())
+    assert n_fused == sum(eas.is_spiking_neuron(m) for m in net.modules()) == 34
+    assert all(isinstance(m, fused.SeqToANNContainer) for m in net.dark5[1].m)

@@ -286,3 +286,25 @@ def test_focus_im2col_and_stem_match_torch(cuda):
     ok, msg = close_report(gotp, want, rtol=1e-5, atol=1e-5)
     print("stem via im2col:", msg)
     assert ok, msg
+
+
+def test_convert_to_spiking_model_reproduces_the_reference_backbone_golden(cuda):
+    """The drop-in seam end to end: a plain ANN CSPDarknet -> ``fused.convert_to_spiking`` -> the reference's converted
+    weights (backbone.npz, strict) -> its own module-by-module forward on [T, B, C, H, W] (each fused layer runs the
+    tensor-core kernel, Focus / pools / concatenations / SEW adds stay PyTorch) -> the reference's spikes."""
+    from eas_snn_b200 import fused
+    from helpers import AnnCSPDarknet, load_golden
+    z = load_golden("backbone")
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    net = fused.convert_to_spiking(AnnCSPDarknet(0.33, 0.125, in_dim=2), eas.ATan(2.0))
+    net.load_state_dict(sd, strict=True)
+    net = net.to(cuda).eval()
+    x = torch.from_numpy(z["x"]).to(cuda)
+    with torch.no_grad():
+        outs = net(x)
+    eas.reset_net(net)
+    for k, v in outs.items():
+        want = torch.from_numpy(z["out/" + k].astype(np.float32))
+        mism = float((v.float().cpu() != want).float().mean())
+        print("convert_to_spiking", k, "spike mismatch %.2e (rate %.3f)" % (mism, float(want.mean())))
+        assert v.shape == want.shape and mism <= 2e-3, (k, mism)
