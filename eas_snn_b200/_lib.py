@@ -72,6 +72,7 @@ SIGNATURES = {
     "eas_conv_bn_plif_ws_bytes": (C.c_size_t, [C.POINTER(ConvCfg)]),
     "eas_conv_bn_plif_fwd": (C.c_int, [C.POINTER(ConvCfg), _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "eas_rvt_event_sum": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "eas_voxel_grid": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "eas_spp_pool_fwd": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "eas_time_mean_planes": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, C.c_int, _P, C.c_int, C.c_int64, _P]),
     "eas_upsample2x_planes": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _P,

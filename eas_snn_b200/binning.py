@@ -92,6 +92,30 @@ def rvt_event_sum(repr_u8: torch.Tensor, n_bins: int = 10) -> torch.Tensor:
     return out
 
 
+def voxel_grid(x, y, t, p, offsets, H: int, W: int, n_bins: int = 10, polarity: str = "reference") -> torch.Tensor:
+    """Voxel grids with bilinear interpolation in time (``to_voxel_grid_numpy``, ``yolox/utils/event_reps.py:30-89``) of
+    B event windows (same SoA layout as :func:`bin_events`) -> ``float32 [B, n_bins, 1, H, W]`` (the reference returns
+    ``(n_bins, 1, H, W)`` per window).  ``polarity``: ``"reference"`` reproduces what the reference computes on its own
+    ``events_struct`` dtype, where ``p`` is bool and ``pols[pols == 0] = -1`` stores True -- every event counts +1
+    (event_reps.py:62-63); ``"signed"`` is the +1 / -1 weighting its comment intends (and what it computes when ``p``
+    is a signed integer field)."""
+    if polarity not in ("reference", "signed"):
+        raise ValueError("polarity must be 'reference' or 'signed'")
+    _lib.require_cuda(x, y, t, p, offsets)
+    if x.dtype != torch.int16 or y.dtype != torch.int16 or t.dtype != torch.int64 or p.dtype not in (torch.uint8, torch.bool) \
+            or offsets.dtype != torch.int64:
+        raise TypeError("expected x,y int16, t int64, p uint8/bool, offsets int64")
+    B = offsets.numel() - 1
+    out = torch.empty((B, n_bins, 1, H, W), dtype=torch.float32, device=x.device)
+    p8 = p.view(torch.uint8) if p.dtype == torch.bool else p
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().eas_voxel_grid(_lib.ptr(x.contiguous()), _lib.ptr(y.contiguous()), _lib.ptr(t.contiguous()),
+                                       _lib.ptr(p8.contiguous()), _lib.ptr(offsets.contiguous()), B, x.numel(), H, W, n_bins,
+                                       int(polarity == "signed"), _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "eas_voxel_grid")
+    return out
+
+
 _TAPS: dict = {}
 
 

@@ -179,3 +179,62 @@ extern "C" int eas_letterbox_bilinear(const void* in, int in_dtype, int64_t n_pl
   EAS_LAUNCH_CHECK();
   return EAS_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// (f-4) Voxel grid with bilinear interpolation in time: to_voxel_grid_numpy, yolox/utils/event_reps.py:30-89
+// (Zhu et al. 2019).  Per window: ts = n_bins * (t - t_first) / (t_last - t_first) in float64 like the reference,
+// ti = int(ts), dt = ts - ti; the event adds pol * (1 - dt) to bin ti (if ti < n_bins) and pol * dt to bin ti + 1 (if
+// ti + 1 < n_bins) of its pixel -- np.add.at, here fp32 reductions into the zero-filled grid.
+// signed_polarity = 1: pol = +1 / -1, what the reference's comment says ("polarity should be +1 / -1").
+// signed_polarity = 0: pol = +1 for every event -- what the reference COMPUTES on its own event dtype: p is a bool
+// field (events_struct, yolox/utils/util.py:119-121) and `pols[pols == 0] = -1` stores bool(-1) = True (:62-63).
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+voxel_grid_kernel(const int16_t* __restrict__ x, const int16_t* __restrict__ y, const int64_t* __restrict__ t,
+                  const uint8_t* __restrict__ p, const int64_t* __restrict__ offsets, int64_t B, int64_t n, int H, int W,
+                  int n_bins, int signed_polarity, float* __restrict__ out) {
+  const int64_t HW = (int64_t)H * W;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int64_t lo = 0, hi = B;   // window of event i: offsets[lo] <= i < offsets[hi]
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (offsets[mid] <= i) lo = mid;
+      else hi = mid;
+    }
+    const int64_t s = offsets[lo], e = offsets[lo + 1];
+    if (i < s || i >= e) continue;
+    const int64_t t0 = t[s], t1 = t[e - 1];
+    if (t1 == t0) continue;   // the reference divides by zero here (NaN bins); such a window stays all zero
+    const int xi = x[i], yi = y[i];
+    if ((unsigned)xi >= (unsigned)W || (unsigned)yi >= (unsigned)H) continue;
+    const double ts = (double)n_bins * (double)(t[i] - t0) / (double)(t1 - t0);
+    const int ti = (int)ts;
+    const double dt = ts - (double)ti;
+    const double pol = (signed_polarity && p[i] == 0) ? -1.0 : 1.0;
+    float* cell = out + ((int64_t)lo * n_bins + ti) * HW + (int64_t)yi * W + xi;
+    if (ti < n_bins) atomicAdd(cell, (float)(pol * (1.0 - dt)));
+    if (ti + 1 < n_bins) atomicAdd(cell + HW, (float)(pol * dt));
+  }
+}
+}  // namespace
+
+extern "C" int eas_voxel_grid(const int16_t* x, const int16_t* y, const int64_t* t, const uint8_t* p,
+                              const int64_t* offsets, int64_t B, int64_t n_events, int H, int W, int n_bins,
+                              int signed_polarity, float* out, void* stream) {
+  EAS_REQUIRE(B >= 0 && n_events >= 0 && H > 0 && W > 0 && n_bins > 0, EAS_E_SHAPE);
+  if (B == 0) return EAS_OK;
+  EAS_REQUIRE(offsets && out, EAS_E_NULL);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * n_bins * H * W, st);
+  if (e != cudaSuccess) return (int)e;
+  if (n_events == 0) return EAS_OK;
+  EAS_REQUIRE(x && y && t && p, EAS_E_NULL);
+  int64_t grid = eas_ceil_div(n_events, 256 * 4);
+  if (grid > 8 * EAS_NUM_SMS) grid = 8 * EAS_NUM_SMS;
+  voxel_grid_kernel<<<(unsigned)grid, 256, 0, st>>>(x, y, t, p, offsets, B, n_events, H, W, n_bins, signed_polarity, out);
+  EAS_LAUNCH_CHECK();
+  return EAS_OK;
+}

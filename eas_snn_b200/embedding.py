@@ -38,35 +38,41 @@ def _pack_ptrs(tensors):
     return s
 
 
+def _sampler_forward(events, mod, params, want_seq):
+    """One ``eas_sampler_fwd`` call.  params: in_w0, in_b0, [in_w1, in_b1], gate_w0, gate_b0, [gate_w1, gate_b1].
+    Returns (out [Ts,B,2,H,W], v_seq, gate_seq ([Tm,B,2,H,W] each, sampler step order, or None), cfg, plist)."""
+    L = _lib.lib()
+    B, Tm, Cc, H, W = events.shape
+    in_dtype = _lib.EAS_I32 if events.dtype == torch.int32 else _lib.EAS_F32
+    cfg = _cfg(B, H, W, Tm, mod, in_dtype)
+    if mod.depth == 2:
+        iw0, ib0, iw1, ib1, gw0, gb0, gw1, gb1 = params
+    else:
+        iw0, ib0, gw0, gb0 = params
+        iw1 = ib1 = gw1 = gb1 = None
+    plist = [iw0, ib0, iw1, ib1, gw0, gb0, gw1, gb1]
+    plist = [None if q is None else q.detach().contiguous().float() for q in plist]
+    wstruct = _pack_ptrs(plist)
+    dev = events.device
+    out = torch.empty((mod.Ts, B, 2, H, W), dtype=torch.float32, device=dev)
+    v_seq = gate_seq = None
+    if want_seq:
+        v_seq = torch.empty((Tm, B, 2, H, W), dtype=torch.float32, device=dev)
+        gate_seq = torch.empty_like(v_seq)
+    ws_bytes = L.eas_sampler_fwd_ws_bytes(C.byref(cfg))
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.eas_sampler_fwd(C.byref(cfg), _lib.ptr(events), C.byref(wstruct), _lib.ptr(out),
+                               _lib.ptr(v_seq), _lib.ptr(gate_seq), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+    _lib.check(rc, "eas_sampler_fwd")
+    return out, v_seq, gate_seq, cfg, plist
+
+
 class _SamplerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, events, mod, *params):
-        # params: in_w0, in_b0, [in_w1, in_b1], gate_w0, gate_b0, [gate_w1, gate_b1]
-        L = _lib.lib()
-        B, Tm, Cc, H, W = events.shape
-        in_dtype = _lib.EAS_I32 if events.dtype == torch.int32 else _lib.EAS_F32
-        cfg = _cfg(B, H, W, Tm, mod, in_dtype)
-        if mod.depth == 2:
-            iw0, ib0, iw1, ib1, gw0, gb0, gw1, gb1 = params
-        else:
-            iw0, ib0, gw0, gb0 = params
-            iw1 = ib1 = gw1 = gb1 = None
-        plist = [iw0, ib0, iw1, ib1, gw0, gb0, gw1, gb1]
-        plist = [None if q is None else q.detach().contiguous().float() for q in plist]
-        wstruct = _pack_ptrs(plist)
         need_grad = any(ctx.needs_input_grad)   # grad mode is off inside Function.forward: ask the ctx
-        dev = events.device
-        out = torch.empty((mod.Ts, B, 2, H, W), dtype=torch.float32, device=dev)
-        v_seq = gate_seq = None
-        if need_grad:
-            v_seq = torch.empty((Tm, B, 2, H, W), dtype=torch.float32, device=dev)
-            gate_seq = torch.empty_like(v_seq)
-        ws_bytes = L.eas_sampler_fwd_ws_bytes(C.byref(cfg))
-        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
-            rc = L.eas_sampler_fwd(C.byref(cfg), _lib.ptr(events), C.byref(wstruct), _lib.ptr(out),
-                                   _lib.ptr(v_seq), _lib.ptr(gate_seq), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
-        _lib.check(rc, "eas_sampler_fwd")
+        out, v_seq, gate_seq, cfg, plist = _sampler_forward(events, mod, params, need_grad)
         if need_grad:
             ctx.mod, ctx.cfg, ctx.plist = mod, cfg, plist
             ctx.save_for_backward(events, v_seq, gate_seq)
@@ -166,9 +172,6 @@ class AdaptiveRSNNEmbedding(nn.Module):
         return out
 
     def forward(self, events, record=False, v_record=False):
-        if record or v_record:
-            raise NotImplementedError("record / v_record are analysis-only outputs of the reference "
-                                      "(embedding.py:198-199, 221-224) and are not produced by the fused kernel")
         if events.dim() < 5:  # parameter-registering passthrough (embedding.py:144-146)
             events, _ = torch.broadcast_tensors(events, torch.zeros((self.Ts,) + events.shape,
                                                                     device=events.device))
@@ -181,7 +184,33 @@ class AdaptiveRSNNEmbedding(nn.Module):
         if events.dtype not in (torch.float32, torch.int32):
             events = events.float()
         events = events.contiguous()
+        if record or v_record:
+            return self._forward_with_record(events, record)
         return _SamplerFn.apply(events, self, *self._params())
+
+    @torch.no_grad()
+    def _forward_with_record(self, events, record: bool):
+        """The reference's analysis outputs (embedding.py:180, 198-199, 221-224; the Fig. 4 study, readme.md:162):
+        ``record`` -> (frames, t_last history ``[steps, B, 2, H, W]`` int64), ``v_record`` -> (frames, the
+        sub-threshold potentials of every step, concatenated).  Both are derived from the per-step potentials the
+        kernel saves for training (``v_seq``); the bookkeeping is replayed with a few tensor ops (analysis path)."""
+        out, v_seq, _, _, _ = _sampler_forward(events, self, self._params(), True)
+        Tm = v_seq.shape[0]
+        spikes = (v_seq - float(self.thresh)) > 0                      # Rectangle.forward, activation.py:21-23
+        seg = torch.zeros_like(v_seq[0], dtype=torch.int64)
+        t_last = torch.full_like(seg, -1)
+        t_rec, v_rec = [], []
+        for t in range(Tm):
+            v_rec.append(v_seq[t][~spikes[t]])
+            valid = spikes[t] & (seg < self.Ts)
+            seg = seg + valid.long()
+            t_last = torch.where(valid, torch.full_like(t_last, t), t_last)
+            t_rec.append(t_last.clone())
+            if int(seg.min()) >= self.Ts:                              # the reference's early break (:200-201)
+                break
+        if record:
+            return out, torch.stack(t_rec, dim=0)
+        return out, torch.cat(v_rec)
 
     def forward_events(self, x, y, t, p, offsets, H: int, W: int, strategy: str = "auto"):
         """Raw time-sorted event windows -> adaptive frames ``[Ts, B, 2, H, W]``.
@@ -234,3 +263,164 @@ class SpikeCountEmbedding(nn.Module):
         """Raw windows -> count frames ``[B, 2, H, W]``: binning (gen1.py:313-360) + the sum over micro-bins."""
         from .binning import bin_events
         return self.forward(bin_events(x, y, t, p, offsets, H, W, self.nb_steps))
+
+
+class _SeqReadoutEmbedding(nn.Module):
+    """Shared host side of the two ablation embeddings: both are the sampler's recurrence without the
+    spike-triggered aggregation, read out as the sum over the steps of the pre-reset potential (``readout='sum'``)
+    or as the final membrane potential (``'last'``).  They run on ``eas_sampler_fwd`` and read the per-step potentials
+    it saves (``v_seq``).  Inference only (the surrogate backward of these read-outs is not built)."""
+
+    Ts = 1
+    spike_attach = False
+    write_zero = True
+    abs = False
+    algo = "auto"
+
+    def _prep(self, events):
+        if events.dim() < 5:   # parameter-registering input: nb_steps copies of one frame (embedding.py:44-45, :287-288)
+            events = events.unsqueeze(0).expand((self.nb_steps,) + tuple(events.shape)).transpose(0, 1)
+        elif events.dim() > 5:
+            events = events.flatten(end_dim=-5)
+        _lib.require_cuda(events)
+        if events.shape[2] != 2:
+            raise ValueError("expected [B, Tm, 2, H, W] micro-bin tensor")
+        if events.dtype not in (torch.float32, torch.int32):
+            events = events.float()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError("%s: inference only on the sm_100a path" % type(self).__name__)
+        return events.contiguous()
+
+    def _readout(self, v_seq, relu=False):
+        if self.readout == "sum":
+            agg = v_seq[0].clone()
+            for t in range(1, v_seq.shape[0]):        # same order as the reference's running sum
+                agg += v_seq[t]
+        elif self.readout == "last":
+            v = v_seq[-1]
+            s = ((v - float(self.thresh)) > 0).float()
+            agg = v - float(self.thresh) * s if self.vreset is None else v * (1 - s) + float(self.vreset) * s
+        else:
+            raise NotImplementedError(self.readout)
+        return torch.relu(agg) if relu else agg
+
+
+class SpikingEmbedding(_SeqReadoutEmbedding):
+    """``SpikingEmbedding`` (``embedding: rsnn``; yolox/models/embedding.py:229-316): the gated recurrent spiking layer
+    of the adaptive sampler (same ``update``, :276-283; same convolutions, the input stack wrapped in ``tdLayer`` ->
+    keys ``input_conv.layer.{0,2}.*``) whose output is sum_t v_t or the last membrane potential, ``[B*Tl, 2, H, W]``."""
+
+    def __init__(self, kernel_size, in_channel=2, out_channel=2, readout="sum", relu=False, depth=1, **kwargs_spikes):
+        super().__init__()
+        if in_channel != 2 or out_channel != 2 or int(depth) not in (1, 2) or int(kernel_size) not in (3, 5, 7):
+            raise NotImplementedError("sampler kernels: 2 polarity channels, depth in {1,2}, kernel_size in {3,5,7}")
+        fn = kwargs_spikes.get("spike_fn", None)
+        if fn is not None and getattr(fn, "__name__", type(fn).__name__) != "Rectangle":
+            raise NotImplementedError("the sampler kernel implements the Rectangle spike function")
+        self.kernel_size, self.depth, self.readout, self.relu = int(kernel_size), int(depth), readout, relu
+        self.kwargs_spikes = kwargs_spikes
+        self.nb_steps = kwargs_spikes["nb_steps"] if "Tm" not in kwargs_spikes else kwargs_spikes["Tm"]
+        self.thresh = kwargs_spikes["thresh"]
+        self.vreset = copy.deepcopy(kwargs_spikes["vreset"])
+        self.input_conv = _TdLayer(AdaptiveRSNNEmbedding.build_conv(in_channel, out_channel * 2, self.kernel_size, self.depth))
+        self.gate_conv = AdaptiveRSNNEmbedding.build_conv(out_channel, out_channel * 2, self.kernel_size, self.depth)
+        for m in self.input_conv.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.orthogonal_(m.weight, gain=nn.init.calculate_gain("relu"))
+        for m in self.gate_conv.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_uniform_(m.weight, nonlinearity="sigmoid")
+
+    def forward(self, events):
+        events = self._prep(events)
+        params = []
+        for convs in (self.input_conv.layer, self.gate_conv):
+            for m in convs:
+                if isinstance(m, nn.Conv2d):
+                    params += [m.weight, m.bias]
+        with torch.no_grad():
+            _, v_seq, _, _, _ = _sampler_forward(events, self, params, True)
+            return self._readout(v_seq, relu=self.relu)
+
+
+class LIFEmbedding(_SeqReadoutEmbedding):
+    """``LIFEmbedding`` (``embedding: snn``; yolox/models/embedding.py:28-76): a feed-forward conv stack (``tdLayer``,
+    keys ``embedding_conv.layer.{0,2}.*``) into one ``LIFCell`` (cell.py:37-65: ``v = sigmoid(decay) * v + psp``,
+    Rectangle spike, soft / hard reset), read out as sum_t v_t or the last potential.  This is the sampler's recurrence
+    with a constant gate and no recurrent input, so it runs on the sampler kernels with synthesised weights: gate
+    channels = zero weights + bias ``decay`` (their sigmoid is the cell's leak), recurrent stack = zeros, current
+    channels = the embedding convolution."""
+
+    def __init__(self, kernel_size, in_channel=2, out_channel=2, readout="sum", depth=1, **kwargs_spikes):
+        super().__init__()
+        if in_channel != 2 or out_channel != 2 or int(depth) not in (1, 2) or int(kernel_size) not in (3, 5, 7):
+            raise NotImplementedError("sampler kernels: 2 polarity channels, depth in {1,2}, kernel_size in {3,5,7}")
+        fn = kwargs_spikes.get("spike_fn", None)
+        if fn is not None and getattr(fn, "__name__", type(fn).__name__) != "Rectangle":
+            raise NotImplementedError("the sampler kernel implements the Rectangle spike function")
+        self.kernel_size, self.depth, self.readout = int(kernel_size), int(depth), readout
+        self.kwargs_spikes = kwargs_spikes
+        self.nb_steps = kwargs_spikes["nb_steps"] if "Tm" not in kwargs_spikes else kwargs_spikes["Tm"]
+        self.embedding_conv = _TdLayer(AdaptiveRSNNEmbedding.build_conv(in_channel, out_channel, self.kernel_size, self.depth))
+        self.cell = _LIFCellParams(decay=kwargs_spikes.get("decay", None), thresh=kwargs_spikes.get("thresh", None),
+                                   vreset=kwargs_spikes.get("vreset", None))
+        for m in self.embedding_conv.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.orthogonal_(m.weight, gain=nn.init.calculate_gain("relu"))
+
+    @property
+    def thresh(self):
+        return self.cell.thresh
+
+    @property
+    def vreset(self):
+        return self.cell.vreset
+
+    def forward(self, events):
+        events = self._prep(events)
+        convs = [m for m in self.embedding_conv.layer if isinstance(m, nn.Conv2d)]
+        k, dev = self.kernel_size, events.device
+        decay = self.cell.decay.detach().float().reshape(()).to(dev)
+        with torch.no_grad():
+            def widen(conv, cin_pad, last):
+                """Conv(c -> 2) as the sampler's Conv(cin_pad -> 4): [gate pair | current pair] output channels (last layer)
+                or [hidden pair | unused pair] (first of two layers)."""
+                w = torch.zeros((4, cin_pad, k, k), device=dev)
+                b = torch.zeros((4,), device=dev)
+                o = 2 if last else 0
+                w[o:o + 2, :conv.weight.shape[1]] = conv.weight.float()
+                b[o:o + 2] = conv.bias.float()
+                if last:
+                    b[0:2] = decay                      # gate pre-activation = decay: sigmoid(decay) is the leak
+                return w, b
+            if self.depth == 1:
+                iw0, ib0 = widen(convs[0], 2, True)
+                params = [iw0, ib0, torch.zeros_like(iw0), torch.zeros_like(ib0)]
+            else:
+                iw0, ib0 = widen(convs[0], 2, False)
+                iw1, ib1 = widen(convs[1], 4, True)
+                z0, z1 = torch.zeros_like(iw0), torch.zeros_like(iw1)
+                params = [iw0, ib0, iw1, ib1, z0, torch.zeros_like(ib0), z1, torch.zeros_like(ib1)]
+            _, v_seq, _, _, _ = _sampler_forward(events, self, params, True)
+            return self._readout(v_seq)
+
+
+class _TdLayer(nn.Module):
+    """``tdLayer`` (yolox/models/layer.py:122-132): only its child name (``layer``) matters here."""
+
+    def __init__(self, layer):
+        super().__init__()
+        self.layer = layer
+
+
+class _LIFCellParams(nn.Module):
+    """The parameters of ``LIFCell`` (cell.py:24-36, 67-79): ``decay`` (a logit; an ``nn.Parameter`` when the caller
+    passes one, as ``EventExp.get_kwargs_spikes`` does), ``thresh``, ``vreset``."""
+
+    def __init__(self, decay=None, thresh=None, vreset=None):
+        super().__init__()
+        self.decay = copy.deepcopy(decay) if decay is not None else nn.Parameter(torch.tensor(0.0))
+        if not isinstance(self.decay, torch.Tensor):
+            self.decay = torch.tensor(float(self.decay))
+        self.thresh = 0.5 if thresh is None else copy.deepcopy(thresh)
+        self.vreset = copy.deepcopy(vreset)

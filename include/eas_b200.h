@@ -265,6 +265,16 @@ int eas_focus_im2col(const float* frames, int64_t n_images, int H, int W, void* 
  * out: f32 [n][plane_elems]; plane_elems = 2*H*W, a multiple of 4. */
 int eas_hist_time_sum(const void* hist, int in_dtype, int64_t n, int Tm, int64_t plane_elems, float* out,
                       void* stream);
+/* (f-4) Voxel grid with bilinear interpolation in time: to_voxel_grid_numpy, yolox/utils/event_reps.py:30-89.
+ * Events as for eas_bin_events (SoA, windows back to back, offsets[B+1]); per window the timestamps are normalised
+ * to [0, n_bins] in float64, every event adds pol * (1 - dt) to bin int(ts) and pol * dt to the next one (bins
+ * >= n_bins dropped: the last event of a window contributes nothing).  signed_polarity 1: pol = +1 / -1 (the
+ * reference's stated intent); 0: pol = +1 for all events, which is what the reference computes on its own
+ * events_struct dtype (p is bool: `pols[pols == 0] = -1` stores True, event_reps.py:62-63).  out: f32
+ * [B][n_bins][H][W], fully written.  A window whose first and last timestamps coincide stays zero (the reference
+ * produces NaN there). */
+int eas_voxel_grid(const int16_t* x, const int16_t* y, const int64_t* t, const uint8_t* p, const int64_t* offsets,
+                   int64_t B, int64_t n_events, int H, int W, int n_bins, int signed_polarity, float* out, void* stream);
 /* (f-3) Letterbox + bilinear resize of micro-frames: GEN1Dataset.get_random_data(random=False),
  * yolox/data/datasets/gen1.py:433-483 (cv2.resize INTER_LINEAR of every plane to [nh][nw], pasted at (dy, dx) into a
  * zero canvas [oh][ow]).  in: [n_planes][ih][iw] f32 or i32 counts; x0 / fx ([nw]) and y0 / fy ([nh]): source tap and

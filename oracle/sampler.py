@@ -180,3 +180,67 @@ def spike_count(events: torch.Tensor, nb_steps: int) -> torch.Tensor:
     else:
         events = events.transpose(0, 1)
     return events.sum(dim=0)
+
+
+def recurrent_layer_forward(events: torch.Tensor, in_w, in_b, gate_w, gate_b, thresh: float = 1.0,
+                            vreset: Optional[float] = 0.0, readout: str = "sum", relu: bool = False):
+    """Dense restatement of ``SpikingEmbedding.forward`` (yolox/models/embedding.py:285-316; ``update`` :276-283): the
+    sampler's gated recurrent spiking layer read out as sum_t v_t (pre-reset) or the last membrane potential."""
+    if events.dim() > 5:
+        events = events.flatten(end_dim=-5)
+    ev = events.transpose(0, 1).flip(0)                                      # :292-297 newest micro-bin first
+    s = vm = torch.zeros_like(ev[0])
+    vsum = 0
+    for t in range(ev.shape[0]):
+        g_rec, c_rec = conv_stack(s, gate_w, gate_b).chunk(2, dim=-3)        # :303-304
+        g_in, c_in = conv_stack(ev[t], in_w, in_b).chunk(2, dim=-3)          # :298-299 (tdLayer: same conv per step)
+        v = torch.sigmoid(g_in + g_rec) * vm + (c_in + c_rec)                # :305-307, :277
+        s = RectangleFn.apply(v - thresh)                                    # :278
+        vm = v - thresh * s if vreset is None else v * (1 - s) + vreset * s  # :279-282
+        vsum = vsum + v                                                      # :308
+    out = vsum if readout == "sum" else vm                                   # :313-316
+    return F.relu(out) if relu else out
+
+
+def lif_layer_forward(events: torch.Tensor, w, b, decay, thresh: float = 1.0, vreset: Optional[float] = 0.0,
+                      readout: str = "sum"):
+    """Dense restatement of ``LIFEmbedding.forward`` (embedding.py:53-76) over ``LIFCell.forward`` (cell.py:37-65):
+    conv stack per step, ``v = sigmoid(decay) * v + psp``, Rectangle spike, soft / hard reset; sum_t v_t or last v."""
+    if events.dim() > 5:
+        events = events.flatten(end_dim=-5)
+    ev = events.transpose(0, 1).flip(0)                                      # :60-63
+    vm = torch.zeros_like(ev[0])
+    vsum = 0
+    for t in range(ev.shape[0]):
+        v = torch.sigmoid(decay) * vm + conv_stack(ev[t], w, b)              # cell.py:48, embedding.py:66
+        s = RectangleFn.apply(v - thresh)                                    # cell.py:55
+        vm = v - thresh * s if vreset is None else v * (1 - s) + vreset * s  # cell.py:58-61
+        vsum = vsum + v                                                      # embedding.py:71
+    return vsum if readout == "sum" else vm
+
+
+def sampler_records(events: torch.Tensor, in_w, in_b, gate_w, gate_b, Ts: int = 1, thresh: float = 1.0,
+                    vreset: Optional[float] = 0.0):
+    """The analysis outputs of the adaptive sampler (embedding.py:180, 198-201, 221-224): ``t_last`` after every
+    executed step ``[steps, B, 2, H, W]`` and the concatenated sub-threshold potentials of every executed step."""
+    if events.dim() > 5:
+        events = events.flatten(end_dim=-5)
+    ev = events.transpose(0, 1).flip(0)
+    s = vm = torch.zeros_like(ev[0])
+    seg = torch.zeros_like(ev[0], dtype=torch.long)
+    tl = torch.zeros_like(ev[0], dtype=torch.long) - 1
+    t_rec, v_rec = [], []
+    for t in range(ev.shape[0]):
+        g_rec, c_rec = conv_stack(s, gate_w, gate_b).chunk(2, dim=-3)
+        g_in, c_in = conv_stack(ev[t], in_w, in_b).chunk(2, dim=-3)
+        v = torch.sigmoid(g_in + g_rec) * vm + (c_in + c_rec)
+        s = (v - thresh > 0).to(v.dtype)
+        vm = v - thresh * s if vreset is None else v * (1 - s) + vreset * s
+        v_rec.append(v[(1 - s).bool()])                                      # :180
+        valid = (s > 0) & (seg < Ts)
+        seg = seg + valid.long()
+        tl = torch.where(valid, torch.full_like(tl, t), tl)
+        t_rec.append(tl.clone())                                             # :198-199
+        if int(seg.min()) >= Ts:                                             # :200-201
+            break
+    return torch.stack(t_rec, 0), torch.cat(v_rec)

@@ -3,7 +3,7 @@
     python tests/golden/make_golden.py          # needs /root/reference (read-only)
 
 Outputs (small, committed): tests/golden/binning.npz, sampler.npz, backbone.npz, psee.npz, detector.npz,
-detector_full_spike.npz, detector_full_spike_v2.npz, count.npz, letterbox.npz.
+detector_full_spike.npz, detector_full_spike_v2.npz, count.npz, ablations.npz, voxel.npz, letterbox.npz.
 The reference is imported in place through ``oracle/ref_loader.py``; nothing is copied from it.
 ``/root/reference`` does not exist on the GPU box, so tests only ever read the .npz files.
 """
@@ -138,6 +138,85 @@ def make_count(emb):
            "y6": m(x6).numpy(), "x4": x4.numpy().astype(np.uint8), "y4": m(x4).numpy()}
     np.savez_compressed(os.path.join(HERE, "count.npz"), **out)
     print("count.npz:", {k: v.shape for k, v in out.items() if k.startswith("y")})
+
+
+def make_ablations(emb, act):
+    """(f-4) The reference's ablation embeddings -- ``LIFEmbedding`` ('snn', embedding.py:28-76) and
+    ``SpikingEmbedding`` ('rsnn', :229-316) -- and the analysis outputs of the adaptive sampler (``record`` /
+    ``v_record``, :198-199, 221-224) on Poisson micro-bin counts; parameters are stored with the outputs."""
+    from yolox.utils.util import warp_decay
+    out, names = {}, []
+    cases = [("lif_d1_k5_sum", "lif", 5, 1, "sum", 0, 0.9), ("lif_d2_k3_last_soft", "lif", 3, 2, "last", None, 1.2),
+             ("rsnn_d2_k5_sum", "rsnn", 5, 2, "sum", 0, 0.9), ("rsnn_d1_k7_last_relu", "rsnn", 7, 1, "last", 0.25, 1.1)]
+    for (name, kind, k, depth, readout, vreset, rate) in cases:
+        torch.manual_seed(80)
+        kw = dict(nb_steps=4, vreset=vreset, thresh=1, spike_fn=act.Rectangle, decay=nn.Parameter(warp_decay(0.5)),
+                  embedding=kind, Ts=1, spike_attach=True)
+        if kind == "lif":
+            m = emb.LIFEmbedding(kernel_size=k, in_channel=2, out_channel=2, readout=readout, depth=depth, **kw)
+        else:
+            m = emb.SpikingEmbedding(kernel_size=k, in_channel=2, out_channel=2, readout=readout,
+                                     relu=name.endswith("relu"), depth=depth, **kw)
+        for mm in m.modules():                      # non-zero biases (the default init leaves them tiny)
+            if isinstance(mm, nn.Conv2d):
+                nn.init.uniform_(mm.bias, -0.3, 0.3)
+        g = torch.Generator().manual_seed(77)
+        x = torch.poisson(torch.full((2, 4, 2, 40, 48), rate), generator=g)
+        with torch.no_grad():
+            y = m(x)
+        assert y.shape == (2, 2, 40, 48) and float((y != 0).float().mean()) > 0.1
+        out[f"{name}/x"] = x.numpy().astype(np.uint8)
+        out[f"{name}/y"] = y.numpy()
+        out[f"{name}/cfg"] = np.array([repr(dict(kind=kind, ksize=k, depth=depth, readout=readout,
+                                                 vreset=-1e30 if vreset is None else vreset, relu=name.endswith("relu")))])
+        for pn, pv in m.state_dict().items():
+            out[f"{name}/sd/{pn}"] = pv.detach().numpy()
+        names.append(name)
+        print(" ablation", name, "out", tuple(y.shape), "mean |y| %.3f" % float(y.abs().mean()))
+    # record / v_record of the adaptive sampler (two configurations: Ts = 1 with the early break never taken, Ts = 2)
+    for name, Ts, rate in (("record_ts1", 1, 1.0), ("record_ts2", 2, 1.4)):
+        torch.manual_seed(80)
+        m = emb.AdaptiveRSNNEmbedding(kernel_size=5, in_channel=2, out_channel=2, readout="sum", split=False,
+                                      write_zero=True, abs=False, depth=2, nb_steps=5, vreset=0, thresh=1,
+                                      spike_fn=act.Rectangle, decay=nn.Parameter(warp_decay(0.5)), embedding="arsnn",
+                                      Ts=Ts, spike_attach=True)
+        g = torch.Generator().manual_seed(78)
+        x = torch.poisson(torch.full((2, 5, 2, 40, 48), rate), generator=g)
+        with torch.no_grad():
+            y, rec = m(x, record=True)
+            y2, vrec = m(x, v_record=True)
+        assert torch.equal(y, y2)
+        out[f"{name}/x"] = x.numpy().astype(np.uint8)
+        out[f"{name}/y"] = y.numpy()
+        out[f"{name}/record"] = rec.numpy().astype(np.int8)
+        out[f"{name}/v_record"] = vrec.numpy()
+        for pn, pv in m.state_dict().items():
+            out[f"{name}/sd/{pn}"] = pv.detach().numpy()
+        print(" record", name, "steps", rec.shape[0], "fired %.3f" % float((rec[-1] >= 0).float().mean()),
+              "v_record", tuple(vrec.shape))
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "ablations.npz"), **out)
+
+
+def make_voxel():
+    """(f-4) ``to_voxel_grid_numpy`` (yolox/utils/event_reps.py:30-89) on synthetic windows: with the reference's own
+    ``events_struct`` dtype (bool polarity: its in-place ``pols[pols == 0] = -1`` then stores True and every event weighs
+    +1) and with a signed int8 polarity field (+1 / -1 as its comment intends).  Inputs come from seeds."""
+    import importlib
+    reps = importlib.import_module("yolox.utils.event_reps")
+    out = {}
+    for i, (n, H, W, nb) in enumerate(((3000, 40, 48, 10), (20000, 64, 80, 5), (1, 24, 32, 4), (2, 24, 32, 3))):
+        rng = np.random.default_rng(500 + i)
+        x, y, t, p = synth.make_window(rng, n, H, W)
+        for tag, pdt in (("bool", bool), ("int8", np.int8)):
+            ev = np.zeros(n, dtype=[("x", np.int16), ("y", np.int16), ("t", np.int64), ("p", pdt)])
+            ev["x"], ev["y"], ev["t"], ev["p"] = x, y, t, p
+            if n >= 2 and t[-1] > t[0]:
+                vg = reps.to_voxel_grid_numpy(ev, (W, H, 2), n_time_bins=nb)
+                out["%d/%s" % (i, tag)] = vg.astype(np.float64)
+        out["%d/cfg" % i] = np.array([n, H, W, nb])
+        print(" voxel", i, (n, H, W, nb), [k for k in out if k.startswith("%d/" % i)])
+    np.savez_compressed(os.path.join(HERE, "voxel.npz"), **out)
 
 
 LETTERBOX_CASES = [  # ih, iw, h, w, center, letterbox
@@ -398,6 +477,10 @@ if __name__ == "__main__":
         make_psee(gen1)
         print("psee.npz", os.path.getsize(os.path.join(HERE, "psee.npz")) // 1024, "KiB")
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "f4":
+        make_ablations(emb, act)
+        make_voxel()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "letterbox":
         make_letterbox(gen1)
         sys.exit(0)
@@ -412,6 +495,8 @@ if __name__ == "__main__":
     make_binning(gen1)
     make_sampler(emb, act)
     make_count(emb)
+    make_ablations(emb, act)
+    make_voxel()
     make_letterbox(gen1)
     make_psee(gen1)          # (before the two below: load_full_model re-imports yolox without the package stubs)
     make_backbone()
@@ -419,5 +504,5 @@ if __name__ == "__main__":
     make_detector("full_spike")
     make_detector("full_spike_v2")
     for f in ("binning.npz", "sampler.npz", "count.npz", "letterbox.npz", "backbone.npz", "psee.npz", "detector.npz",
-              "detector_full_spike.npz", "detector_full_spike_v2.npz"):
+              "detector_full_spike.npz", "detector_full_spike_v2.npz", "ablations.npz", "voxel.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -273,3 +273,86 @@ def test_spike_count_embedding_golden_and_events(cuda):
     got = m.forward_events(*(torch.from_numpy(a).to(cuda) for a in (x, y, t, p, off)), 240, 304)
     want = ob.micro_sum_batch(x, y, t, p, off, 240, 304, 4).sum(axis=1)
     assert got.shape == (5, 2, 240, 304) and np.array_equal(got.cpu().numpy(), want.astype(np.float32))
+
+
+def _ablation_case(z, name):
+    import ast
+    cfg = ast.literal_eval(str(z[name + "/cfg"][0]))
+    sd = {k[len(name) + 4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(name + "/sd/")}
+    return cfg, sd, torch.from_numpy(z[name + "/x"].astype(np.float32)), torch.from_numpy(z[name + "/y"])
+
+
+def test_ablation_embeddings_golden(cuda):
+    """(f-4) ``LIFEmbedding`` ('snn') and ``SpikingEmbedding`` ('rsnn') -- strict subsets of the sampler's arithmetic,
+    run on the sampler kernels -- against the reference classes' outputs; their state dicts load key for key
+    (``embedding_conv.layer.0.weight``, ``cell.decay``, ``input_conv.layer.2.bias``, ``gate_conv.0.weight``)."""
+    z = load_golden("ablations")
+    for name in [str(n) for n in z["names"]]:
+        cfg, sd, x, want = _ablation_case(z, name)
+        vreset = None if cfg["vreset"] < -1e29 else cfg["vreset"]
+        kw = dict(nb_steps=4, vreset=vreset, thresh=1, decay=torch.nn.Parameter(torch.tensor(0.0)), Ts=1)
+        if cfg["kind"] == "lif":
+            m = eas.LIFEmbedding(kernel_size=cfg["ksize"], readout=cfg["readout"], depth=cfg["depth"], **kw)
+        else:
+            m = eas.SpikingEmbedding(kernel_size=cfg["ksize"], readout=cfg["readout"], relu=cfg["relu"],
+                                     depth=cfg["depth"], **kw)
+        assert set(m.state_dict()) == set(sd), (name, set(m.state_dict()) ^ set(sd))
+        m.load_state_dict(sd, strict=True)
+        m = m.to(cuda).eval()
+        for algo in (["fp32", "auto"] if cfg["ksize"] == 5 and cfg["depth"] == 2 else ["fp32"]):
+            m.algo = algo
+            with torch.no_grad():
+                got = m(x.to(cuda))
+            ok, frac, msg = _compare(got, want, budget=2e-3)
+            print(name, algo, msg)
+            assert got.shape == want.shape and ok, name + " " + algo + ": " + msg
+
+
+def test_record_and_v_record_golden(cuda):
+    """The analysis outputs ``forward(events, record=True)`` / ``v_record=True`` (embedding.py:198-199, 221-224; the
+    Fig. 4 study of the README) against the reference's: the t_last history exactly, the sub-threshold potentials 1e-5."""
+    z = load_golden("ablations")
+    for name, Ts in (("record_ts1", 1), ("record_ts2", 2)):
+        sd = {k[len(name) + 4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(name + "/sd/")}
+        x = torch.from_numpy(z[name + "/x"].astype(np.float32)).to(cuda)
+        m = eas.AdaptiveRSNNEmbedding(kernel_size=5, depth=2, nb_steps=5, thresh=1, vreset=0, Ts=Ts, write_zero=True,
+                                      spike_attach=True).to(cuda)
+        m.load_state_dict(sd, strict=True)
+        m.algo = "fp32"
+        y, rec = m(x, record=True)
+        y2, vrec = m(x, v_record=True)
+        want_rec = torch.from_numpy(z[name + "/record"].astype(np.int64))
+        assert rec.shape == want_rec.shape and rec.dtype == torch.int64
+        assert float((rec.cpu() != want_rec).float().mean()) <= 1e-4, name
+        ok, frac, msg = _compare(y, torch.from_numpy(z[name + "/y"]), budget=2e-3)
+        assert ok and torch.equal(y, y2), msg
+        want_v = torch.from_numpy(z[name + "/v_record"])
+        assert vrec.shape == want_v.shape, (vrec.shape, want_v.shape)      # same spikes -> same number of entries
+        assert torch.allclose(vrec.cpu(), want_v, rtol=1e-5, atol=1e-5)
+
+
+def test_voxel_grid_golden_and_oracle(cuda):
+    """(f-4) ``eas.voxel_grid`` (to_voxel_grid_numpy, event_reps.py:30-89): the reference's outputs on its own bool-polarity
+    dtype (every event +1) and on a signed dtype (+1 / -1); several windows in one call vs the oracle; a degenerate window."""
+    from oracle import reps
+    z = load_golden("voxel")
+    i = 0
+    while "%d/cfg" % i in z.files:
+        n, H, W, nb = (int(v) for v in z["%d/cfg" % i])
+        x, y, t, p = synth.make_window(np.random.default_rng(500 + i), n, H, W)
+        d = [torch.from_numpy(a).to(cuda) for a in (x, y, t, p, np.array([0, n], np.int64))]
+        for tag, mode in (("bool", "reference"), ("int8", "signed")):
+            if "%d/%s" % (i, tag) in z.files:
+                got = eas.voxel_grid(*d, H, W, nb, polarity=mode)
+                want = torch.from_numpy(z["%d/%s" % (i, tag)]).float().unsqueeze(0)
+                assert got.shape == want.shape and torch.allclose(got.cpu(), want, rtol=1e-5, atol=1e-5), (i, tag)
+            elif n == 1:
+                assert float(eas.voxel_grid(*d, H, W, nb, polarity=mode).abs().sum()) == 0.0   # t_last == t_first
+        i += 1
+    arrs = synth.make_batch(31, 5, 120, 152, 2e4, 9e4)
+    got = eas.voxel_grid(*(torch.from_numpy(a).to(cuda) for a in arrs), 120, 152, 6, polarity="signed").cpu()
+    off = arrs[4]
+    for b in range(5):
+        sl = slice(off[b], off[b + 1])
+        want = reps.to_voxel_grid(arrs[0][sl], arrs[1][sl], arrs[2][sl], arrs[3][sl], 120, 152, 6, p_is_bool=False)
+        assert torch.allclose(got[b], torch.from_numpy(want).float(), rtol=1e-5, atol=2e-5), b

@@ -162,3 +162,61 @@ def test_letterbox_golden():
         assert got.sum() == chk[0] and np.abs(got).max() == chk[1]
         n += 1
     assert n == 7
+
+
+def _ablation_case(z, name):
+    import ast
+    cfg = ast.literal_eval(str(z[name + "/cfg"][0]))
+    sd = {k[len(name) + 4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(name + "/sd/")}
+    x = torch.from_numpy(z[name + "/x"].astype(np.float32))
+    return cfg, sd, x, torch.from_numpy(z[name + "/y"])
+
+
+def test_ablation_embeddings_and_records_golden():
+    """(f-4) oracle restatements of LIFEmbedding / SpikingEmbedding and of the sampler's record / v_record outputs
+    against the reference classes' own outputs (tests/golden/ablations.npz): bit-identical on the CPU."""
+    z = load_golden("ablations")
+    for name in [str(n) for n in z["names"]]:
+        cfg, sd, x, want = _ablation_case(z, name)
+        vreset = None if cfg["vreset"] < -1e29 else cfg["vreset"]
+        with torch.no_grad():
+            if cfg["kind"] == "lif":
+                n = cfg["depth"]
+                w = [sd["embedding_conv.layer.%d.weight" % (2 * i)] for i in range(n)]
+                b = [sd["embedding_conv.layer.%d.bias" % (2 * i)] for i in range(n)]
+                got = sampler.lif_layer_forward(x, w, b, sd["cell.decay"], 1.0, vreset, cfg["readout"])
+            else:
+                n = cfg["depth"]
+                iw = [sd["input_conv.layer.%d.weight" % (2 * i)] for i in range(n)]
+                ib = [sd["input_conv.layer.%d.bias" % (2 * i)] for i in range(n)]
+                gw = [sd["gate_conv.%d.weight" % (2 * i)] for i in range(n)]
+                gb = [sd["gate_conv.%d.bias" % (2 * i)] for i in range(n)]
+                got = sampler.recurrent_layer_forward(x, iw, ib, gw, gb, 1.0, vreset, cfg["readout"], cfg["relu"])
+        assert torch.equal(got, want), name
+    for name, Ts in (("record_ts1", 1), ("record_ts2", 2)):
+        sd = {k[len(name) + 4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(name + "/sd/")}
+        x = torch.from_numpy(z[name + "/x"].astype(np.float32))
+        iw, ib = [sd["input_conv.0.weight"], sd["input_conv.2.weight"]], [sd["input_conv.0.bias"], sd["input_conv.2.bias"]]
+        gw, gb = [sd["gate_conv.0.weight"], sd["gate_conv.2.weight"]], [sd["gate_conv.0.bias"], sd["gate_conv.2.bias"]]
+        with torch.no_grad():
+            rec, vrec = sampler.sampler_records(x, iw, ib, gw, gb, Ts=Ts, thresh=1.0, vreset=0)
+        assert torch.equal(rec, torch.from_numpy(z[name + "/record"].astype(np.int64))), name
+        assert torch.equal(vrec, torch.from_numpy(z[name + "/v_record"])), name
+
+
+def test_voxel_grid_golden():
+    """(f-4) oracle.reps.to_voxel_grid == the reference's to_voxel_grid_numpy, including what its in-place
+    ``pols[pols == 0] = -1`` does on a bool polarity field (every event weighs +1)."""
+    from oracle import reps
+    from eas_snn_b200 import synth
+    z = load_golden("voxel")
+    i = 0
+    while "%d/cfg" % i in z.files:
+        n, H, W, nb = (int(v) for v in z["%d/cfg" % i])
+        x, y, t, p = synth.make_window(np.random.default_rng(500 + i), n, H, W)
+        for tag in ("bool", "int8"):
+            if "%d/%s" % (i, tag) in z.files:
+                got = reps.to_voxel_grid(x, y, t, p, H, W, nb, p_is_bool=(tag == "bool"))
+                assert np.array_equal(got, z["%d/%s" % (i, tag)]), (i, tag)
+        i += 1
+    assert i == 4
