@@ -70,8 +70,9 @@ def _sampler_forward(events, mod, params, want_seq):
 
 class _SamplerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, events, mod, *params):
-        need_grad = any(ctx.needs_input_grad)   # grad mode is off inside Function.forward: ask the ctx
+    def forward(ctx, events, mod, need_grad, *params):
+        # need_grad is decided by the caller: ctx.needs_input_grad is True for every Parameter even under
+        # torch.no_grad(), and saving the per-step sequences costs 2 x [Tm, B, 2, H, W] of stores per forward
         out, v_seq, gate_seq, cfg, plist = _sampler_forward(events, mod, params, need_grad)
         if need_grad:
             ctx.mod, ctx.cfg, ctx.plist = mod, cfg, plist
@@ -102,7 +103,7 @@ class _SamplerFn(torch.autograd.Function):
             gp = grads
         else:
             gp = [grads[0], grads[1], grads[4], grads[5]]
-        return (g_ev, None) + tuple(gp)
+        return (g_ev, None, None) + tuple(gp)
 
 
 class AdaptiveRSNNEmbedding(nn.Module):
@@ -186,7 +187,9 @@ class AdaptiveRSNNEmbedding(nn.Module):
         events = events.contiguous()
         if record or v_record:
             return self._forward_with_record(events, record)
-        return _SamplerFn.apply(events, self, *self._params())
+        params = self._params()
+        need_grad = torch.is_grad_enabled() and (events.requires_grad or any(q.requires_grad for q in params))
+        return _SamplerFn.apply(events, self, need_grad, *params)
 
     @torch.no_grad()
     def _forward_with_record(self, events, record: bool):
