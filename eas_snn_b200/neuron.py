@@ -164,9 +164,10 @@ class ParametricLIFNode(nn.Module):
     def forward(self, x):
         seq = x if self.step_mode == "m" else x.unsqueeze(0)
         v0 = self.v if isinstance(self.v, torch.Tensor) else None
-        if v0 is not None and torch.is_grad_enabled() and (x.requires_grad or self.w.requires_grad):
-            # the carried potential is a plain buffer (grad_v0 is not produced): BPTT across separate calls
-            # would be silently truncated.  The reference resets after every batch (trainer.py:115-117).
+        if v0 is not None and torch.is_grad_enabled() and x.requires_grad:
+            # the carried potential is a plain buffer (grad_v0 is not produced): BPTT across separate calls inside a
+            # network would be silently truncated.  The reference resets after every batch (trainer.py:115-117).
+            # (A stand-alone node fed constants may carry its state with grad mode on: nothing flows back.)
             raise RuntimeError("ParametricLIFNode: state carried across calls under autograd is not differentiable here; "
                                "use step_mode='m' over the whole sequence and reset_net() between batches")
         spikes, v_out = plif_multistep(seq, self.w, self, v0=v0, want_v=self.keep_v)

@@ -298,6 +298,9 @@ def test_convert_to_spiking_model_reproduces_the_reference_backbone_golden(cuda)
     sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
     net = fused.convert_to_spiking(AnnCSPDarknet(0.33, 0.125, in_dim=2), eas.ATan(2.0))
     net.load_state_dict(sd, strict=True)
+    for m in net.modules():          # init_yolo (event_yolox_base.py:179-183), applied AFTER the conversion like get_model
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.eps, m.momentum = 1e-3, 0.03
     net = net.to(cuda).eval()
     x = torch.from_numpy(z["x"]).to(cuda)
     with torch.no_grad():
