@@ -13,17 +13,134 @@ import torch
 from . import _lib
 
 STRATEGY = {"auto": 0, "reds": 1, "tiles": 2}
+SAT_CAP = 4096          # EAS_HIST_U8_SAT_CAP (include/eas_b200.h)
+
+
+class CompactHist:
+    """The byte histogram of ``bin_events(..., dtype=torch.uint8)`` (``include/eas_b200.h``, EAS_U8): one device buffer
+    holding ``min(count, 255)`` per bin followed by the exact ``{bin, count}`` list of the bins that reached 255 -- the
+    information of the int32 histogram in a quarter of the bytes.  The sampler kernels read it directly
+    (``AdaptiveRSNNEmbedding.forward(CompactHist)``); :meth:`dense` gives the ``[B, Tm, 2, H, W]`` tensor back.
+
+    Only when more than ``SAT_CAP`` bins saturate in one call is information lost (``lost`` flag in the buffer).
+    That is checked without stalling the stream: every call queues a copy of the flag and :func:`poll_compact` (run by
+    the next binning call, or by hand) raises ``OverflowError`` for any finished call that lost counts;
+    :meth:`check` waits and checks now."""
+
+    def __init__(self, buf: torch.Tensor, shape):
+        self.buf, self.shape = buf, tuple(int(v) for v in shape)
+        self.nbins = int(np.prod(self.shape))
+        self._tail_off = (self.nbins + 255) // 256 * 256
+
+    @staticmethod
+    def nbytes_for(shape) -> int:
+        nbins = int(np.prod(shape))
+        return (nbins + 255) // 256 * 256 + 16 + SAT_CAP * 8
+
+    @classmethod
+    def empty(cls, shape, device) -> "CompactHist":
+        return cls(torch.empty(cls.nbytes_for(shape), dtype=torch.uint8, device=device), shape)
+
+    @property
+    def device(self):
+        return self.buf.device
+
+    @property
+    def counts(self) -> torch.Tensor:
+        """uint8 ``[B, Tm, 2, H, W]`` view: the counts, 255 where a bin saturated."""
+        return self.buf[:self.nbins].view(self.shape)
+
+    @property
+    def tail(self) -> torch.Tensor:
+        """int32 view of the list header: ``[n_saturated, lost, 0, 0]``."""
+        return self.buf[self._tail_off:self._tail_off + 16].view(torch.int32)
+
+    def saturated(self):
+        """(bin indices, exact counts) of the saturated bins (synchronises)."""
+        n = min(int(self.tail[0]), SAT_CAP)
+        ent = self.buf[self._tail_off + 16:self._tail_off + 16 + 8 * n].view(torch.int32).view(n, 2)
+        return ent[:, 0].to(torch.int64) & 0xFFFFFFFF, ent[:, 1].clone()
+
+    def dense(self, dtype: torch.dtype = torch.int32) -> torch.Tensor:
+        """The ``[B, Tm, 2, H, W]`` int32 / float32 histogram (``eas_hist_u8_expand``)."""
+        if dtype not in (torch.int32, torch.float32):
+            raise TypeError("dense histogram dtype must be int32 or float32")
+        out = torch.empty(self.shape, dtype=dtype, device=self.buf.device)
+        B, Tm, _, H, W = self.shape
+        with torch.cuda.device(self.buf.device):
+            rc = _lib.lib().eas_hist_u8_expand(_lib.ptr(self.buf), B, Tm, H, W, _lib.ptr(out),
+                                               _lib.EAS_F32 if dtype == torch.float32 else _lib.EAS_I32,
+                                               _lib.stream_ptr())
+        _lib.check(rc, "eas_hist_u8_expand")
+        return out
+
+    def check(self):
+        """Wait for the binning call and raise if it lost counts."""
+        if int(self.tail[1]) != 0:
+            raise OverflowError(_LOST_MSG)
+        return self
+
+    def _queue_check(self):
+        if torch.cuda.is_current_stream_capturing():
+            return                                  # (a captured call is checked by hand: .check())
+        ev, host = _FREE.pop() if _FREE else (torch.cuda.Event(), torch.empty(4, dtype=torch.int32).pin_memory())
+        host.copy_(self.tail, non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.buf.device))
+        _PENDING.append((ev, host))
+
+
+_LOST_MSG = ("compact histogram: more than %d bins collected >= 255 events in one call, counts were lost; "
+             "bin with dtype=torch.int32 / float32 (hist_dtype='dense')" % SAT_CAP)
+_PENDING: list = []      # (event, pinned copy of the list header) of the calls not checked yet
+_FREE: list = []         # recycled (event, pinned buffer) pairs
+
+
+def poll_compact(wait: bool = False):
+    """Raise ``OverflowError`` if a finished compact binning call lost counts (``wait=True``: finish them all first)."""
+    keep, lost = [], False
+    for ev, host in _PENDING:
+        if wait:
+            ev.synchronize()
+        if ev.query():
+            lost = lost or int(host[1]) != 0
+            _FREE.append((ev, host))
+        else:
+            keep.append((ev, host))
+    _PENDING[:] = keep
+    if lost:
+        raise OverflowError(_LOST_MSG)
+
+
+def _hist_out(B, Tm, H, W, out, dtype, device):
+    """Allocate / validate the output of a binning call; returns (object handed back, buffer, EAS dtype)."""
+    shape = (B, Tm, 2, H, W)
+    if out is None:
+        if dtype == torch.uint8:
+            out = CompactHist.empty(shape, device)
+        elif dtype in (torch.int32, torch.float32):
+            out = torch.empty(shape, dtype=dtype, device=device)
+        else:
+            raise TypeError("histogram dtype must be int32, float32 or uint8 (compact)")
+    if isinstance(out, CompactHist):
+        if out.shape != shape or out.buf.numel() < CompactHist.nbytes_for(shape):
+            raise ValueError("out: CompactHist of another shape")
+        return out, out.buf, _lib.EAS_U8
+    if out.shape != shape or out.dtype not in (torch.int32, torch.float32) or not out.is_contiguous():
+        raise ValueError("out must be a contiguous int32/float32 [B, Tm, 2, H, W] tensor or a CompactHist")
+    return out, out, _lib.EAS_F32 if out.dtype == torch.float32 else _lib.EAS_I32
 
 
 def bin_events(x: torch.Tensor, y: torch.Tensor, t: torch.Tensor, p: torch.Tensor, offsets: torch.Tensor,
-               H: int, W: int, Tm: int, strategy: str = "auto", out: torch.Tensor | None = None,
-               dtype: torch.dtype = torch.int32) -> torch.Tensor:
+               H: int, W: int, Tm: int, strategy: str = "auto", out=None,
+               dtype: torch.dtype = torch.int32):
     """Histogram B time-sorted windows.
 
     x, y : int16 ``[N]``; t : int64 ``[N]`` (sorted inside each window); p : uint8/bool ``[N]``;
     offsets : int64 ``[B+1]`` with ``offsets[0] == 0`` and ``offsets[B] == N``.  All CUDA tensors.
     Returns ``[B, Tm, 2, H, W]`` counts, int32 (default) or float32 (``dtype=torch.float32``: exact
-    below 2^24, the dtype the reference casts to on the device and the sampler consumes).
+    below 2^24, the dtype the reference casts to on the device and the sampler consumes), or -- with
+    ``dtype=torch.uint8`` -- a :class:`CompactHist` (bytes + exact saturation list; frames that fit the shared-memory
+    tiles kernel only).
     """
     _lib.require_cuda(x, y, t, p, offsets)
     if p.dtype == torch.bool:
@@ -37,23 +154,30 @@ def bin_events(x: torch.Tensor, y: torch.Tensor, t: torch.Tensor, p: torch.Tenso
         raise ValueError("x, y, t, p must have the same length")
     x, y, t, p, offsets = (a.contiguous() for a in (x, y, t, p, offsets))
     B = offsets.numel() - 1
-    if out is None:
-        if dtype not in (torch.int32, torch.float32):
-            raise TypeError("histogram dtype must be int32 or float32")
-        out = torch.empty((B, Tm, 2, H, W), dtype=dtype, device=x.device)
-    elif (out.shape != (B, Tm, 2, H, W) or out.dtype not in (torch.int32, torch.float32)
-          or not out.is_contiguous()):
-        raise ValueError("out must be a contiguous int32/float32 [B, Tm, 2, H, W] tensor")
+    out, buf, eas_dtype = _hist_out(B, Tm, H, W, out, dtype, x.device)
     L = _lib.lib()
     ws_bytes = L.eas_bin_events_ws_bytes(B, Tm)
     ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
         rc = L.eas_bin_events_ex(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), _lib.ptr(offsets),
-                                 B, n, H, W, Tm, _lib.ptr(out), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(),
-                                 STRATEGY[strategy],
-                                 _lib.EAS_F32 if out.dtype == torch.float32 else _lib.EAS_I32)
+                                 B, n, H, W, Tm, _lib.ptr(buf), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(),
+                                 STRATEGY[strategy], eas_dtype)
     _lib.check(rc, "eas_bin_events")
+    if isinstance(out, CompactHist) and B > 0:
+        poll_compact()
+        out._queue_check()
     return out
+
+
+def compact_fits(H: int, W: int) -> bool:
+    """Whether the byte histogram can be written for this frame size: the shared-memory tiles kernel holds a row slab
+    of 16-bit counters per CTA (<= 8 slabs of <= 72 KB; bin_events.cu ``slab_geo``)."""
+    slab = 72 * 1024
+    n_slabs = min(-(-(H * W * 2) // slab), H)
+    rows = -(-H // n_slabs)
+    n_slabs = -(-H // rows)
+    smem = ((rows * W + 1) // 2 + 3) // 4 * 4 * 4
+    return smem <= slab + 4096 and n_slabs <= 8
 
 
 class HostEventBatch:

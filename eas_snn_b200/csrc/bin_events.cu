@@ -18,7 +18,9 @@
 //      bin_hist_global_kernel ("reds"): event-parallel, 8 events per thread with 16 B loads,
 //         red.global.add.u32 into the (L2-resident when it fits) histogram after a memset.  Used for
 //         frames that do not fit in shared memory and for very long windows.
+#include <type_traits>
 #include "common.cuh"
+#include "hist_u8.cuh"
 
 namespace {
 
@@ -80,10 +82,11 @@ constexpr int kChunk = 65535;
 template <typename SRC>
 __global__ void __launch_bounds__(128)
 bin_bounds_kernel(const SRC src, int64_t B, int Tm, int64_t* __restrict__ bounds,
-                  unsigned int* __restrict__ work_counter) {
+                  unsigned int* __restrict__ work_counter, uint32_t* __restrict__ sat_tail) {
   const int lane = threadIdx.x & 31;
   const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (gid == 0 && lane == 0) *work_counter = 0u;
+  if (gid == 0 && lane < 2 && sat_tail) sat_tail[lane] = 0u;   // compact output: empty saturation list
   if (gid >= B * (Tm + 1)) return;
   const int64_t b = gid / (Tm + 1);
   const int k = (int)(gid - b * (Tm + 1));
@@ -131,7 +134,8 @@ template <typename OUT_T, typename SRC>
 __global__ void __launch_bounds__(kSmemThreads)
 bin_hist_smem_kernel(const SRC src, const int64_t* __restrict__ bounds, int64_t n_items,
                      int H, int W, int Tm, int n_slabs, int slab_rows, uint32_t* __restrict__ hist,
-                     unsigned int* __restrict__ work_counter) {
+                     unsigned int* __restrict__ work_counter, uint32_t* __restrict__ sat_tail) {
+  constexpr bool kU8 = std::is_same<OUT_T, uint8_t>::value;
   extern __shared__ __align__(16) uint32_t cnt[];  // ceil(slab_rows*W/2) words, two 16-bit counters per word
   __shared__ unsigned int sh_item;
   const int64_t HW = (int64_t)H * W;
@@ -197,7 +201,52 @@ bin_hist_smem_kernel(const SRC src, const int64_t* __restrict__ bounds, int64_t 
         }
       }
       __syncthreads();
-      if (vec_ok) {
+      if constexpr (kU8) {
+        // compact output: one byte per bin, the exact count of a saturated bin goes to the side list (hist_u8.cuh)
+        const int64_t base = bkc * HW + (int64_t)y_lo * W;
+        uint8_t* __restrict__ out8 = reinterpret_cast<uint8_t*>(hist) + base;
+        const uint32_t idx0 = (uint32_t)base;
+        if (first && (npix & 15) == 0 && (base & 15) == 0) {
+          // 8 words = 16 counters -> one 16 B store
+          for (int w = threadIdx.x * 8; w < nwords; w += kSmemThreads * 8) {
+            const uint4 va = *reinterpret_cast<const uint4*>(cnt + w), vb = *reinterpret_cast<const uint4*>(cnt + w + 4);
+            const uint32_t cw[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t c0 = cw[2 * j] & 0xffffu, c1 = cw[2 * j] >> 16, c2 = cw[2 * j + 1] & 0xffffu, c3 = cw[2 * j + 1] >> 16;
+              if ((c0 | c1 | c2 | c3) >= kHistU8Sat) {   // (a superset of "one of them saturates")
+                const uint32_t q = idx0 + 2u * (uint32_t)w + 4u * (uint32_t)j;
+                c0 = hist_u8_enc(sat_tail, q, c0), c1 = hist_u8_enc(sat_tail, q + 1, c1);
+                c2 = hist_u8_enc(sat_tail, q + 2, c2), c3 = hist_u8_enc(sat_tail, q + 3, c3);
+              }
+              o[j] = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+            }
+            st_stream_u4(reinterpret_cast<uint4*>(out8 + 2 * w), make_uint4(o[0], o[1], o[2], o[3]));
+          }
+        } else {
+          for (int q = threadIdx.x; q < npix; q += kSmemThreads) {
+            const uint32_t v = (cnt[q >> 1] >> ((q & 1) << 4)) & 0xffffu;
+            if (first) {
+              out8[q] = (uint8_t)hist_u8_enc(sat_tail, idx0 + (uint32_t)q, v);
+            } else if (v) {   // a further chunk of a very long micro-bin (same thread as the first chunk's write)
+              const uint32_t old = out8[q];
+              if (old < kHistU8Sat) {
+                out8[q] = (uint8_t)hist_u8_enc(sat_tail, idx0 + (uint32_t)q, old + v);
+              } else {
+                uint32_t n = sat_tail[0];
+                if (n > (uint32_t)EAS_HIST_U8_SAT_CAP) n = (uint32_t)EAS_HIST_U8_SAT_CAP;
+                uint2* ent = reinterpret_cast<uint2*>(sat_tail + 4);
+                for (uint32_t i = 0; i < n; ++i)
+                  if (ent[i].x == idx0 + (uint32_t)q) {
+                    ent[i].y += v;
+                    break;
+                  }
+              }
+            }
+          }
+        }
+      } else if (vec_ok) {
         // 2 words = 4 counters -> one 16 B store
         for (int w = threadIdx.x * 2; w < nwords; w += kSmemThreads * 2) {
           const uint2 v = *reinterpret_cast<const uint2*>(cnt + w);
@@ -333,7 +382,7 @@ SlabGeo slab_geo(int H, int W) {
 
 template <typename OUT_T, typename SRC>
 int launch_tiles(const SRC& src, const int64_t* bounds, int64_t n_items, int H, int W, int Tm, const SlabGeo& g,
-                 void* hist, unsigned int* counter, cudaStream_t stream) {
+                 void* hist, unsigned int* counter, cudaStream_t stream, uint32_t* sat_tail = nullptr) {
   auto kern = bin_hist_smem_kernel<OUT_T, SRC>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return (int)e;
@@ -341,7 +390,7 @@ int launch_tiles(const SRC& src, const int64_t* bounds, int64_t n_items, int H, 
   int64_t grid = (int64_t)EAS_NUM_SMS * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
   if (grid > n_items) grid = n_items;
   kern<<<(unsigned)grid, kSmemThreads, g.smem, stream>>>(src, bounds, n_items, H, W, Tm, g.n_slabs, g.slab_rows,
-                                                         (uint32_t*)hist, counter);
+                                                         (uint32_t*)hist, counter, sat_tail);
   EAS_LAUNCH_CHECK();
   return EAS_OK;
 }
@@ -424,7 +473,7 @@ extern "C" int eas_bin_dat(const void* rec, int64_t n_rec, const int64_t* ranges
   EAS_REQUIRE(H > 0 && W > 0 && H <= 16384 && W <= 16384 && Tm > 0 && Tm <= 1024, EAS_E_SHAPE);
   EAS_REQUIRE((int64_t)H * W < (1ll << 30), EAS_E_SHAPE);
   EAS_REQUIRE(strategy >= 0 && strategy <= 2, EAS_E_UNSUPPORTED);
-  EAS_REQUIRE(out_dtype == EAS_I32 || out_dtype == EAS_F32, EAS_E_UNSUPPORTED);
+  EAS_REQUIRE(out_dtype == EAS_I32 || out_dtype == EAS_F32 || out_dtype == EAS_U8, EAS_E_UNSUPPORTED);
   if (B == 0) return EAS_OK;
   EAS_REQUIRE(ranges && hist && ws && (rec || n_rec == 0), EAS_E_NULL);
   EAS_REQUIRE(ws_bytes >= eas_bin_dat_ws_bytes(B, Tm), EAS_E_WORKSPACE);
@@ -434,18 +483,28 @@ extern "C" int eas_bin_dat(const void* rec, int64_t n_rec, const int64_t* ranges
       (unsigned int*)((char*)ws + eas_align_up((size_t)B * (size_t)(Tm + 1) * sizeof(int64_t), 256));
   const DatSrc src{(const uint2*)rec, ranges, n_rec};
   const int64_t nb = B * (Tm + 1);
-  bin_bounds_kernel<DatSrc><<<(unsigned)eas_ceil_div(nb * 32, 128), 128, 0, stream>>>(src, B, Tm, bounds, counter);
+  const int64_t nbins = B * Tm * 2 * (int64_t)H * W;
+  uint32_t* sat_tail = nullptr;
+  if (out_dtype == EAS_U8) {
+    EAS_REQUIRE(nbins < (1ll << 32), EAS_E_SHAPE);
+    sat_tail = (uint32_t*)((char*)hist + hist_u8_tail_offset((size_t)nbins));
+  }
+  bin_bounds_kernel<DatSrc><<<(unsigned)eas_ceil_div(nb * 32, 128), 128, 0, stream>>>(src, B, Tm, bounds, counter,
+                                                                                    sat_tail);
   EAS_LAUNCH_CHECK();
   const SlabGeo g = slab_geo(H, W);
   const int64_t n_items = B * Tm * 2 * g.n_slabs;
   // window lengths live on the device: "auto" takes the write-once tiles whenever the frame fits them
   // (event windows of tens of ms), the event-parallel kernel otherwise
-  if (strategy == 0) strategy = (g.fits && n_items >= EAS_NUM_SMS) ? 2 : 1;
+  if (strategy == 0) strategy = (g.fits && (n_items >= EAS_NUM_SMS || out_dtype == EAS_U8)) ? 2 : 1;
   if (strategy == 2) {
     EAS_REQUIRE(g.fits, EAS_E_UNSUPPORTED);
+    if (out_dtype == EAS_U8)
+      return launch_tiles<uint8_t>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream, sat_tail);
     return out_dtype == EAS_F32 ? launch_tiles<float>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream)
                                 : launch_tiles<int32_t>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream);
   }
+  EAS_REQUIRE(out_dtype != EAS_U8, EAS_E_UNSUPPORTED);   // the byte form is written by the tiles kernel only
   const int64_t HW = (int64_t)H * W;
   cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)B * Tm * 2 * HW * sizeof(int32_t), stream);
   if (e != cudaSuccess) return (int)e;
@@ -473,7 +532,7 @@ extern "C" int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64
   EAS_REQUIRE(H > 0 && W > 0 && Tm > 0 && Tm <= 1024, EAS_E_SHAPE);
   EAS_REQUIRE((int64_t)H * W < (1ll << 30), EAS_E_SHAPE);
   EAS_REQUIRE(strategy >= 0 && strategy <= 2, EAS_E_UNSUPPORTED);
-  EAS_REQUIRE(out_dtype == EAS_I32 || out_dtype == EAS_F32, EAS_E_UNSUPPORTED);
+  EAS_REQUIRE(out_dtype == EAS_I32 || out_dtype == EAS_F32 || out_dtype == EAS_U8, EAS_E_UNSUPPORTED);
   if (B == 0) return EAS_OK;
   EAS_REQUIRE(offsets && hist && ws, EAS_E_NULL);
   EAS_REQUIRE(n_events == 0 || (x && y && t && p), EAS_E_NULL);
@@ -487,7 +546,13 @@ extern "C" int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64
   const int64_t HW = (int64_t)H * W;
   const int64_t nb = B * (Tm + 1);
   const SoaSrc src{x, y, t, p, offsets, n_events};
-  bin_bounds_kernel<SoaSrc><<<(unsigned)eas_ceil_div(nb * 32, 128), 128, 0, stream>>>(src, B, Tm, bounds, counter);
+  uint32_t* sat_tail = nullptr;
+  if (out_dtype == EAS_U8) {
+    EAS_REQUIRE(B * Tm * 2 * HW < (1ll << 32), EAS_E_SHAPE);
+    sat_tail = (uint32_t*)((char*)hist + hist_u8_tail_offset((size_t)(B * Tm * 2 * HW)));
+  }
+  bin_bounds_kernel<SoaSrc><<<(unsigned)eas_ceil_div(nb * 32, 128), 128, 0, stream>>>(src, B, Tm, bounds, counter,
+                                                                                    sat_tail);
   EAS_LAUNCH_CHECK();
 
   // row slabs so that one slab of 16-bit counters fits the per-CTA shared memory budget
@@ -498,13 +563,16 @@ extern "C" int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64
     // tiles: every event of a segment is scanned by 2*n_slabs CTAs (from L2); only worth it while
     // the write-once output dominates, i.e. for short windows; long windows go event-parallel.
     const bool enough = n_items >= EAS_NUM_SMS && n_events / (B * Tm) <= (1 << 17);
-    strategy = (fits && enough) ? 2 : 1;
+    strategy = (fits && (enough || out_dtype == EAS_U8)) ? 2 : 1;
   }
   if (strategy == 2) {
     EAS_REQUIRE(fits, EAS_E_UNSUPPORTED);
+    if (out_dtype == EAS_U8)
+      return launch_tiles<uint8_t>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream, sat_tail);
     return out_dtype == EAS_F32 ? launch_tiles<float>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream)
                                 : launch_tiles<int32_t>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream);
   } else {
+    EAS_REQUIRE(out_dtype != EAS_U8, EAS_E_UNSUPPORTED);   // the byte form is written by the tiles kernel only
     cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)B * Tm * 2 * HW * sizeof(int32_t), stream);
     if (e != cudaSuccess) return (int)e;
     if (n_events > 0) {
@@ -528,4 +596,63 @@ extern "C" int eas_bin_events(const int16_t* x, const int16_t* y, const int64_t*
                               const int64_t* offsets, int64_t B, int64_t n_events, int H, int W, int Tm,
                               int32_t* hist, void* ws, size_t ws_bytes, void* stream) {
   return eas_bin_events_ex(x, y, t, p, offsets, B, n_events, H, W, Tm, hist, ws, ws_bytes, stream, 0, EAS_I32);
+}
+
+// ---- compact histogram (hist_u8.cuh) -> dense counts ----------------------------------------------
+namespace {
+template <typename OUT_T>
+__global__ void __launch_bounds__(256)
+hist_u8_expand_kernel(const uint8_t* __restrict__ h, int64_t nbins, OUT_T* __restrict__ out,
+                      const int* __restrict__ run_if) {
+  if (run_if && *run_if == 0) return;
+  const uint32_t* tail = reinterpret_cast<const uint32_t*>(h + hist_u8_tail_offset((size_t)nbins));
+  const int64_t n4 = nbins >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t w = reinterpret_cast<const uint32_t*>(h)[i];
+    uint32_t c[4] = {w & 0xffu, (w >> 8) & 0xffu, (w >> 16) & 0xffu, w >> 24};
+    if (__vcmpeq4(w, 0xffffffffu)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c[j] == kHistU8Sat) c[j] = hist_u8_lookup(tail, (uint32_t)(4 * i + j));
+    }
+    if constexpr (std::is_same<OUT_T, float>::value)
+      reinterpret_cast<float4*>(out)[i] = make_float4((float)c[0], (float)c[1], (float)c[2], (float)c[3]);
+    else
+      reinterpret_cast<int4*>(out)[i] = make_int4((int)c[0], (int)c[1], (int)c[2], (int)c[3]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (nbins & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    uint32_t c = h[i];
+    if (c == kHistU8Sat) c = hist_u8_lookup(tail, (uint32_t)i);
+    out[i] = (OUT_T)c;
+  }
+}
+}  // namespace
+
+int eas_hist_u8_expand_if(const void* hist_u8, int64_t nbins, void* out, int out_dtype, const int* run_if,
+                          cudaStream_t stream) {
+  const unsigned grid = EAS_NUM_SMS * 8;
+  if (out_dtype == EAS_F32)
+    hist_u8_expand_kernel<float><<<grid, 256, 0, stream>>>((const uint8_t*)hist_u8, nbins, (float*)out, run_if);
+  else
+    hist_u8_expand_kernel<int32_t><<<grid, 256, 0, stream>>>((const uint8_t*)hist_u8, nbins, (int32_t*)out, run_if);
+  EAS_LAUNCH_CHECK();
+  return EAS_OK;
+}
+
+extern "C" size_t eas_hist_u8_bytes(int64_t B, int Tm, int H, int W) {
+  if (B <= 0 || Tm <= 0 || H <= 0 || W <= 0) return 0;
+  return hist_u8_bytes((size_t)B * (size_t)Tm * 2 * (size_t)H * (size_t)W);
+}
+
+extern "C" int eas_hist_u8_expand(const void* hist_u8, int64_t B, int Tm, int H, int W, void* out, int out_dtype,
+                                  void* stream) {
+  EAS_REQUIRE(B >= 0 && Tm > 0 && H > 0 && W > 0, EAS_E_SHAPE);
+  EAS_REQUIRE(out_dtype == EAS_I32 || out_dtype == EAS_F32, EAS_E_UNSUPPORTED);
+  if (B == 0) return EAS_OK;
+  EAS_REQUIRE(hist_u8 && out, EAS_E_NULL);
+  EAS_REQUIRE((uintptr_t)hist_u8 % 16 == 0 && (uintptr_t)out % 16 == 0, EAS_E_ALIGN);
+  const int64_t nbins = B * Tm * 2 * (int64_t)H * W;
+  EAS_REQUIRE(nbins < (1ll << 32), EAS_E_SHAPE);
+  return eas_hist_u8_expand_if(hist_u8, nbins, out, out_dtype, nullptr, (cudaStream_t)stream);
 }

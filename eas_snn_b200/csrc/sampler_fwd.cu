@@ -20,6 +20,7 @@
 // k 5), not HBM bound; see DESIGN.md.
 #include <type_traits>
 #include "sampler_common.cuh"
+#include "hist_u8.cuh"
 
 namespace {
 
@@ -421,7 +422,8 @@ int check(const eas_sampler_cfg* c) {
   EAS_REQUIRE(c->depth == 1 || c->depth == 2, EAS_E_UNSUPPORTED);
   EAS_REQUIRE(c->ksize == 3 || c->ksize == 5 || c->ksize == 7, EAS_E_UNSUPPORTED);
   EAS_REQUIRE(c->readout >= EAS_READOUT_SUM && c->readout <= EAS_READOUT_AVG, EAS_E_UNSUPPORTED);
-  EAS_REQUIRE(c->in_dtype == EAS_F32 || c->in_dtype == EAS_I32, EAS_E_UNSUPPORTED);
+  EAS_REQUIRE(c->in_dtype == EAS_F32 || c->in_dtype == EAS_I32 || c->in_dtype == EAS_U8, EAS_E_UNSUPPORTED);
+  if (c->in_dtype == EAS_U8) EAS_REQUIRE((int64_t)c->B * c->Tm * 2 * c->H * c->W < (1ll << 32), EAS_E_SHAPE);
   EAS_REQUIRE(c->algo >= EAS_SAMPLER_AUTO && c->algo <= EAS_SAMPLER_TENSOR_SPLIT, EAS_E_UNSUPPORTED);
   return EAS_OK;
 }
@@ -435,7 +437,10 @@ extern "C" size_t eas_sampler_fwd_ws_bytes(const eas_sampler_cfg* c) {
   // + the packed weight tiles of the tensor-core path
   const size_t wimg = eas_sampler_tc_wimg_bytes() > eas_sampler_tc2_wimg_bytes() ? eas_sampler_tc_wimg_bytes()
                                                                                : eas_sampler_tc2_wimg_bytes();
-  return 4 * eas_align_up(n * 4, 256) + eas_align_up(n * 2, 256) + 256 + eas_align_up(wimg, 256);
+  // + for the compact byte histogram: room for its dense fp32 form, which only the kernels that cannot read bytes
+  //   (FP32-pipe fall-back, first tensor-core kernel) ever touch
+  const size_t dense = c->in_dtype == EAS_U8 ? eas_align_up(n * (size_t)c->Tm * 4, 256) : 0;
+  return 4 * eas_align_up(n * 4, 256) + eas_align_up(n * 2, 256) + 256 + eas_align_up(wimg, 256) + dense;
 }
 
 extern "C" int eas_sampler_fwd(const eas_sampler_cfg* c, const void* events, const eas_sampler_weights* w,
@@ -465,6 +470,9 @@ extern "C" int eas_sampler_fwd(const eas_sampler_cfg* c, const void* events, con
   a.meta = (uint16_t*)p;
   p += eas_align_up(n * 2, 256);
   void* wimg = (void*)p;
+  p += eas_align_up(eas_sampler_tc_wimg_bytes() > eas_sampler_tc2_wimg_bytes() ? eas_sampler_tc_wimg_bytes()
+                                                                              : eas_sampler_tc2_wimg_bytes(), 256) + 256;
+  float* dense = (float*)p;   // in_dtype EAS_U8 only
   a.out = out;
   a.v_seq = v_seq;
   a.gate_seq = gate_seq;
@@ -481,7 +489,7 @@ extern "C" int eas_sampler_fwd(const eas_sampler_cfg* c, const void* events, con
   // data) raise a device flag; the FP32-pipe launches below then recompute the whole step sequence,
   // otherwise they exit at once.
   const bool tc2_ok = eas_sampler_tc2_supported(c, events, out, v_seq, gate_seq);
-  const bool tc1_ok = eas_sampler_tc_supported(c, events, out, v_seq, gate_seq);
+  const bool tc1_ok = c->in_dtype != EAS_U8 && eas_sampler_tc_supported(c, events, out, v_seq, gate_seq);
   if (c->algo == EAS_SAMPLER_TENSOR) EAS_REQUIRE(tc2_ok, EAS_E_UNSUPPORTED);
   if (c->algo == EAS_SAMPLER_TENSOR_SPLIT) EAS_REQUIRE(tc1_ok, EAS_E_UNSUPPORTED);
   if (tc2_ok && (c->algo == EAS_SAMPLER_AUTO || c->algo == EAS_SAMPLER_TENSOR)) {
@@ -497,6 +505,14 @@ extern "C" int eas_sampler_fwd(const eas_sampler_cfg* c, const void* events, con
   // 16-byte vector path: rows must keep 16 B alignment (W % 4 == 0) and so must every base pointer
   const bool vec = (c->W % 4 == 0) && ((uintptr_t)events % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
                    (!v_seq || ((uintptr_t)v_seq % 16 == 0 && (uintptr_t)gate_seq % 16 == 0));
+  if (c->in_dtype == EAS_U8) {
+    // the FP32-pipe kernel reads dense counts: expand the byte histogram (a no-op, like the step launches after it,
+    // unless the tensor-core kernel raised its flag)
+    rc = eas_hist_u8_expand_if(events, (int64_t)n * c->Tm, dense, EAS_F32, a.run_if, st);
+    if (rc) return rc;
+    a.events = dense;
+    return vec ? dispatch<float, true>(c, a, s0, s1, st) : dispatch<float, false>(c, a, s0, s1, st);
+  }
   if (c->in_dtype == EAS_F32)
     return vec ? dispatch<float, true>(c, a, s0, s1, st) : dispatch<float, false>(c, a, s0, s1, st);
   return vec ? dispatch<int32_t, true>(c, a, s0, s1, st) : dispatch<int32_t, false>(c, a, s0, s1, st);

@@ -46,6 +46,7 @@
 // element-wise work of the two epilogues (~24 k warp instructions per 2048-pixel tile) costs about as many issue
 // slots as the MMAs cost cycles; the kernel alternates between the two rather than overlapping them fully.
 #include "sampler_common.cuh"
+#include "hist_u8.cuh"
 
 namespace eas_sampler {
 namespace {
@@ -374,11 +375,24 @@ __device__ __noinline__ bool x0_fill_row(uint4 c0, uint4 c1, uint32_t spk, uint3
   return bad;
 }
 
+// exact counts of the saturated bytes of one quad (both channels) of the compact histogram
+__device__ __noinline__ void sat_fix(uint4& c0, uint4& c1, const uint32_t* __restrict__ tail, uint32_t q0, uint32_t HW) {
+  if (c0.x == kHistU8Sat) c0.x = hist_u8_lookup(tail, q0);
+  if (c0.y == kHistU8Sat) c0.y = hist_u8_lookup(tail, q0 + 1);
+  if (c0.z == kHistU8Sat) c0.z = hist_u8_lookup(tail, q0 + 2);
+  if (c0.w == kHistU8Sat) c0.w = hist_u8_lookup(tail, q0 + 3);
+  if (c1.x == kHistU8Sat) c1.x = hist_u8_lookup(tail, q0 + HW);
+  if (c1.y == kHistU8Sat) c1.y = hist_u8_lookup(tail, q0 + HW + 1);
+  if (c1.z == kHistU8Sat) c1.z = hist_u8_lookup(tail, q0 + HW + 2);
+  if (c1.w == kHistU8Sat) c1.w = hist_u8_lookup(tail, q0 + HW + 3);
+}
+
+// kIn: 0 = fp32 counts, 1 = int32 counts, 2 = the compact byte histogram (hist_u8.cuh).
 // kSimple: the published read-out (sum, Ts = 1, no ReLU on the frames, no saved sequences) -- seg is one bit
 // and t_last is not needed, which halves the update code of epilogue 2.
 // kStep (kSimple only): 0 first step, 1 middle, 2 last, 3 first and last (Tm == 1): compile-time first / last
 // remove a third of the update's predicate logic; -1 = decided at run time.
-template <bool kInt, bool kSimple, int kStep>
+template <int kIn, bool kSimple, int kStep>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 sampler_tc2_step_kernel(const StepArgs a, const Tc2State st, const Tc2Geo g, const uint8_t* __restrict__ wimg,
                         int* __restrict__ ovf_flag) {
@@ -442,16 +456,23 @@ sampler_tc2_step_kernel(const StepArgs a, const Tc2State st, const Tc2Geo g, con
     // (row group, quad) of all four row planes.  The loads of the next unit are in flight while the
     // current one is converted.
     const int pw = warp - W_PROD;
+    const uint32_t* sat_tail = reinterpret_cast<const uint32_t*>(
+        reinterpret_cast<const uint8_t*>(a.events) + hist_u8_tail_offset((size_t)a.B * a.Tm * 2 * HW));
+    (void)sat_tail;
     SegIter it(a, g);
     Seg s;
     int gt = 0;  // global X0 tile counter at the segment start
     while (it.next(s)) {
-      const uint32_t* ev_img =
-          reinterpret_cast<const uint32_t*>(a.events) + ((int64_t)s.b * a.Tm + tm) * 2 * HW;
+      // a thread's unit: one quad of both channels in each of the 4 row planes -- 16 B per (row, channel) of fp32 /
+      // int32 counts, 4 B of the compact byte histogram
+      using V = typename std::conditional<kIn == 2, uint32_t, uint4>::type;
+      constexpr int EB = kIn == 2 ? 1 : 4;   // bytes per count
+      const int64_t img_bin0 = ((int64_t)s.b * a.Tm + tm) * 2 * HW;
+      const uint8_t* ev_img = reinterpret_cast<const uint8_t*>(a.events) + img_bin0 * EB;
       const uint8_t* sp_img = st.sb_prev + (int64_t)s.b * 2 * a.H * WQ;
-      uint4 cur[4][2], nxt[4][2] = {};
+      V cur[4][2], nxt[4][2] = {};
       uint32_t csp[4], nsp[4] = {};
-      auto load_unit = [&](int u, uint4 (&v)[4][2], uint32_t (&sp)[4]) {
+      auto load_unit = [&](int u, V (&v)[4][2], uint32_t (&sp)[4]) {
         const int p = u * TILE + pw * 32 + lane;
         const int grp = p / QPR, m = p - grp * QPR;
         const int x = s.xs - 4 + 4 * m;
@@ -461,8 +482,13 @@ sampler_tc2_step_kernel(const StepArgs a, const Tc2State st, const Tc2Geo g, con
           const int y = s.ya - 4 + 4 * grp + rho;
           const bool ok = col_ok && (unsigned)y < (unsigned)a.H;
           const int64_t off = ok ? (int64_t)y * a.W + x : 0;
-          v[rho][0] = ok ? ld_stream_u4(reinterpret_cast<const uint4*>(ev_img + off)) : make_uint4(0u, 0u, 0u, 0u);
-          v[rho][1] = ok ? ld_stream_u4(reinterpret_cast<const uint4*>(ev_img + HW + off)) : make_uint4(0u, 0u, 0u, 0u);
+          if constexpr (kIn == 2) {
+            v[rho][0] = ok ? ld_stream_u32(reinterpret_cast<const uint32_t*>(ev_img + off)) : 0u;
+            v[rho][1] = ok ? ld_stream_u32(reinterpret_cast<const uint32_t*>(ev_img + HW + off)) : 0u;
+          } else {
+            v[rho][0] = ok ? ld_stream_u4(reinterpret_cast<const uint4*>(ev_img + off * 4)) : make_uint4(0u, 0u, 0u, 0u);
+            v[rho][1] = ok ? ld_stream_u4(reinterpret_cast<const uint4*>(ev_img + (HW + off) * 4)) : make_uint4(0u, 0u, 0u, 0u);
+          }
           sp[rho] = (ok && !first) ? ((ld_stream_u8(sp_img + y * WQ + (x >> 2)) & 15u) |
                                       (ld_stream_u8(sp_img + (a.H + y) * WQ + (x >> 2)) << 4))
                                    : 0u;
@@ -486,8 +512,23 @@ sampler_tc2_step_kernel(const StepArgs a, const Tc2State st, const Tc2Geo g, con
         const uint32_t mirror = (slot == 0 && qt == 0) ? 1u : 0u;
         bool bad = false;
 #pragma unroll
-        for (int rho = 0; rho < 4; ++rho)
-          bad |= x0_fill_row<kInt>(cur[rho][0], cur[rho][1], csp[rho], row0 + (uint32_t)rho * X0_PLANE, sw, mirror);
+        for (int rho = 0; rho < 4; ++rho) {
+          if constexpr (kIn == 2) {
+            const uint32_t w0 = cur[rho][0], w1 = cur[rho][1];
+            uint4 c0 = make_uint4(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu, w0 >> 24);
+            uint4 c1 = make_uint4(w1 & 0xffu, (w1 >> 8) & 0xffu, (w1 >> 16) & 0xffu, w1 >> 24);
+            if (__vcmpeq4(w0, 0xffffffffu) | __vcmpeq4(w1, 0xffffffffu)) {
+              // a saturated byte (rare): its exact count is in the list behind the histogram
+              const int p = u * TILE + pw * 32 + lane;
+              const int grp = p / QPR, m = p - grp * QPR;
+              const uint32_t q0 = (uint32_t)(img_bin0 + (int64_t)(s.ya - 4 + 4 * grp + rho) * a.W + (s.xs - 4 + 4 * m));
+              sat_fix(c0, c1, sat_tail, q0, (uint32_t)HW);
+            }
+            bad |= x0_fill_row<true>(c0, c1, csp[rho], row0 + (uint32_t)rho * X0_PLANE, sw, mirror);
+          } else {
+            bad |= x0_fill_row<kIn == 1>(cur[rho][0], cur[rho][1], csp[rho], row0 + (uint32_t)rho * X0_PLANE, sw, mirror);
+          }
+        }
         if (bad) *ovf_flag = 1;
         fence_async_smem();
         __syncwarp();
@@ -896,17 +937,19 @@ int eas_sampler_tc2_run(const eas_sampler_cfg* cfg, StepArgs a, uint8_t* meta8, 
   EAS_REQUIRE((int64_t)cfg->B * g.ns * cfg->H < (1ll << 31) && (int64_t)cfg->H * cfg->W * 2 < (1ll << 31), EAS_E_SHAPE);
   const bool simple = cfg->readout == EAS_READOUT_SUM && cfg->Ts == 1 && !cfg->use_abs && a.v_seq == nullptr;
   using kern_t = void (*)(const StepArgs, const Tc2State, const Tc2Geo, const uint8_t*, int*);
-  const bool ki = cfg->in_dtype == EAS_I32;
+  const int ki = cfg->in_dtype == EAS_I32 ? 1 : (cfg->in_dtype == EAS_U8 ? 2 : 0);
   kern_t kerns[4];  // by step kind: first, middle, last, first and last
+#define TC2_PICK(S, K) (ki == 2 ? sampler_tc2_step_kernel<2, S, K> : ki == 1 ? sampler_tc2_step_kernel<1, S, K> \
+                                                                            : sampler_tc2_step_kernel<0, S, K>)
   if (simple) {
-    kerns[0] = ki ? sampler_tc2_step_kernel<true, true, 0> : sampler_tc2_step_kernel<false, true, 0>;
-    kerns[1] = ki ? sampler_tc2_step_kernel<true, true, 1> : sampler_tc2_step_kernel<false, true, 1>;
-    kerns[2] = ki ? sampler_tc2_step_kernel<true, true, 2> : sampler_tc2_step_kernel<false, true, 2>;
-    kerns[3] = ki ? sampler_tc2_step_kernel<true, true, 3> : sampler_tc2_step_kernel<false, true, 3>;
+    kerns[0] = TC2_PICK(true, 0);
+    kerns[1] = TC2_PICK(true, 1);
+    kerns[2] = TC2_PICK(true, 2);
+    kerns[3] = TC2_PICK(true, 3);
   } else {
-    kerns[0] = kerns[1] = kerns[2] = kerns[3] =
-        ki ? sampler_tc2_step_kernel<true, false, -1> : sampler_tc2_step_kernel<false, false, -1>;
+    kerns[0] = kerns[1] = kerns[2] = kerns[3] = TC2_PICK(false, -1);
   }
+#undef TC2_PICK
   for (int i = 0; i < 4; ++i) {
     cudaError_t e = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;

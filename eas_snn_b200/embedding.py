@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .binning import bin_events
+from .binning import CompactHist, bin_events, compact_fits
 
 
 def _cfg(B, H, W, Tm, mod, in_dtype):
@@ -43,7 +43,10 @@ def _sampler_forward(events, mod, params, want_seq):
     Returns (out [Ts,B,2,H,W], v_seq, gate_seq ([Tm,B,2,H,W] each, sampler step order, or None), cfg, plist)."""
     L = _lib.lib()
     B, Tm, Cc, H, W = events.shape
-    in_dtype = _lib.EAS_I32 if events.dtype == torch.int32 else _lib.EAS_F32
+    if isinstance(events, CompactHist):
+        in_dtype, ev_buf = _lib.EAS_U8, events.buf
+    else:
+        in_dtype, ev_buf = (_lib.EAS_I32 if events.dtype == torch.int32 else _lib.EAS_F32), events
     cfg = _cfg(B, H, W, Tm, mod, in_dtype)
     if mod.depth == 2:
         iw0, ib0, iw1, ib1, gw0, gb0, gw1, gb1 = params
@@ -62,7 +65,7 @@ def _sampler_forward(events, mod, params, want_seq):
     ws_bytes = L.eas_sampler_fwd_ws_bytes(C.byref(cfg))
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        rc = L.eas_sampler_fwd(C.byref(cfg), _lib.ptr(events), C.byref(wstruct), _lib.ptr(out),
+        rc = L.eas_sampler_fwd(C.byref(cfg), _lib.ptr(ev_buf), C.byref(wstruct), _lib.ptr(out),
                                _lib.ptr(v_seq), _lib.ptr(gate_seq), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
     _lib.check(rc, "eas_sampler_fwd")
     return out, v_seq, gate_seq, cfg, plist
@@ -173,6 +176,12 @@ class AdaptiveRSNNEmbedding(nn.Module):
         return out
 
     def forward(self, events, record=False, v_record=False):
+        if isinstance(events, CompactHist):   # the byte histogram of bin_events(dtype=torch.uint8): read as it is
+            params = self._params()
+            if record or v_record or self.algo == "tensor_split" or \
+                    (torch.is_grad_enabled() and any(q.requires_grad for q in params)):
+                return self.forward(events.dense(torch.float32), record, v_record)
+            return _sampler_forward(events, self, params, False)[0]
         if events.dim() < 5:  # parameter-registering passthrough (embedding.py:144-146)
             events, _ = torch.broadcast_tensors(events, torch.zeros((self.Ts,) + events.shape,
                                                                     device=events.device))
@@ -215,20 +224,37 @@ class AdaptiveRSNNEmbedding(nn.Module):
             return out, torch.stack(t_rec, dim=0)
         return out, torch.cat(v_rec)
 
-    def forward_events(self, x, y, t, p, offsets, H: int, W: int, strategy: str = "auto"):
+    def _hist_dtype(self, H, W, strategy, hist_dtype):
+        """The histogram format between binning and sampling: ``"compact"`` = one byte per bin + the exact list of
+        saturated bins (a quarter of the bytes written and read; the tensor-core kernel and the tiles binning
+        kernel), ``"dense"`` = fp32 counts, ``"auto"`` = compact whenever those two kernels take the call."""
+        if hist_dtype not in ("auto", "compact", "dense"):
+            raise ValueError("hist_dtype must be 'auto', 'compact' or 'dense'")
+        ok = (self.depth == 2 and self.kernel_size == 5 and W % 4 == 0 and self.Ts <= 15 and self.nb_steps <= 14 and
+              self.algo in ("auto", "tensor") and strategy in ("auto", "tiles") and compact_fits(H, W) and
+              not (torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters())))
+        if hist_dtype == "compact" and not ok:
+            raise ValueError("the compact histogram needs the tensor-core sampler (depth 2, k 5, W % 4 == 0, inference) "
+                             "and a frame that fits the tiles binning kernel")
+        return torch.uint8 if (ok and hist_dtype != "dense") else torch.float32
+
+    def forward_events(self, x, y, t, p, offsets, H: int, W: int, strategy: str = "auto", hist_dtype: str = "auto"):
         """Raw time-sorted event windows -> adaptive frames ``[Ts, B, 2, H, W]``.
 
-        Binning (gen1.py:313-360) and sampling (embedding.py:141-226) back to back on the GPU;
-        the histogram is written as fp32 counts and consumed directly by the sampler kernel.
+        Binning (gen1.py:313-360) and sampling (embedding.py:141-226) back to back on the GPU; the histogram between
+        them is the compact byte form (:class:`eas_snn_b200.binning.CompactHist`) where the kernels support it, fp32
+        counts otherwise -- the same frames either way.
         """
-        hist = bin_events(x, y, t, p, offsets, H, W, self.nb_steps, strategy=strategy, dtype=torch.float32)
+        hist = bin_events(x, y, t, p, offsets, H, W, self.nb_steps, strategy=strategy,
+                          dtype=self._hist_dtype(H, W, strategy, hist_dtype))
         return self.forward(hist)
 
-    def forward_dat(self, records, ranges, H: int, W: int, strategy: str = "auto"):
+    def forward_dat(self, records, ranges, H: int, W: int, strategy: str = "auto", hist_dtype: str = "auto"):
         """Raw PSEE ``.dat`` records + one record range per window (:func:`eas_snn_b200.psee.dat_windows`)
         -> adaptive frames ``[Ts, B, 2, H, W]``: decode, binning and sampling without leaving the GPU."""
         from .psee import bin_dat
-        hist = bin_dat(records, ranges, H, W, self.nb_steps, strategy=strategy, dtype=torch.float32)
+        hist = bin_dat(records, ranges, H, W, self.nb_steps, strategy=strategy,
+                       dtype=self._hist_dtype(H, W, strategy, hist_dtype))
         return self.forward(hist)
 
 
@@ -264,7 +290,7 @@ class SpikeCountEmbedding(nn.Module):
 
     def forward_events(self, x, y, t, p, offsets, H: int, W: int):
         """Raw windows -> count frames ``[B, 2, H, W]``: binning (gen1.py:313-360) + the sum over micro-bins."""
-        from .binning import bin_events
+        from .binning import CompactHist, bin_events, compact_fits
         return self.forward(bin_events(x, y, t, p, offsets, H, W, self.nb_steps))
 
 

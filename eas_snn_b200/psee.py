@@ -88,8 +88,9 @@ def dat_windows(records: torch.Tensor, t_label: torch.Tensor, window=(-50000, 0)
 
 
 def bin_dat(records: torch.Tensor, ranges: torch.Tensor, H: int, W: int, Tm: int, strategy: str = "auto",
-            out: torch.Tensor | None = None, dtype: torch.dtype = torch.int32) -> torch.Tensor:
-    """Histogram record ranges: ``[B, Tm, 2, H, W]`` int32 / float32 counts, bit-identical to decoding the
+            out=None, dtype: torch.dtype = torch.int32):
+    """Histogram record ranges: ``[B, Tm, 2, H, W]`` int32 / float32 counts (or the compact byte form,
+    ``dtype=torch.uint8`` -> :class:`eas_snn_b200.binning.CompactHist`), bit-identical to decoding the
     records and calling :func:`eas_snn_b200.bin_events` (``agrregate('micro_sum')``, gen1.py:313-360)."""
     records = _records(records)
     _lib.require_cuda(ranges)
@@ -97,20 +98,18 @@ def bin_dat(records: torch.Tensor, ranges: torch.Tensor, H: int, W: int, Tm: int
         raise TypeError("ranges must be int64 [B, 2]")
     ranges = ranges.contiguous()
     B = ranges.shape[0]
-    if out is None:
-        if dtype not in (torch.int32, torch.float32):
-            raise TypeError("histogram dtype must be int32 or float32")
-        out = torch.empty((B, Tm, 2, H, W), dtype=dtype, device=records.device)
-    elif (out.shape != (B, Tm, 2, H, W) or out.dtype not in (torch.int32, torch.float32) or not out.is_contiguous()):
-        raise ValueError("out must be a contiguous int32/float32 [B, Tm, 2, H, W] tensor")
+    from .binning import CompactHist, _hist_out, poll_compact
+    out, buf, eas_dtype = _hist_out(B, Tm, H, W, out, dtype, records.device)
     L = _lib.lib()
     ws_bytes = L.eas_bin_dat_ws_bytes(B, Tm)
     ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=records.device)
     with torch.cuda.device(records.device):
-        rc = L.eas_bin_dat(_lib.ptr(records), records.shape[0], _lib.ptr(ranges), B, H, W, Tm, _lib.ptr(out),
-                           _lib.ptr(ws), ws_bytes, _lib.stream_ptr(), STRATEGY[strategy],
-                           _lib.EAS_F32 if out.dtype == torch.float32 else _lib.EAS_I32)
+        rc = L.eas_bin_dat(_lib.ptr(records), records.shape[0], _lib.ptr(ranges), B, H, W, Tm, _lib.ptr(buf),
+                           _lib.ptr(ws), ws_bytes, _lib.stream_ptr(), STRATEGY[strategy], eas_dtype)
     _lib.check(rc, "eas_bin_dat")
+    if isinstance(out, CompactHist) and B > 0:
+        poll_compact()
+        out._queue_check()
     return out
 
 

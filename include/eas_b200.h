@@ -62,7 +62,21 @@ int eas_bin_events(const int16_t* x, const int16_t* y, const int64_t* t, const u
                    int32_t* hist, void* ws, size_t ws_bytes, void* stream);
 /* Same with options: strategy 0 = auto, 1 = global reductions, 2 = shared-memory tiles;
  * out_dtype EAS_I32, or EAS_F32 (the counts as fp32, exact below 2^24: what the sampler's first
- * convolution consumes, and the dtype the reference casts its histogram to on the device). */
+ * convolution consumes, and the dtype the reference casts its histogram to on the device), or EAS_U8:
+ * the compact form the sampler reads directly (eas_sampler_cfg.in_dtype = EAS_U8) -- a quarter of the
+ * bytes to write and to read.  `hist` is then ONE buffer of eas_hist_u8_bytes(B, Tm, H, W) bytes:
+ *   [0, nbins)                    uint8 min(count, 255), nbins = B*Tm*2*H*W (< 2^32)
+ *   at nbins rounded up to 256    uint32 n_sat, uint32 lost, uint32 pad[2],
+ *                                 then EAS_HIST_U8_SAT_CAP x {uint32 bin index, uint32 count} for the
+ *                                 bins that reached 255: the information of the int histogram, exactly,
+ *                                 unless more than EAS_HIST_U8_SAT_CAP bins saturate in one call (lost = 1;
+ *                                 callers check it -- the Python side raises).
+ * EAS_U8 is written by the shared-memory tiles strategy only (frames that fit it; EAS_E_UNSUPPORTED
+ * otherwise).  eas_hist_u8_expand turns it back into the dense int32 / fp32 histogram. */
+#define EAS_HIST_U8_SAT_CAP 4096
+size_t eas_hist_u8_bytes(int64_t B, int Tm, int H, int W);
+int eas_hist_u8_expand(const void* hist_u8, int64_t B, int Tm, int H, int W, void* out, int out_dtype,
+                       void* stream);
 int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64_t* t, const uint8_t* p,
                       const int64_t* offsets, int64_t B, int64_t n_events, int H, int W, int Tm,
                       void* hist, void* ws, size_t ws_bytes, void* stream, int strategy, int out_dtype);
@@ -94,7 +108,7 @@ int eas_bin_dat(const void* rec, int64_t n_rec, const int64_t* ranges, int64_t B
  * (a-2) Adaptive event sampler.  Replaces AdaptiveRSNNEmbedding.forward / update,
  *       yolox/models/embedding.py:132-226 with the Rectangle surrogate, activation.py:17-30.
  *
- * events [B][Tm][2][H][W] (f32, or the int32 histogram of eas_bin_events);
+ * events [B][Tm][2][H][W] (f32, or the int32 / compact uint8 histogram of eas_bin_events);
  * weights of input_conv / gate_conv in PyTorch layout: w0 [4][2][k][k], b0 [4] and, for
  * depth == 2, w1 [4][4][k][k], b1 [4] (pass NULL for depth 1);
  * out [Ts][B][2][H][W] f32, fully written.
@@ -112,7 +126,7 @@ typedef struct {
   int32_t spike_attach; /* SAT: read-out multiplied by the spike                 */
   int32_t write_zero;   /* RPD: residual potential of silent pixels dropped      */
   int32_t use_abs;      /* relu on the aggregated frames                         */
-  int32_t in_dtype;     /* EAS_F32 or EAS_I32                                    */
+  int32_t in_dtype;     /* EAS_F32, EAS_I32 or EAS_U8 (compact histogram, see above) */
   int32_t algo;         /* EAS_SAMPLER_* (forward only): AUTO picks the row-folded tensor-core kernel for
                            depth 2, k 5, W % 4 == 0, 16 B aligned buffers (and re-runs on the FP32-pipe
                            kernel when an input is not exact in fp16), else the FP32-pipe kernel */

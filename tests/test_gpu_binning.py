@@ -116,3 +116,86 @@ def test_letterbox_frames_match_the_reference_resize(cuda):
     hist = torch.poisson(torch.full((2, 4, 2, 240, 304), 0.5)).to(cuda)
     out = eas.letterbox_frames(hist, (640, 640))
     assert out.shape == (2, 4, 2, 640, 640) and not out[..., 505:, :].any() and out[..., :505, :].any()
+
+
+# ---- the compact byte histogram (EAS_U8): same information as the int32 histogram --------------------------------
+def _compact_vs_dense(d, H, W, Tm, want_i32):
+    ch = eas.bin_events(*d, H, W, Tm, dtype=torch.uint8)
+    assert isinstance(ch, eas.CompactHist) and ch.shape == tuple(want_i32.shape)
+    ch.check()
+    want = torch.from_numpy(want_i32)
+    assert torch.equal(ch.counts.cpu(), want.clamp(max=255).to(torch.uint8))            # bytes: min(count, 255)
+    assert torch.equal(ch.dense(torch.int32).cpu(), want)                                 # exact again through the list
+    assert torch.equal(ch.dense(torch.float32).cpu(), want.float())
+    idx, cnt = ch.saturated()
+    sat = (want.flatten() >= 255).nonzero().flatten()
+    order = torch.argsort(idx.cpu())
+    assert torch.equal(idx.cpu()[order], sat) and torch.equal(cnt.cpu()[order].long(), want.flatten()[sat].long())
+    return ch
+
+
+def test_compact_histogram_golden_cases(cuda):
+    """Every reference golden (incl. the pixel whose count passes 65535 -- several 16-bit chunks -- and tw == 0)."""
+    z = load_golden("binning")
+    n_sat = 0
+    for name in z["names"]:
+        H, W, Tm = (int(v) for v in z[f"{name}/dims"])
+        x, y, t, p = (z[f"{name}/{k}"] for k in "xytp")
+        off = np.array([0, len(x)], np.int64)
+        want = z[f"{name}/hist"][None].astype(np.int32)
+        if not eas.binning.compact_fits(H, W):
+            with pytest.raises(RuntimeError):
+                eas.bin_events(*_dev((x, y, t, p, off), cuda), H, W, Tm, dtype=torch.uint8)
+            continue
+        ch = _compact_vs_dense(_dev((x, y, t, p, off), cuda), H, W, Tm, want)
+        n_sat += int(ch.tail[0])
+    assert n_sat > 0, "no golden exercised the saturation list"
+
+
+def test_compact_histogram_hot_pixels_and_gen1_batch(cuda):
+    """Gen1 batch with planted hot pixels at 254 / 255 / 256 / 3000 events per micro-bin, SoA and .dat front doors."""
+    H, W = synth.GEN1
+    x, y, t, p, off = synth.gen1_batch(8)
+    rng = np.random.default_rng(5)
+    xs, ys, ts, ps, sizes = [], [], [], [], []
+    for b in range(8):
+        s, e = int(off[b]), int(off[b + 1])
+        xb, yb, tb, pb = x[s:e].copy(), y[s:e].copy(), t[s:e].copy(), p[s:e].copy()
+        first_bin = np.nonzero(tb < tb[0] + (tb[-1] - tb[0]) // 4)[0]
+        for k, n_hot in enumerate((254, 255, 256, 3000)):
+            seg = len(first_bin) // 4
+            sel = first_bin[k * seg:k * seg + min(n_hot, seg)]        # move these events onto one pixel / polarity
+            xb[sel], yb[sel], pb[sel] = 10 + k, 20 + b, (k + b) & 1
+        xs.append(xb), ys.append(yb), ts.append(tb), ps.append(pb), sizes.append(e - s)
+    x, y, t, p = (np.concatenate(v) for v in (xs, ys, ts, ps))
+    want = ob.micro_sum_batch(x, y, t, p, off, H, W, 4).astype(np.int32)
+    assert (want >= 255).sum() >= 8 * 3
+    d = _dev((x, y, t, p, off), cuda)
+    _compact_vs_dense(d, H, W, 4, want)
+    rec = torch.from_numpy(eas.pack_records(x, y, t, p)).to(cuda)
+    rng_ = torch.from_numpy(np.stack([off[:-1], off[1:]], 1)).to(cuda)
+    ch = eas.bin_dat(rec, rng_, H, W, 4, dtype=torch.uint8)
+    assert torch.equal(ch.dense().cpu(), torch.from_numpy(want))
+    buf = eas.CompactHist.empty((8, 4, 2, H, W), cuda)            # caller-owned buffer, reused
+    for _ in range(2):
+        assert eas.bin_events(*d, H, W, 4, out=buf) is buf
+        assert torch.equal(buf.dense().cpu(), torch.from_numpy(want))
+
+
+def test_compact_histogram_reports_lost_counts(cuda):
+    """More saturated bins than the list holds: the call says so (lazily through poll_compact, or .check())."""
+    H, W, per = 64, 80, 256
+    n = H * W * per
+    x = np.tile(np.arange(W, dtype=np.int16), H * per)
+    y = np.repeat(np.arange(H, dtype=np.int16), W * per)
+    t = np.arange(n, dtype=np.int64)
+    p = np.ones(n, np.uint8)
+    order = np.random.default_rng(0).permutation(n)
+    d = _dev((x[order], y[order], t, p, np.array([0, n], np.int64)), cuda)
+    ch = eas.bin_events(*d, H, W, 1, dtype=torch.uint8)
+    with pytest.raises(OverflowError):
+        ch.check()
+    with pytest.raises(OverflowError):
+        eas.poll_compact(wait=True)
+    eas.poll_compact(wait=True)                                     # reported once
+    assert int(eas.bin_events(*d, H, W, 1).sum()) == n - 1          # the dense histogram is unaffected (last event: t == t0 + tw, dropped)

@@ -356,3 +356,62 @@ def test_voxel_grid_golden_and_oracle(cuda):
         sl = slice(off[b], off[b + 1])
         want = reps.to_voxel_grid(arrs[0][sl], arrs[1][sl], arrs[2][sl], arrs[3][sl], 120, 152, 6, p_is_bool=False)
         assert torch.allclose(got[b], torch.from_numpy(want).float(), rtol=1e-5, atol=2e-5), b
+
+
+# ---- the compact byte histogram as the sampler's input (in_dtype EAS_U8) ------------------------------------------
+@pytest.mark.parametrize("flags", [dict(readout="sum", Ts=1, vreset=0, spike_attach=True, write_zero=True, abs=False),
+                                   dict(readout="avg", Ts=2, vreset=None, spike_attach=False, write_zero=False, abs=True)])
+def test_compact_histogram_input_is_bit_identical_to_dense(cuda, flags):
+    """Same counts, same fp16 operands, same kernel: the byte histogram (incl. saturated bins served from its list,
+    and a count beyond fp16's exact range that sends both down the FP32 fall-back) gives the dense input's frames
+    bit for bit -- on ragged geometries and at the Gen1 shape."""
+    torch.manual_seed(21)
+    for (B, Tm, H, W), hot in (((3, 4, 61, 100), (255, 300)), ((8, 4, 240, 304), (254, 255, 1999)), ((2, 3, 33, 480), (5000,)),
+                               ((2, 4, 40, 64), ())):
+        m = eas.AdaptiveRSNNEmbedding(kernel_size=5, depth=2, nb_steps=Tm, thresh=1, **flags).to(cuda)
+        rng = np.random.default_rng(B * 7 + H)
+        n = int(B * H * W * 1.5)
+        sizes = rng.multinomial(n, np.ones(B) / B)
+        parts = [synth.make_window(rng, int(k), H, W) for k in sizes]
+        x, y, t, p = (np.concatenate([q[i] for q in parts]) for i in range(4))
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        for j, n_hot in enumerate(hot):                # hot pixels in the first micro-bin of window 0 and the last of B-1
+            s, e = (int(off[0]), int(off[1])) if j % 2 == 0 else (int(off[B - 1]), int(off[B]))
+            sel = np.arange(s, s + n_hot) if j % 2 == 0 else np.arange(e - n_hot - 1, e - 1)
+            x[sel], y[sel], p[sel] = 7 + 4 * j, 5 + j, j & 1
+        d = [torch.from_numpy(a).to(cuda) for a in (x, y, t, p, off)]
+        ch = eas.bin_events(*d, H, W, Tm, dtype=torch.uint8)
+        dense = eas.bin_events(*d, H, W, Tm, dtype=torch.float32)
+        assert torch.equal(ch.dense(torch.float32), dense)
+        if hot:
+            assert int(ch.tail[0]) >= 1 and int(dense.max()) >= 255
+        for algo in ("auto", "fp32"):
+            m.algo = algo
+            with torch.no_grad():
+                a, b = m(ch), m(dense)
+            assert torch.equal(a, b), ((B, Tm, H, W), algo, float((a - b).abs().max()))
+        m.algo = "auto"
+        with torch.no_grad():
+            b = m(dense)
+        with torch.no_grad():
+            c = m.forward_events(*d, H, W, hist_dtype="compact")
+            e_ = m.forward_events(*d, H, W, hist_dtype="dense")
+            f_ = m.forward_events(*d, H, W)
+        assert torch.equal(c, b) and torch.equal(e_, b) and torch.equal(f_, b)
+
+
+def test_compact_histogram_training_and_unsupported_shapes_take_the_dense_path(cuda):
+    torch.manual_seed(22)
+    H, W = 30, 50                                       # W % 4 != 0: FP32-pipe sampler; the byte form is still accepted
+    arrs = synth.make_batch(9, 2, H, W, 3e3, 6e3)
+    d = [torch.from_numpy(a).to(cuda) for a in arrs]
+    m = eas.AdaptiveRSNNEmbedding(kernel_size=5, depth=2, nb_steps=4, thresh=1, vreset=0, Ts=1).to(cuda)
+    ch = eas.bin_events(*d, H, W, 4, dtype=torch.uint8)
+    with torch.no_grad():
+        assert torch.equal(m(ch), m(ch.dense(torch.float32)))
+        assert torch.equal(m.forward_events(*d, H, W), m(ch.dense(torch.float32)))
+    with pytest.raises(ValueError):
+        m.forward_events(*d, H, W, hist_dtype="compact")
+    out = m(ch)                                         # grad mode: dense path, differentiable w.r.t. the parameters
+    out.sum().backward()
+    assert m.input_conv[0].weight.grad is not None and float(m.input_conv[0].weight.grad.abs().sum()) > 0
