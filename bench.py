@@ -250,10 +250,14 @@ def run_ours(args):
     host = [HostEventBatch(*b) for b in host_np]
     devb = [hb.to_device(dev) for hb in host]
     hist_buf = torch.empty((BATCH, TM, 2, H, W), dtype=torch.float32, device=dev)
+    # the histogram between the two kernels is the compact byte form (one byte per bin + the exact list of saturated
+    # bins, include/eas_b200.h EAS_U8): the same information as the reference's dense tensor, a quarter of the bytes
+    # to write and to read -- what forward_events / forward_dat use whenever the tensor-core sampler takes the call
+    chist_buf = eas.CompactHist.empty((BATCH, TM, 2, H, W), dev)
     torch.cuda.synchronize()
 
     def step(db):
-        hist = eas.bin_events(*db, H, W, TM, out=hist_buf)
+        hist = eas.bin_events(*db, H, W, TM, out=chist_buf)
         with torch.no_grad():
             return model(hist)
 
@@ -584,24 +588,35 @@ def run_ours(args):
                  "loss": float(loss.detach())}
 
     # ---- per-kernel durations (CUDA events on the launching stream) for the roofline -----------
-    def time_call(fn, reps=10, warm=3):
+    def time_call(fn, reps=10, warm=3, inner=16):
+        """Median over `reps` of (CUDA-event time of `inner` back-to-back calls) / inner.  One call between two events
+        measures the host's launch latency too (the GPU idles while Python issues a 60 us kernel); a queue of calls
+        keeps the device busy, which is also how the step loop drives these kernels."""
         ts = []
         for r in range(warm + reps):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
             a.record()
-            fn(r)
+            for i in range(inner):
+                fn(r * inner + i)
             b.record()
             torch.cuda.synchronize()
             if r >= warm:
-                ts.append(a.elapsed_time(b))
+                ts.append(a.elapsed_time(b) / inner)
         return float(np.median(ts))
 
-    t_bin = time_call(lambda r: eas.bin_events(*devb[r % NSETS], H, W, TM, out=hist_buf))
+    # (four output buffers in turn, 150 MB: a single 37 MB buffer would simply stay in L2 between the calls)
+    chist_rot = [chist_buf] + [eas.CompactHist.empty((BATCH, TM, 2, H, W), dev) for _ in range(NSETS - 1)]
+    t_bin = time_call(lambda r: eas.bin_events(*devb[r % NSETS], H, W, TM, out=chist_rot[r % NSETS]))
+    t_bin_f32 = time_call(lambda r: eas.bin_events(*devb[r % NSETS], H, W, TM, out=hist_buf))
     rec_dev = [(r.to(dev), g.to(dev)) for r, g in zip(host_rec, host_rng)]
-    t_bin_dat = time_call(lambda r: psee.bin_dat(*rec_dev[r % NSETS], H, W, TM, out=hist_buf))
+    t_bin_dat = time_call(lambda r: psee.bin_dat(*rec_dev[r % NSETS], H, W, TM, out=chist_rot[r % NSETS]))
+    del chist_rot
     hist_fixed = eas.bin_events(*devb[0], H, W, TM, dtype=torch.float32).clone()
+    chist_fixed = eas.bin_events(*devb[0], H, W, TM, dtype=torch.uint8)
     with torch.no_grad():
-        t_smp = time_call(lambda r: model(hist_fixed))
+        t_smp = time_call(lambda r: model(chist_fixed))
+        t_smp_dense = time_call(lambda r: model(hist_fixed))
         model.algo = "fp32"
         t_smp_fp32 = time_call(lambda r: model(hist_fixed))
         model.algo = "auto"
@@ -626,6 +641,7 @@ def run_ours(args):
     bins = BATCH * TM * 2 * H * W
     bin_bytes = 13.0 * n_avg + 4.0 * bins                 # 13 B/event + 4 B/bin
     bin_bytes_touched = 5.0 * n_avg + 4.0 * bins          # t is only touched by the Tm+1 binary searches
+    bin_bytes_compact = 5.0 * n_avg + 1.0 * bins          # what the compact call moves: 1 B per bin
     smp_launch_ms = t_smp / TM                                # one of the Tm step launches (+ 1/Tm of the weight pack)
     smp_bytes_launch = 8.0 * H * W * (TM + TS) * BATCH / TM   # SURVEY 8d, per launch (one of Tm steps)
     smp_flop_launch = 2400.0 * H * W * BATCH                  # 2400 FLOP per pixel-step
@@ -652,7 +668,7 @@ def run_ours(args):
         "frac": smp_flop_launch / smp_launch_ms / 1e9 / tensor_peak,
         "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": "measured cuBLAS bf16 burst (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
-        "launch_ms": smp_launch_ms,
+        "launch_ms": smp_launch_ms, "launch_ms_dense_f32_input": t_smp_dense / TM,
         "note": "algorithmic FLOPs (2400 per pixel-step, SURVEY 8d) over the dense bf16 GEMM peak.  The convolutions have "
                 "2/8 input and 4 output channels: on the tensor cores they run as block-Toeplitz GEMMs over the x axis "
                 "(5 of 8 K positions used) x 4 output rows folded into N (5 of 8 input rows used per output row) x fp16 "
@@ -673,11 +689,21 @@ def run_ours(args):
         "others": {"bin_events (bounds + tiles)": {
             "bound": "hbm", "call_ms": t_bin, "achieved": bin_bytes / t_bin / 1e6, "peak": peak_gbs,
             "unit": "GB/s", "frac": bin_bytes / t_bin / 1e6 / peak_gbs,
-            "achieved_bytes_touched": bin_bytes_touched / t_bin / 1e6},
+            "achieved_bytes_moved": bin_bytes_compact / t_bin / 1e6,
+            "frac_bytes_moved": bin_bytes_compact / t_bin / 1e6 / peak_gbs,
+            "note": "the step's call: compact byte histogram.  achieved / frac = SURVEY 8d's algorithmic bytes (13 B per "
+                    "event + 4 B per bin: the reference's dense histogram) over the call time; *_bytes_moved = what this "
+                    "call really reads and writes (5 B per event + 1 B per bin)"},
+            "bin_events, dense fp32 histogram": {
+                "bound": "hbm", "call_ms": t_bin_f32, "achieved": bin_bytes / t_bin_f32 / 1e6, "peak": peak_gbs,
+                "unit": "GB/s", "frac": bin_bytes / t_bin_f32 / 1e6 / peak_gbs,
+                "achieved_bytes_touched": bin_bytes_touched / t_bin_f32 / 1e6,
+                "note": "the public default (what the reference's loader produces); a plain memset of its 149 MB takes "
+                        "0.046 ms on this GPU (scripts/write_bw_probe.py)"},
             "bin_dat (bounds + tiles on raw 8-byte records)": {
                 "bound": "hbm", "call_ms": t_bin_dat, "achieved": (8.0 * n_avg + 4.0 * bins) / t_bin_dat / 1e6,
                 "peak": peak_gbs, "unit": "GB/s", "frac": (8.0 * n_avg + 4.0 * bins) / t_bin_dat / 1e6 / peak_gbs,
-                "note": "algorithmic bytes = 8 B/record + 4 B/bin"},
+                "note": "compact byte histogram; algorithmic bytes = 8 B/record + 4 B/bin"},
             "plif_fwd_kernel (f32, T=3)": {
                 "bound": "hbm", "call_ms": t_plif_f, "achieved": 8.0 * pT * pN / t_plif_f / 1e6, "peak": peak_gbs,
                 "unit": "GB/s", "frac": 8.0 * pT * pN / t_plif_f / 1e6 / peak_gbs, "note": "8 B per element-step"},
@@ -740,8 +766,9 @@ def run_ours(args):
                                                 "once, no kernels: what this box's host memory / PCIe path can feed"},
                     "frac_of_host_ceiling": e2e_val / ceil_val,
                     "checksum": checksum, "numa": numa},
-            # bin: bounds + histogram (2), sampler: weight pack (1) + Tm step launches + Tm fall-back launches (exit at once)
-            "gpu_launches": args.steps * repeats * (2 + 1 + 2 * TM),
+            # bin: bounds + histogram (2), sampler: weight pack (1) + Tm step launches + the fall-back's histogram
+            # expansion (1) and Tm step launches (all exit at once unless the tensor-core kernel raised its flag)
+            "gpu_launches": args.steps * repeats * (2 + 1 + TM + 1 + TM),
             "clocks": clk, "roofline": roofline}
     if sweep is not None:
         line["binning_sweep"] = sweep

@@ -23,9 +23,9 @@ class CompactHist:
     (``AdaptiveRSNNEmbedding.forward(CompactHist)``); :meth:`dense` gives the ``[B, Tm, 2, H, W]`` tensor back.
 
     Only when more than ``SAT_CAP`` bins saturate in one call is information lost (``lost`` flag in the buffer).
-    That is checked without stalling the stream: every call queues a copy of the flag and :func:`poll_compact` (run by
-    the next binning call, or by hand) raises ``OverflowError`` for any finished call that lost counts;
-    :meth:`check` waits and checks now."""
+    That is reported without stalling the stream: a 1-thread kernel behind every call ORs the flag into a pinned host
+    int and :func:`poll_compact` (run by the next binning call, or by hand) raises ``OverflowError`` once it is set;
+    :meth:`check` waits and checks this buffer now."""
 
     def __init__(self, buf: torch.Tensor, shape):
         self.buf, self.shape = buf, tuple(int(v) for v in shape)
@@ -81,33 +81,34 @@ class CompactHist:
         return self
 
     def _queue_check(self):
-        if torch.cuda.is_current_stream_capturing():
-            return                                  # (a captured call is checked by hand: .check())
-        ev, host = _FREE.pop() if _FREE else (torch.cuda.Event(), torch.empty(4, dtype=torch.int32).pin_memory())
-        host.copy_(self.tail, non_blocking=True)
-        ev.record(torch.cuda.current_stream(self.buf.device))
-        _PENDING.append((ev, host))
+        """One 1-thread kernel after the binning call ORs the buffer's ``lost`` word into a pinned host int (sticky):
+        no copy-engine traffic, no event, nothing for the stream to wait on."""
+        flag = _sticky_flag()
+        B, Tm, _, H, W = self.shape
+        with torch.cuda.device(self.buf.device):
+            rc = _lib.lib().eas_hist_u8_report(_lib.ptr(self.buf), B, Tm, H, W, C.c_void_p(flag.data_ptr()),
+                                               _lib.stream_ptr())
+        _lib.check(rc, "eas_hist_u8_report")
 
 
 _LOST_MSG = ("compact histogram: more than %d bins collected >= 255 events in one call, counts were lost; "
              "bin with dtype=torch.int32 / float32 (hist_dtype='dense')" % SAT_CAP)
-_PENDING: list = []      # (event, pinned copy of the list header) of the calls not checked yet
-_FREE: list = []         # recycled (event, pinned buffer) pairs
+_STICKY: list = []       # one pinned int32: set by the device when a compact binning call lost counts
+
+
+def _sticky_flag() -> torch.Tensor:
+    if not _STICKY:
+        _STICKY.append(torch.zeros(1, dtype=torch.int32).pin_memory())
+    return _STICKY[0]
 
 
 def poll_compact(wait: bool = False):
-    """Raise ``OverflowError`` if a finished compact binning call lost counts (``wait=True``: finish them all first)."""
-    keep, lost = [], False
-    for ev, host in _PENDING:
-        if wait:
-            ev.synchronize()
-        if ev.query():
-            lost = lost or int(host[1]) != 0
-            _FREE.append((ev, host))
-        else:
-            keep.append((ev, host))
-    _PENDING[:] = keep
-    if lost:
+    """Raise ``OverflowError`` (once) if a compact binning call that has run so far lost counts; ``wait=True``
+    synchronises the device first, so that every call issued so far is covered."""
+    if wait:
+        torch.cuda.synchronize()
+    if _STICKY and int(_STICKY[0][0]) != 0:
+        _STICKY[0][0] = 0
         raise OverflowError(_LOST_MSG)
 
 
@@ -169,15 +170,16 @@ def bin_events(x: torch.Tensor, y: torch.Tensor, t: torch.Tensor, p: torch.Tenso
     return out
 
 
-def compact_fits(H: int, W: int) -> bool:
+def compact_fits(H: int, W: int) -> int:
     """Whether the byte histogram can be written for this frame size: the shared-memory tiles kernel holds a row slab
-    of 16-bit counters per CTA (<= 8 slabs of <= 72 KB; bin_events.cu ``slab_geo``)."""
+    of 16-bit counters per CTA (<= 8 slabs of <= 72 KB; bin_events.cu ``slab_geo``).  Returns the number of row slabs
+    (work items per window = Tm * 2 * slabs), 0 when the frame does not fit."""
     slab = 72 * 1024
     n_slabs = min(-(-(H * W * 2) // slab), H)
     rows = -(-H // n_slabs)
     n_slabs = -(-H // rows)
     smem = ((rows * W + 1) // 2 + 3) // 4 * 4 * 4
-    return smem <= slab + 4096 and n_slabs <= 8
+    return n_slabs if (smem <= slab + 4096 and n_slabs <= 8) else 0
 
 
 class HostEventBatch:

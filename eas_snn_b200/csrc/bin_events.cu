@@ -131,7 +131,7 @@ template <> struct Cvt<float> {  // counts < 2^24 are exact in fp32
 };
 
 template <typename OUT_T, typename SRC>
-__global__ void __launch_bounds__(kSmemThreads)
+__global__ void __launch_bounds__(kSmemThreads, 3)
 bin_hist_smem_kernel(const SRC src, const int64_t* __restrict__ bounds, int64_t n_items,
                      int H, int W, int Tm, int n_slabs, int slab_rows, uint32_t* __restrict__ hist,
                      unsigned int* __restrict__ work_counter, uint32_t* __restrict__ sat_tail) {
@@ -165,38 +165,46 @@ bin_hist_smem_kernel(const SRC src, const int64_t* __restrict__ bounds, int64_t 
         *reinterpret_cast<uint4*>(cnt + w) = make_uint4(0u, 0u, 0u, 0u);
       __syncthreads();
       const int64_t ce = (e - cs > kChunk) ? cs + kChunk : e;
+      // the scan is issue bound (ncu: ALU pipe 60 %, ~50 thread instructions per event): chunk-relative 32-bit
+      // indices and unsigned range tests keep the per-event work to a dozen instructions
+      const uint32_t uW = (uint32_t)W, urows = (uint32_t)rows, uc = (uint32_t)c;
       auto count = [&](int xi, int yi, int ci) {
-        yi -= y_lo;
-        if (ci == c && (unsigned)xi < (unsigned)W && (unsigned)yi < (unsigned)rows) {
-          const int pix = yi * W + xi;
-          atomicAdd(cnt + (pix >> 1), 1u << ((pix & 1) << 4));
+        const uint32_t yr = (uint32_t)(yi - y_lo);
+        if ((uint32_t)ci == uc && (uint32_t)xi < uW && yr < urows) {
+          const uint32_t pix = yr * uW + (uint32_t)xi;
+          atomicAdd(cnt + (pix >> 1), 1u << ((pix & 1u) << 4));
         }
       };
+      const int n_chunk = (int)(ce - cs);   // <= 65535
       if constexpr (SRC::VW > 1) {
         // SRC::VW events per thread and iteration from 16-byte aligned groups (the scan is load-latency bound: ncu showed
         // 43 % of the kernel's stall samples behind the 2-byte / 1-byte event loads); ragged ends are masked
         constexpr int VW = SRC::VW;
+        const int64_t g0 = cs & ~(int64_t)(VW - 1);      // aligned start of the chunk's first group
+        const int lead = (int)(cs - g0);                 // events of that group before the chunk
+        const int64_t avail = src.n - g0;               // events from g0 on that whole groups cover (clamped: int)
+        const int n_full = (int)((avail < (1 << 20) ? avail : (int64_t)(1 << 20)) / VW * VW);
 #pragma unroll 2
-        for (int64_t iv = (cs & ~(int64_t)(VW - 1)) + (int64_t)threadIdx.x * VW; iv < ce; iv += (int64_t)kSmemThreads * VW) {
-          if (iv + VW <= src.n) {
+        for (int o = (int)threadIdx.x * VW; o < lead + n_chunk; o += kSmemThreads * VW) {
+          if (o + VW <= n_full) {
             int xs[VW], ys[VW], cc[VW];
-            src.loadv(iv, xs, ys, cc);
+            src.loadv(g0 + o, xs, ys, cc);
 #pragma unroll
             for (int j = 0; j < VW; ++j)
-              if (iv + j >= cs && iv + j < ce) count(xs[j], ys[j], cc[j]);
+              if ((uint32_t)(o + j - lead) < (uint32_t)n_chunk) count(xs[j], ys[j], cc[j]);
           } else {
-            for (int64_t i = (iv > cs ? iv : cs); i < ce; ++i) {   // the last, partial group of the arrays
+            for (int i = o > lead ? o : lead; i < lead + n_chunk; ++i) {   // the last, partial group of the arrays
               int xi, yi, ci;
-              src.xyc(i, xi, yi, ci);
+              src.xyc(g0 + i, xi, yi, ci);
               count(xi, yi, ci);
             }
           }
         }
       } else {
 #pragma unroll 4
-        for (int64_t i = cs + threadIdx.x; i < ce; i += kSmemThreads) {
+        for (int i = (int)threadIdx.x; i < n_chunk; i += kSmemThreads) {
           int xi, yi, ci;
-          src.xyc(i, xi, yi, ci);
+          src.xyc(cs + i, xi, yi, ci);
           count(xi, yi, ci);
         }
       }
@@ -636,6 +644,24 @@ int eas_hist_u8_expand_if(const void* hist_u8, int64_t nbins, void* out, int out
     hist_u8_expand_kernel<float><<<grid, 256, 0, stream>>>((const uint8_t*)hist_u8, nbins, (float*)out, run_if);
   else
     hist_u8_expand_kernel<int32_t><<<grid, 256, 0, stream>>>((const uint8_t*)hist_u8, nbins, (int32_t*)out, run_if);
+  EAS_LAUNCH_CHECK();
+  return EAS_OK;
+}
+
+namespace {
+__global__ void hist_u8_report_kernel(const uint8_t* __restrict__ h, int64_t nbins, volatile int32_t* sticky) {
+  const uint32_t* tail = reinterpret_cast<const uint32_t*>(h + hist_u8_tail_offset((size_t)nbins));
+  if (tail[1] != 0u) *sticky = 1;
+}
+}  // namespace
+
+extern "C" int eas_hist_u8_report(const void* hist_u8, int64_t B, int Tm, int H, int W, int32_t* sticky_flag,
+                                  void* stream) {
+  EAS_REQUIRE(B >= 0 && Tm > 0 && H > 0 && W > 0, EAS_E_SHAPE);
+  if (B == 0) return EAS_OK;
+  EAS_REQUIRE(hist_u8 && sticky_flag, EAS_E_NULL);
+  hist_u8_report_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const uint8_t*)hist_u8, B * Tm * 2 * (int64_t)H * W,
+                                                         sticky_flag);
   EAS_LAUNCH_CHECK();
   return EAS_OK;
 }

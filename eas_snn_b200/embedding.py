@@ -224,10 +224,11 @@ class AdaptiveRSNNEmbedding(nn.Module):
             return out, torch.stack(t_rec, dim=0)
         return out, torch.cat(v_rec)
 
-    def _hist_dtype(self, H, W, strategy, hist_dtype):
+    def _hist_dtype(self, B, H, W, strategy, hist_dtype):
         """The histogram format between binning and sampling: ``"compact"`` = one byte per bin + the exact list of
         saturated bins (a quarter of the bytes written and read; the tensor-core kernel and the tiles binning
-        kernel), ``"dense"`` = fp32 counts, ``"auto"`` = compact whenever those two kernels take the call."""
+        kernel), ``"dense"`` = fp32 counts, ``"auto"`` = compact whenever those two kernels take the call and the batch
+        gives the tiles kernel a work item per SM (a lone window bins faster through the global-reduction kernel)."""
         if hist_dtype not in ("auto", "compact", "dense"):
             raise ValueError("hist_dtype must be 'auto', 'compact' or 'dense'")
         ok = (self.depth == 2 and self.kernel_size == 5 and W % 4 == 0 and self.Ts <= 15 and self.nb_steps <= 14 and
@@ -236,6 +237,8 @@ class AdaptiveRSNNEmbedding(nn.Module):
         if hist_dtype == "compact" and not ok:
             raise ValueError("the compact histogram needs the tensor-core sampler (depth 2, k 5, W % 4 == 0, inference) "
                              "and a frame that fits the tiles binning kernel")
+        if hist_dtype == "auto" and ok:
+            ok = B * self.nb_steps * 2 * compact_fits(H, W) >= 148
         return torch.uint8 if (ok and hist_dtype != "dense") else torch.float32
 
     def forward_events(self, x, y, t, p, offsets, H: int, W: int, strategy: str = "auto", hist_dtype: str = "auto"):
@@ -246,7 +249,7 @@ class AdaptiveRSNNEmbedding(nn.Module):
         counts otherwise -- the same frames either way.
         """
         hist = bin_events(x, y, t, p, offsets, H, W, self.nb_steps, strategy=strategy,
-                          dtype=self._hist_dtype(H, W, strategy, hist_dtype))
+                          dtype=self._hist_dtype(offsets.numel() - 1, H, W, strategy, hist_dtype))
         return self.forward(hist)
 
     def forward_dat(self, records, ranges, H: int, W: int, strategy: str = "auto", hist_dtype: str = "auto"):
@@ -254,7 +257,7 @@ class AdaptiveRSNNEmbedding(nn.Module):
         -> adaptive frames ``[Ts, B, 2, H, W]``: decode, binning and sampling without leaving the GPU."""
         from .psee import bin_dat
         hist = bin_dat(records, ranges, H, W, self.nb_steps, strategy=strategy,
-                       dtype=self._hist_dtype(H, W, strategy, hist_dtype))
+                       dtype=self._hist_dtype(ranges.shape[0], H, W, strategy, hist_dtype))
         return self.forward(hist)
 
 

@@ -77,6 +77,10 @@ int eas_bin_events(const int16_t* x, const int16_t* y, const int64_t* t, const u
 size_t eas_hist_u8_bytes(int64_t B, int Tm, int H, int W);
 int eas_hist_u8_expand(const void* hist_u8, int64_t B, int Tm, int H, int W, void* out, int out_dtype,
                        void* stream);
+/* Error reporting without a stream stall: sets *sticky_flag = 1 (never clears it) when the histogram's `lost`
+ * word is set.  sticky_flag may be pinned host memory (device-accessible under unified addressing): the host
+ * then polls a plain int. */
+int eas_hist_u8_report(const void* hist_u8, int64_t B, int Tm, int H, int W, int32_t* sticky_flag, void* stream);
 int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64_t* t, const uint8_t* p,
                       const int64_t* offsets, int64_t B, int64_t n_events, int H, int W, int Tm,
                       void* hist, void* ws, size_t ws_bytes, void* stream, int strategy, int out_dtype);

@@ -6,10 +6,10 @@ import eas_snn_b200 as eas
 dev = torch.device("cuda:0")
 torch.manual_seed(80)
 model = eas.AdaptiveRSNNEmbedding(**bench.SAMPLER_KW).to(dev).eval()
-if len(sys.argv) > 1:
+if len(sys.argv) > 1 and sys.argv[1] != "dense":
     model.algo = sys.argv[1]
 b = [torch.from_numpy(a).to(dev) for a in bench.host_batches(0, bench.BATCH)[0]]
-hist = eas.bin_events(*b, bench.H, bench.W, bench.TM, dtype=torch.float32)
+hist = eas.bin_events(*b, bench.H, bench.W, bench.TM, dtype=torch.float32 if "dense" in sys.argv else torch.uint8)
 with torch.no_grad():
     for _ in range(3):
         out = model(hist)
