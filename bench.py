@@ -578,13 +578,41 @@ def run_ours(args):
             torch.cuda.synchronize()
             parts += [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
         barrier()
-        t_ms = parallel.max_over_ranks((time.perf_counter() - t0) * 1e3 / tsteps, dev)
-        train = {"value": world * TB / t_ms * 1e3, "unit": "samples/s", "ms_per_step": t_ms,
-                 "parts_ms": dict(zip(("forward", "backward", "allreduce", "adam+reset"), (parts / tsteps).round(3).tolist())),
-                 "what": "SYOLOX-S training step, %d windows per GPU, T=3, 256x320, fp32: sampler fwd + BPTT bwd (SAT "
-                         "surrogate + RPD) and 34 PLIF fwd/bwd on our kernels, conv / batch-stat BN through cuDNN, "
-                         "proxy loss on dark3-5 firing rates, NCCL gradient all-reduce (%d params), Adam"
-                         % (TB, sum(p.numel() for p in t_params)),
+        t_eager = parallel.max_over_ranks((time.perf_counter() - t0) * 1e3 / tsteps, dev)
+        # the same step as two CUDA graphs around the all-reduce (fused.GraphedTrainStep): the host issues ~1500
+        # launches per step in eager mode, about 1.5x the time the GPU needs for them
+        opt_g = torch.optim.Adam(t_params, lr=1e-4, capturable=True)
+        loss_eager = float(loss.detach())
+        del loss            # (the eager graph keeps the parameters' AccumulateGrad nodes bound to the default stream)
+        import gc
+        gc.collect()
+
+        def t_loss(h):
+            fr = torch.nn.functional.pad(t_emb(h), (0, 320 - W, 0, 256 - H))
+            return sum((v.mean() - 0.2) ** 2 for v in t_bb(fr).values())
+
+        gstep = fused.GraphedTrainStep(t_loss, [t_hist], t_params, opt_g, allreduce=parallel.allreduce_gradients,
+                                       after=lambda: eas.reset_net(t_bb))
+        for _ in range(3):
+            gstep(t_hist)
+        barrier()
+        gsteps = 40
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(gsteps):
+            loss = gstep(t_hist)
+        g1.record()
+        barrier()
+        t_ms = parallel.max_over_ranks(g0.elapsed_time(g1) / gsteps, dev)
+        train = {"value": world * TB / t_ms * 1e3, "unit": "samples/s", "ms_per_step": t_ms, "steps": gsteps,
+                 "eager": {"ms_per_step": t_eager, "loss": loss_eager,
+                           "parts_ms": dict(zip(("forward", "backward", "allreduce", "adam+reset"),
+                                                (parts / tsteps).round(3).tolist()))},
+                 "what": "SYOLOX-S training step, %d windows per GPU, T=3, 256x320, fp32, replayed as two CUDA graphs around "
+                         "the gradient all-reduce (GraphedTrainStep; `eager` = the same step issued launch by launch): "
+                         "sampler fwd + BPTT bwd (SAT surrogate + RPD) and 34 PLIF fwd/bwd on our kernels, conv / "
+                         "batch-stat BN through cuDNN, proxy loss on dark3-5 firing rates, NCCL gradient all-reduce "
+                         "(%d params), Adam" % (TB, sum(p.numel() for p in t_params)),
                  "loss": float(loss.detach())}
 
     # ---- per-kernel durations (CUDA events on the launching stream) for the roofline -----------

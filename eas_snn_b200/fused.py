@@ -520,6 +520,69 @@ class GraphedForward:
         return self.static_out
 
 
+class GraphedTrainStep:
+    """CUDA-graph replay of one training step (the reference's ``train_one_iter``, yolox/core/trainer.py:96-125:
+    forward, loss, backward, optimizer step, ``reset_net``) for launch-bound sizes: a SYOLOX-S step on 8 windows is
+    ~1500 kernel launches (cuDNN conv / BN, the PLIF forward / backward kernels, the sampler's BPTT, element-wise glue,
+    Adam) that the host issues in 16 ms while the GPU needs a third of that.
+
+    Two graphs around the one collective: ``backward`` graph = zero the gradients, ``loss_fn(*static inputs)``,
+    ``loss.backward()``; then the gradient all-reduce runs eagerly (``allreduce``, a callable or None); then the
+    ``update`` graph = ``optimizer.step()`` (the optimizer must be built with ``capturable=True``) and whatever
+    ``after`` does on the device.  Python-side state (the neurons' ``v`` handles) is left as ``reset_net`` leaves it.
+
+    ``loss_fn`` takes the static input tensors and returns the scalar loss; ``__call__(*inputs)`` copies new inputs
+    into the static buffers, replays, and returns the (static) loss tensor.  Build it before any eager backward through
+    the same parameters, or after every tensor of those eager graphs has been dropped: a live graph keeps the
+    parameters' gradient accumulators bound to the stream they first ran on, which a capture may not wait for."""
+
+    def __init__(self, loss_fn, inputs, params, optimizer, allreduce=None, after=None, warmup: int = 3):
+        params = list(params)
+        dev = params[0].device
+        self.static_in = [t.clone() for t in inputs]
+        self.allreduce, self.params = allreduce, params
+
+        def fwd_bwd():
+            for q in params:                         # (grads stay allocated: the update graph reads these tensors)
+                if q.grad is not None:
+                    q.grad.zero_()
+            loss = loss_fn(*self.static_in)
+            loss.backward()
+            return loss.detach()
+
+        def update():
+            optimizer.step()
+            if after is not None:
+                after()
+
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                  # cuDNN picks its algorithms, gradients and Adam state get allocated
+                fwd_bwd()
+                if allreduce is not None:
+                    allreduce(params)
+                update()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.g_bwd, self.g_upd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_bwd):
+            self.loss = fwd_bwd()
+        pool = self.g_bwd.pool()
+        with torch.cuda.graph(self.g_upd, pool=pool):
+            update()
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.static_in, inputs):
+            if src is not dst:
+                dst.copy_(src)
+        self.g_bwd.replay()
+        if self.allreduce is not None:
+            self.allreduce(self.params)
+        self.g_upd.replay()
+        return self.loss
+
+
 def convert_to_spiking(model: nn.Module, spike_fn, fuse: bool = True, n_wsplit: int = 2) -> nn.Module:
     """``yolox/utils/utils_snn.py:16-58`` with the fused layer: every child that looks like the
     reference's ``BaseConv`` (``.conv`` Conv2d, ``.bn`` BatchNorm2d, ``.act``) becomes a

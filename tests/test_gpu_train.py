@@ -103,3 +103,49 @@ def test_sampler_plus_backbone_optimiser_step(cuda):
     moved = sum(int(not torch.equal(a, b)) for a, b in zip(before, params))
     assert moved > 0.9 * len(params), (moved, len(params))
     assert any(p.grad.abs().max() > 0 for p in emb.parameters()), "no gradient reached the sampler"
+
+
+def test_graphed_train_step_replays_the_eager_step(cuda):
+    """fused.GraphedTrainStep (zero grads + forward + loss + backward | all-reduce | SGD step + reset_net as CUDA
+    graphs): the gradients of a replay equal the eager step's on the same parameters (the sampler's weight gradients
+    are summed with atomics: 1e-6 relative), replays follow new input, and the parameters move."""
+    def build():
+        torch.manual_seed(3)
+        emb = eas.AdaptiveRSNNEmbedding(kernel_size=5, depth=2, nb_steps=4, thresh=1, vreset=0, Ts=1, write_zero=True,
+                                        spike_attach=True).to(cuda).train()
+        bb = fused.SpikingCSPDarknet(0.33, 0.25, in_dim=2, T=3).to(cuda).train()
+        for m in bb.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.bias.data.fill_(0.6)
+        return emb, bb, list(emb.parameters()) + list(bb.parameters())
+
+    def loss_of(emb, bb):
+        return lambda h: sum((v.mean() - 0.2) ** 2 for v in bb(emb(h)).values())
+
+    hist = torch.poisson(torch.full((2, 4, 2, 64, 96), 1.0)).to(cuda)
+    hist2 = torch.poisson(torch.full((2, 4, 2, 64, 96), 0.6)).to(cuda)
+    # lr = 0 during warm-up and capture: the graphed model stays at its initial parameters
+    emb, bb, params = build()
+    opt = torch.optim.SGD(params, lr=0.0)
+    step = fused.GraphedTrainStep(loss_of(emb, bb), [hist], params, opt, after=lambda: eas.reset_net(bb), warmup=2)
+    emb_e, bb_e, params_e = build()
+    for h in (hist, hist2):
+        loss_g = float(step(h))
+        for q in params_e:
+            q.grad = None
+        loss_e = loss_of(emb_e, bb_e)(h)
+        loss_e.backward()
+        eas.reset_net(bb_e)
+        assert abs(loss_g - float(loss_e)) <= 1e-6 * max(1.0, abs(float(loss_e))), (loss_g, float(loss_e))
+        for a, b in zip(params, params_e):
+            scale = float(b.grad.abs().max()) + 1e-12
+            assert float((a.grad - b.grad).abs().max()) <= 2e-3 * scale
+    # and with a learning rate (baked into the update graph at capture) the replayed update moves the parameters
+    emb, bb, params = build()
+    step = fused.GraphedTrainStep(loss_of(emb, bb), [hist], params, torch.optim.Adam(params, lr=1e-3, capturable=True),
+                                  after=lambda: eas.reset_net(bb), warmup=2)
+    before = [p.detach().clone() for p in params]
+    step(hist)
+    torch.cuda.synchronize()
+    moved = sum(int(not torch.equal(a, b)) for a, b in zip(before, params))
+    assert moved > 0.9 * len(params), (moved, len(params))
