@@ -21,6 +21,12 @@ for r in rows[2:]:
                      "dram_read_bytes": rd, "dram_write_bytes": wr,
                      "tensor_active_pct": float(r[col("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")]),
                      "issue_active_pct": float(r[col("smsp__issue_active.avg.pct_of_peak_sustained_active")])})
+# one forward = from a first-step instantiation (<.., 0> / <.., 3>) up to the next one
+import re
+first = [i for i, l in enumerate(launches) if re.search(r", \(?(?:int\))?[03]\)?>", l["kernel"])]
+if first:
+    end = first[1] if len(first) > 1 else len(launches)
+    launches = launches[first[0]:end]
 d = {"report": rep.split("/")[-1], "launches": launches,
      "dram_bytes_per_launch": launches[pick]["dram_read_bytes"] + launches[pick]["dram_write_bytes"],
      "dram_bytes_per_forward": sum(l["dram_read_bytes"] + l["dram_write_bytes"] for l in launches),
