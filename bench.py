@@ -541,6 +541,9 @@ def run_ours(args):
         torch.manual_seed(82)
         t_emb = eas.AdaptiveRSNNEmbedding(**SAMPLER_KW).to(dev).train()
         t_bb = fused.SpikingCSPDarknet(0.33, 0.50, in_dim=2, T=3).to(dev).train()       # e_yolox_s.py:13-14
+        # channels-last parameters: cuDNN then runs NHWC convolutions / BN end to end and the neurons work on those
+        # buffers as they lie -- the NCHW<->NHWC conversion kernels were 10 % of the step
+        t_bb = t_bb.to(memory_format=torch.channels_last)
         for mod in t_bb.modules():
             if isinstance(mod, torch.nn.BatchNorm2d):
                 mod.bias.data.fill_(0.6)
@@ -611,7 +614,7 @@ def run_ours(args):
                  "what": "SYOLOX-S training step, %d windows per GPU, T=3, 256x320, fp32, replayed as two CUDA graphs around "
                          "the gradient all-reduce (GraphedTrainStep; `eager` = the same step issued launch by launch): "
                          "sampler fwd + BPTT bwd (SAT surrogate + RPD) and 34 PLIF fwd/bwd on our kernels, conv / "
-                         "batch-stat BN through cuDNN, proxy loss on dark3-5 firing rates, NCCL gradient all-reduce "
+                         "batch-stat BN through cuDNN (channels-last), proxy loss on dark3-5 firing rates, NCCL gradient all-reduce "
                          "(%d params), Adam" % (TB, sum(p.numel() for p in t_params)),
                  "loss": float(loss.detach())}
 

@@ -122,6 +122,12 @@ def plif_multistep(x_seq, w, node, v0=None, want_v=False):
     _lib.require_cuda(x_seq, w)
     if x_seq.dtype not in (torch.float32, torch.bfloat16):
         x_seq = x_seq.float()
+    if x_seq.dim() == 5 and not x_seq.is_contiguous() and x_seq.permute(0, 1, 3, 4, 2).is_contiguous():
+        # [T, B, C, H, W] view of channels-last activations (what cuDNN's NHWC convolutions hand over): the neuron is
+        # element-wise over everything but T, so it runs on the memory as it lies instead of forcing an NCHW copy
+        v0p = None if v0 is None else v0.permute(0, 2, 3, 1)
+        spikes, v_out = plif_multistep(x_seq.permute(0, 1, 3, 4, 2), w, node, v0=v0p, want_v=want_v)
+        return spikes.permute(0, 1, 4, 2, 3), None if v_out is None else v_out.permute(0, 3, 1, 2)
     x_seq = x_seq.contiguous()
     if v0 is not None:
         # the kernels index v0[i] for every element of one time step: a state carried over from another batch

@@ -18,6 +18,8 @@ def build():
     for m in bb.modules():
         if isinstance(m, torch.nn.BatchNorm2d):
             m.bias.data.fill_(0.6)
+    if "cl" in sys.argv:
+        bb = bb.to(memory_format=torch.channels_last)
     params = list(emb.parameters()) + list(bb.parameters())
     return emb, bb, params
 

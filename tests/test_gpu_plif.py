@@ -114,3 +114,27 @@ def test_large_backbone_shape_property(cuda):
     v_T = ((x - s) * wts).sum(0)
     assert torch.allclose(node.v, v_T, atol=1e-5)
     assert set(s.unique().tolist()) <= {0.0, 1.0}
+
+
+def test_channels_last_views_run_in_place_and_match_the_contiguous_path(cuda):
+    """[T, B, C, H, W] views of channels-last activations (cuDNN's NHWC convolutions in the training path) are
+    processed on the memory as it lies: same spikes, state and input gradients as the NCHW-contiguous copy, bit for bit, and
+    the outputs keep the channels-last layout (no conversion kernels between conv and neuron)."""
+    torch.manual_seed(9)
+    T, B, Cc, H, W = 3, 2, 8, 6, 10
+    base = (torch.randn(T * B, Cc, H, W, device=cuda) + 0.4).contiguous(memory_format=torch.channels_last)
+    outs = []
+    for cl in (True, False):
+        x = (base if cl else base.contiguous()).detach().clone(memory_format=torch.preserve_format).requires_grad_(True)
+        node = eas.ParametricLIFNode(decay_input=False, v_reset=None, surrogate_function=eas.ATan(2.0),
+                                     step_mode="m").to(cuda)
+        s = node(x.view(T, B, Cc, H, W))
+        if cl:
+            assert s.permute(0, 1, 3, 4, 2).is_contiguous() and node.v.permute(0, 2, 3, 1).is_contiguous()
+        g = torch.arange(s.numel(), device=cuda, dtype=torch.float32).view_as(s).sin()
+        (s * g).sum().backward()
+        outs.append((s.detach().clone(), node.v.clone(), x.grad.clone(), node.w.grad.clone()))
+    for a, b in list(zip(*outs))[:3]:
+        assert torch.equal(a.contiguous(), b.contiguous())
+    gw_cl, gw = outs[0][3], outs[1][3]                  # d w: same terms, summed in memory order
+    assert abs(float(gw_cl) - float(gw)) <= 1e-5 * abs(float(gw)) + 1e-7

@@ -107,8 +107,9 @@ def test_sampler_plus_backbone_optimiser_step(cuda):
 
 def test_graphed_train_step_replays_the_eager_step(cuda):
     """fused.GraphedTrainStep (zero grads + forward + loss + backward | all-reduce | SGD step + reset_net as CUDA
-    graphs): the gradients of a replay equal the eager step's on the same parameters (the sampler's weight gradients
-    are summed with atomics: 1e-6 relative), replays follow new input, and the parameters move."""
+    graphs): the gradients of a replay equal the eager step's on the same parameters up to summation order (the
+    sampler's weight gradients are summed with atomics, cuDNN may pick another algorithm under capture; measured
+    <= 6e-3 of a tensor's largest gradient), replays follow new input, and the parameters move."""
     def build():
         torch.manual_seed(3)
         emb = eas.AdaptiveRSNNEmbedding(kernel_size=5, depth=2, nb_steps=4, thresh=1, vreset=0, Ts=1, write_zero=True,
