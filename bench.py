@@ -584,7 +584,7 @@ def run_ours(args):
         t_eager = parallel.max_over_ranks((time.perf_counter() - t0) * 1e3 / tsteps, dev)
         # the same step as two CUDA graphs around the all-reduce (fused.GraphedTrainStep): the host issues ~1500
         # launches per step in eager mode, about 1.5x the time the GPU needs for them
-        opt_g = torch.optim.Adam(t_params, lr=1e-4, capturable=True)
+        opt_g = torch.optim.Adam(t_params, lr=1e-4, capturable=True, fused=True)
         loss_eager = float(loss.detach())
         del loss            # (the eager graph keeps the parameters' AccumulateGrad nodes bound to the default stream)
         import gc

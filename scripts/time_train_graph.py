@@ -44,7 +44,7 @@ for _ in range(10): le = eager()
 torch.cuda.synchronize(); t_eager = (time.perf_counter() - t0) / 10 * 1e3
 # graphed, from the same initial state
 emb2, bb2, params2 = build()
-opt2 = torch.optim.Adam(params2, lr=1e-4, capturable=True)
+opt2 = torch.optim.Adam(params2, lr=1e-4, capturable=True, fused="fused" in sys.argv)
 step = fused.GraphedTrainStep(loss_of(emb2, bb2), [hist], params2, opt2, after=lambda: eas.reset_net(bb2), warmup=3)
 for _ in range(10): lg = step(hist)
 torch.cuda.synchronize(); t0 = time.perf_counter()
