@@ -43,6 +43,28 @@ static __device__ __noinline__ uint32_t hist_u8_lookup(const uint32_t* __restric
   return kHistU8Sat;
 }
 
+// grid-stride expansion of a compact histogram into dense fp32 counts (callable from inside a kernel)
+static __device__ __forceinline__ void hist_u8_expand_f32(const uint8_t* __restrict__ h, int64_t nbins, float* __restrict__ out) {
+  const uint32_t* tail = reinterpret_cast<const uint32_t*>(h + hist_u8_tail_offset((size_t)nbins));
+  const int64_t n4 = nbins >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t w = reinterpret_cast<const uint32_t*>(h)[i];
+    uint32_t c[4] = {w & 0xffu, (w >> 8) & 0xffu, (w >> 16) & 0xffu, w >> 24};
+    if (__vcmpeq4(w, 0xffffffffu)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c[j] == kHistU8Sat) c[j] = hist_u8_lookup(tail, (uint32_t)(4 * i + j));
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4((float)c[0], (float)c[1], (float)c[2], (float)c[3]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (nbins & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    uint32_t c = h[i];
+    if (c == kHistU8Sat) c = hist_u8_lookup(tail, (uint32_t)i);
+    out[i] = (float)c;
+  }
+}
+
 // dense counts (EAS_F32 / EAS_I32) of a compact histogram; a no-op unless *run_if != 0 when run_if is given (bin_events.cu)
 int eas_hist_u8_expand_if(const void* hist_u8, int64_t nbins, void* out, int out_dtype, const int* run_if,
                           cudaStream_t stream);

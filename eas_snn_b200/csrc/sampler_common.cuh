@@ -24,6 +24,15 @@ struct StepArgs {
   int readout, hard_reset, write_zero, use_abs;
   float vreset, thresh;
   const int* run_if;      // FP32-pipe kernel only: when set, the launch is a no-op unless *run_if != 0
+  // FP32-pipe kernel as ONE cooperative launch over steps [t, t + t_count) (the predicated fall-back behind the
+  // tensor-core kernels: one idle launch instead of Tm + 1): s0 / s1 = the two spike buffers (step t reads what
+  // step t - 1 wrote), grid_bar = a zeroed device word for the barrier between the steps, expand_src = compact byte
+  // histogram to expand into `events` first (or null)
+  int t_count;
+  float* s0;
+  float* s1;
+  unsigned int* grid_bar;
+  const void* expand_src;
 };
 
 

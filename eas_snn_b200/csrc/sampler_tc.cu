@@ -213,7 +213,7 @@ __global__ void sampler_tc_pack_weights(const eas_sampler_weights w, uint8_t* im
     b[4 + threadIdx.x] = w.in_b0[threadIdx.x];
     b[8 + threadIdx.x] = w.gate_b0[threadIdx.x];
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *flag = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) flag[0] = 0, flag[1] = 0;   // fall-back flag, fall-back grid barrier
 }
 
 // ---- the step kernel ----------------------------------------------------------------------------
