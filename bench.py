@@ -740,7 +740,9 @@ def run_ours(args):
                 "unit": "GB/s", "frac": 8.0 * pT * pN / t_plif_f / 1e6 / peak_gbs, "note": "8 B per element-step"},
             "plif_bwd_kernel (f32, T=3, ATan)": {
                 "bound": "hbm", "call_ms": t_plif_b, "achieved": 12.0 * pT * pN / t_plif_b / 1e6, "peak": peak_gbs,
-                "unit": "GB/s", "frac": 12.0 * pT * pN / t_plif_b / 1e6 / peak_gbs, "note": "12 B per element-step"}},
+                "unit": "GB/s", "frac": 12.0 * pT * pN / t_plif_b / 1e6 / peak_gbs,
+                "note": "12 B per element-step (8 read + 4 written); the peak is the measured COPY bandwidth (half reads, "
+                        "half writes), which a read-heavy kernel can slightly exceed"}},
     }
 
     # ---- BASELINE config 5: binning microbenchmark, one window of N events, Tm = 4 -----------------------------
