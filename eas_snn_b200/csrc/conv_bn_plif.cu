@@ -195,6 +195,7 @@ template <int BLOCK_N, int TMAX, int BK, bool REUSE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
                     const ConvArgs a) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next layer may set itself up beside this one
   using L = SmemLayout<BLOCK_N, BK, REUSE>;
   constexpr int SA = L::SA, SB = L::SB, A_BYTES = L::A_BYTES, BLOCK_K = BK;
   extern __shared__ uint8_t smem_raw[];
@@ -246,6 +247,10 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: this grid may have started while the layer before it was still running (its CTAs
+  // take SMs that one leaves idle -- small maps, batch 1); everything above touched no global memory.  From here on
+  // the previous grid has completed and its stores are visible.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -703,8 +708,14 @@ int launch_conv(const CUtensorMap& xmap, const CUtensorMap& wmap, const ConvArgs
   auto kern = conv_bn_plif_kernel<BLOCK_N, TMAX, BK, REUSE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
   if (e != cudaSuccess) return (int)e;
-  kern<<<(unsigned)grid, NUM_THREADS, L::TOTAL, st>>>(xmap, wmap, a);
-  EAS_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(NUM_THREADS), cfg.dynamicSmemBytes = L::TOTAL, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, xmap, wmap, a);
+  if (e != cudaSuccess) return (int)e;
   return EAS_OK;
 }
 
