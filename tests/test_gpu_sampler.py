@@ -415,3 +415,43 @@ def test_compact_histogram_training_and_unsupported_shapes_take_the_dense_path(c
     out = m(ch)                                         # grad mode: dense path, differentiable w.r.t. the parameters
     out.sum().backward()
     assert m.input_conv[0].weight.grad is not None and float(m.input_conv[0].weight.grad.abs().sum()) > 0
+
+
+def test_tensor_kernel_randomised_geometries_vs_fp32_kernel(cuda):
+    """Seeded sweep over what shapes the row-folded kernel's schedule: heights from one row to several row groups,
+    1..6 strips per row, batches that give a CTA less than one segment or several, Tm = 1 (first-and-last step code),
+    Tm up to the byte-packed limit, Ts up to 15, all three read-outs, byte / int32 / fp32 histograms -- against the
+    FP32-pipe kernel (itself pinned to the oracle above) with the same 1e-5 bar."""
+    rng = np.random.default_rng(2024)
+    n_cases = 0
+    for trial in range(36):
+        H = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 9, 13, 31, 64, 97]))
+        W = 4 * int(rng.choice([1, 2, 3, 7, 19, 29, 30, 58, 59, 77, 120, 160]))
+        B = int(rng.choice([1, 2, 3, 5, 17, 40]))
+        if B * H * W > 1_500_000:
+            B = 2
+        Tm = int(rng.choice([1, 2, 3, 4, 6, 14]))
+        Ts = int(rng.choice([1, 1, 2, 3, 15]))
+        flags = dict(readout=str(rng.choice(["sum", "avg", "last"])), Ts=Ts,
+                     vreset=[0, None, 0.25][int(rng.integers(3))], spike_attach=bool(rng.integers(2)),
+                     write_zero=bool(rng.integers(2)), abs=bool(rng.integers(2)))
+        torch.manual_seed(100 + trial)
+        m = eas.AdaptiveRSNNEmbedding(kernel_size=5, depth=2, nb_steps=Tm, thresh=1, **flags).to(cuda)
+        g = torch.Generator().manual_seed(trial)
+        x = torch.poisson(torch.full((B, Tm, 2, H, W), float(rng.choice([0.3, 1.0, 2.5]))), generator=g).to(cuda)
+        kind = trial % 3
+        inp = x if kind == 0 else x.to(torch.int32)
+        m.algo = "fp32"
+        with torch.no_grad():
+            want = m(inp)
+            m.algo = "tensor"
+            got = m(inp)
+            if kind == 2 and eas.binning.compact_fits(H, W):   # the same counts as a compact byte histogram
+                ch = eas.CompactHist.empty((B, Tm, 2, H, W), cuda)
+                ch.buf.zero_()
+                ch.counts.copy_(x.to(torch.uint8))
+                assert torch.equal(m(ch), got), (trial, "compact")
+        ok, frac, msg = _compare(got, want.cpu(), budget=2e-3 if want.numel() < 20000 else 3e-4)
+        assert ok, "trial %d %s %s: %s" % (trial, (B, Tm, H, W), flags, msg)
+        n_cases += 1
+    assert n_cases == 36
