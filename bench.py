@@ -842,9 +842,9 @@ def run_ours(args):
                                                 "once, no kernels: what this box's host memory / PCIe path can feed"},
                     "frac_of_host_ceiling": e2e_val / ceil_val,
                     "checksum": checksum, "numa": numa},
-            # bin: bounds + histogram + lost-count report (3), sampler: weight pack (1) + Tm step launches + ONE
-            # cooperative fall-back launch (idle unless the tensor-core kernel raised its flag)
-            "gpu_launches": args.steps * repeats * (3 + 1 + TM + 1),
+            # bin: bounds + histogram (2), sampler: weight pack (1) + Tm step launches + ONE cooperative fall-back
+            # launch (idle unless the tensor-core kernel raised its flag)
+            "gpu_launches": args.steps * repeats * (2 + 1 + TM + 1),
             "clocks": clk, "roofline": roofline}
     if sweep is not None:
         line["binning_sweep"] = sweep

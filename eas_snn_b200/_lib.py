@@ -63,6 +63,7 @@ SIGNATURES = {
     "eas_hist_u8_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int, C.c_int]),
     "eas_hist_u8_expand": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),
     "eas_hist_u8_report": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "eas_hist_u8_set_sticky": (C.c_int, [_P]),
     "eas_sampler_fwd_ws_bytes": (C.c_size_t, [C.POINTER(SamplerCfg)]),
     "eas_sampler_fwd": (C.c_int, [C.POINTER(SamplerCfg), _P, C.POINTER(SamplerPtrs), _P, _P, _P, _P,
                                   C.c_size_t, _P]),

@@ -23,9 +23,9 @@ class CompactHist:
     (``AdaptiveRSNNEmbedding.forward(CompactHist)``); :meth:`dense` gives the ``[B, Tm, 2, H, W]`` tensor back.
 
     Only when more than ``SAT_CAP`` bins saturate in one call is information lost (``lost`` flag in the buffer).
-    That is reported without stalling the stream: a 1-thread kernel behind every call ORs the flag into a pinned host
-    int and :func:`poll_compact` (run by the next binning call, or by hand) raises ``OverflowError`` once it is set;
-    :meth:`check` waits and checks this buffer now."""
+    That is reported without stalling the stream: the binning kernel sets a pinned host int (registered with the library
+    once per process) at the moment it loses a count, and :func:`poll_compact` (run by the next binning call, or by hand)
+    raises ``OverflowError`` once it is set; :meth:`check` waits and checks this buffer now."""
 
     def __init__(self, buf: torch.Tensor, shape):
         self.buf, self.shape = buf, tuple(int(v) for v in shape)
@@ -81,14 +81,9 @@ class CompactHist:
         return self
 
     def _queue_check(self):
-        """One 1-thread kernel after the binning call ORs the buffer's ``lost`` word into a pinned host int (sticky):
-        no copy-engine traffic, no event, nothing for the stream to wait on."""
-        flag = _sticky_flag()
-        B, Tm, _, H, W = self.shape
-        with torch.cuda.device(self.buf.device):
-            rc = _lib.lib().eas_hist_u8_report(_lib.ptr(self.buf), B, Tm, H, W, C.c_void_p(flag.data_ptr()),
-                                               _lib.stream_ptr())
-        _lib.check(rc, "eas_hist_u8_report")
+        """Nothing to launch: the binning kernel itself sets the registered pinned host int (``_sticky_flag``) at the
+        moment it loses a count; :func:`poll_compact` reads it."""
+        _sticky_flag()
 
 
 _LOST_MSG = ("compact histogram: more than %d bins collected >= 255 events in one call, counts were lost; "
@@ -97,8 +92,12 @@ _STICKY: list = []       # one pinned int32: set by the device when a compact bi
 
 
 def _sticky_flag() -> torch.Tensor:
+    """The process-wide pinned int32 the compact binning kernels set when they lose a count (registered with the
+    library once: ``eas_hist_u8_set_sticky``; pinned host memory is device-accessible under unified addressing)."""
     if not _STICKY:
-        _STICKY.append(torch.zeros(1, dtype=torch.int32).pin_memory())
+        flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+        _lib.check(_lib.lib().eas_hist_u8_set_sticky(C.c_void_p(flag.data_ptr())), "eas_hist_u8_set_sticky")
+        _STICKY.append(flag)
     return _STICKY[0]
 
 
@@ -125,6 +124,7 @@ def _hist_out(B, Tm, H, W, out, dtype, device):
     if isinstance(out, CompactHist):
         if out.shape != shape or out.buf.numel() < CompactHist.nbytes_for(shape):
             raise ValueError("out: CompactHist of another shape")
+        _sticky_flag()                       # (registered with the library before the first compact call)
         return out, out.buf, _lib.EAS_U8
     if out.shape != shape or out.dtype not in (torch.int32, torch.float32) or not out.is_contiguous():
         raise ValueError("out must be a contiguous int32/float32 [B, Tm, 2, H, W] tensor or a CompactHist")

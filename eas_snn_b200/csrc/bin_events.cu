@@ -24,6 +24,9 @@
 
 namespace {
 
+// Process-wide: where compact binning calls report lost counts (eas_hist_u8_set_sticky); may be pinned host memory.
+int32_t* g_sticky = nullptr;
+
 // Where the events come from.  SoaSrc: the reference's events_struct de-interleaved (x, y, t, p) with
 // windows back to back (offsets[B+1]).  DatSrc: raw 8-byte PSEE .dat Event2D records
 // {u32 t; u32 x:14 | y:14 << 14 | p << 28} (dat_events_tools.py:24, 46-51) with one [first, last) record
@@ -82,11 +85,12 @@ constexpr int kChunk = 65535;
 template <typename SRC>
 __global__ void __launch_bounds__(128)
 bin_bounds_kernel(const SRC src, int64_t B, int Tm, int64_t* __restrict__ bounds,
-                  unsigned int* __restrict__ work_counter, uint32_t* __restrict__ sat_tail) {
+                  unsigned int* __restrict__ work_counter, uint32_t* __restrict__ sat_tail, int32_t* sticky) {
   const int lane = threadIdx.x & 31;
   const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (gid == 0 && lane == 0) *work_counter = 0u;
   if (gid == 0 && lane < 2 && sat_tail) sat_tail[lane] = 0u;   // compact output: empty saturation list
+  if (gid == 0 && lane == 2 && sat_tail) *reinterpret_cast<int32_t**>(sat_tail + 2) = sticky;
   if (gid >= B * (Tm + 1)) return;
   const int64_t b = gid / (Tm + 1);
   const int k = (int)(gid - b * (Tm + 1));
@@ -498,7 +502,7 @@ extern "C" int eas_bin_dat(const void* rec, int64_t n_rec, const int64_t* ranges
     sat_tail = (uint32_t*)((char*)hist + hist_u8_tail_offset((size_t)nbins));
   }
   bin_bounds_kernel<DatSrc><<<(unsigned)eas_ceil_div(nb * 32, 128), 128, 0, stream>>>(src, B, Tm, bounds, counter,
-                                                                                    sat_tail);
+                                                                                    sat_tail, g_sticky);
   EAS_LAUNCH_CHECK();
   const SlabGeo g = slab_geo(H, W);
   const int64_t n_items = B * Tm * 2 * g.n_slabs;
@@ -560,7 +564,7 @@ extern "C" int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64
     sat_tail = (uint32_t*)((char*)hist + hist_u8_tail_offset((size_t)(B * Tm * 2 * HW)));
   }
   bin_bounds_kernel<SoaSrc><<<(unsigned)eas_ceil_div(nb * 32, 128), 128, 0, stream>>>(src, B, Tm, bounds, counter,
-                                                                                    sat_tail);
+                                                                                    sat_tail, g_sticky);
   EAS_LAUNCH_CHECK();
 
   // row slabs so that one slab of 16-bit counters fits the per-CTA shared memory budget
@@ -663,6 +667,11 @@ extern "C" int eas_hist_u8_report(const void* hist_u8, int64_t B, int Tm, int H,
   hist_u8_report_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const uint8_t*)hist_u8, B * Tm * 2 * (int64_t)H * W,
                                                          sticky_flag);
   EAS_LAUNCH_CHECK();
+  return EAS_OK;
+}
+
+extern "C" int eas_hist_u8_set_sticky(int32_t* sticky_flag) {
+  g_sticky = sticky_flag;
   return EAS_OK;
 }
 

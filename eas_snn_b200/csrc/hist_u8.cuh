@@ -3,7 +3,8 @@
 //   bytes [0, nbins)                 min(count, 255); 255 = "saturated: the count is in the list"
 //   at eas_align_up(nbins, 256)      uint32 n_sat   entries appended (may exceed the capacity)
 //                                    uint32 lost    1 when an entry did not fit: the histogram is NOT exact any more
-//                                    uint32 pad[2]
+//                                    uint64 sticky  address of a caller-registered int32 (eas_hist_u8_set_sticky) that is set to 1
+//                                                   together with `lost`, or 0
 //   then EAS_HIST_U8_SAT_CAP         uint2 {bin index, count >= 255}
 // The reference's histogram is an int64 / float tensor (gen1.py:330-360); on event data almost every count is a
 // single digit, so the byte form carries the same information in a quarter of the fp32 bytes -- what the binning
@@ -25,8 +26,11 @@ __device__ __forceinline__ void hist_u8_append(uint32_t* __restrict__ tail, uint
   const uint32_t slot = atomicAdd(tail, 1u);
   if (slot < (uint32_t)EAS_HIST_U8_SAT_CAP)
     reinterpret_cast<uint2*>(tail + 4)[slot] = make_uint2(idx, count);
-  else
+  else {
     tail[1] = 1u;
+    int32_t* sticky = *reinterpret_cast<int32_t* const*>(tail + 2);   // pinned host int of the caller, if registered
+    if (sticky) *reinterpret_cast<volatile int32_t*>(sticky) = 1;
+  }
 }
 __device__ __forceinline__ uint32_t hist_u8_enc(uint32_t* __restrict__ tail, uint32_t idx, uint32_t count) {
   if (count < kHistU8Sat) return count;

@@ -66,7 +66,7 @@ int eas_bin_events(const int16_t* x, const int16_t* y, const int64_t* t, const u
  * the compact form the sampler reads directly (eas_sampler_cfg.in_dtype = EAS_U8) -- a quarter of the
  * bytes to write and to read.  `hist` is then ONE buffer of eas_hist_u8_bytes(B, Tm, H, W) bytes:
  *   [0, nbins)                    uint8 min(count, 255), nbins = B*Tm*2*H*W (< 2^32)
- *   at nbins rounded up to 256    uint32 n_sat, uint32 lost, uint32 pad[2],
+ *   at nbins rounded up to 256    uint32 n_sat, uint32 lost, uint64 (address of the registered sticky flag, or 0),
  *                                 then EAS_HIST_U8_SAT_CAP x {uint32 bin index, uint32 count} for the
  *                                 bins that reached 255: the information of the int histogram, exactly,
  *                                 unless more than EAS_HIST_U8_SAT_CAP bins saturate in one call (lost = 1;
@@ -81,6 +81,9 @@ int eas_hist_u8_expand(const void* hist_u8, int64_t B, int Tm, int H, int W, voi
  * word is set.  sticky_flag may be pinned host memory (device-accessible under unified addressing): the host
  * then polls a plain int. */
 int eas_hist_u8_report(const void* hist_u8, int64_t B, int Tm, int H, int W, int32_t* sticky_flag, void* stream);
+/* The same without a launch: registers (process-wide; NULL = none) an int32 that every later EAS_U8 binning call sets
+ * to 1 at the moment it loses a count.  Device-accessible memory, e.g. pinned host memory. */
+int eas_hist_u8_set_sticky(int32_t* sticky_flag);
 int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64_t* t, const uint8_t* p,
                       const int64_t* offsets, int64_t B, int64_t n_events, int H, int W, int Tm,
                       void* hist, void* ws, size_t ws_bytes, void* stream, int strategy, int out_dtype);
