@@ -86,6 +86,7 @@ template <typename SRC>
 __global__ void __launch_bounds__(128)
 bin_bounds_kernel(const SRC src, int64_t B, int Tm, int64_t* __restrict__ bounds,
                   unsigned int* __restrict__ work_counter, uint32_t* __restrict__ sat_tail, int32_t* sticky) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the histogram kernel may be scheduled behind this one
   const int lane = threadIdx.x & 31;
   const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (gid == 0 && lane == 0) *work_counter = 0u;
@@ -140,6 +141,9 @@ bin_hist_smem_kernel(const SRC src, const int64_t* __restrict__ bounds, int64_t 
                      int H, int W, int Tm, int n_slabs, int slab_rows, uint32_t* __restrict__ hist,
                      unsigned int* __restrict__ work_counter, uint32_t* __restrict__ sat_tail) {
   constexpr bool kU8 = std::is_same<OUT_T, uint8_t>::value;
+  // programmatic dependent launch: this grid may have been scheduled before the bounds kernel finished -- wait for it
+  // before reading anything
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   extern __shared__ __align__(16) uint32_t cnt[];  // ceil(slab_rows*W/2) words, two 16-bit counters per word
   __shared__ unsigned int sh_item;
   const int64_t HW = (int64_t)H * W;
@@ -401,9 +405,15 @@ int launch_tiles(const SRC& src, const int64_t* bounds, int64_t n_items, int H, 
   const int per_sm = (int)((220 * 1024) / (g.smem + 1024));
   int64_t grid = (int64_t)EAS_NUM_SMS * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
   if (grid > n_items) grid = n_items;
-  kern<<<(unsigned)grid, kSmemThreads, g.smem, stream>>>(src, bounds, n_items, H, W, Tm, g.n_slabs, g.slab_rows,
-                                                         (uint32_t*)hist, counter, sat_tail);
-  EAS_LAUNCH_CHECK();
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)grid), lc.blockDim = dim3(kSmemThreads), lc.dynamicSmemBytes = g.smem, lc.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr, lc.numAttrs = 1;
+  e = cudaLaunchKernelEx(&lc, kern, src, bounds, n_items, H, W, Tm, g.n_slabs, g.slab_rows, (uint32_t*)hist, counter,
+                         sat_tail);
+  if (e != cudaSuccess) return (int)e;
   return EAS_OK;
 }
 

@@ -396,6 +396,7 @@ template <int kIn, bool kSimple, int kStep>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 sampler_tc2_step_kernel(const StepArgs a, const Tc2State st, const Tc2Geo g, const uint8_t* __restrict__ wimg,
                         int* __restrict__ ovf_flag) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next step's grid may be scheduled behind this one
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -437,6 +438,9 @@ sampler_tc2_step_kernel(const StepArgs a, const Tc2State st, const Tc2Geo g, con
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // programmatic dependent launch: the grid was allowed to start before the previous step (or the weight pack) had
+  // finished; nothing above touched global memory, everything below may read what that grid wrote
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   {
     const uint4* src = reinterpret_cast<const uint4*>(wimg);
     uint4* dst = reinterpret_cast<uint4*>(smem);
@@ -931,6 +935,8 @@ int eas_sampler_tc2_run(const eas_sampler_cfg* cfg, StepArgs a, uint8_t* meta8, 
                         cudaStream_t st) {
   EAS_REQUIRE((uintptr_t)wimg % 16 == 0 && (uintptr_t)meta8 % 4 == 0, EAS_E_ALIGN);
   int* flag = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(wimg) + WIMG_BYTES);
+  // (a plain launch: the pack WRITES into the caller's workspace without reading anything first, so it must not start
+  // while the kernel before it may still be using memory the stream-ordered allocator has recycled into that workspace)
   sampler_tc2_pack_weights<<<40, 256, 0, st>>>(a.w, reinterpret_cast<uint8_t*>(wimg), flag);
   EAS_LAUNCH_CHECK();
   const Tc2Geo g = pick_geo(cfg->W);
@@ -966,8 +972,14 @@ int eas_sampler_tc2_run(const eas_sampler_cfg* cfg, StepArgs a, uint8_t* meta8, 
     s2.sb_prev = (t & 1) ? sb0 : sb1;  // step t reads what step t-1 wrote
     s2.sb_next = (t & 1) ? sb1 : sb0;
     const int kind = (t == 0 ? (cfg->Tm == 1 ? 3 : 0) : (t == cfg->Tm - 1 ? 2 : 1));
-    kerns[kind]<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, st>>>(a, s2, g, reinterpret_cast<const uint8_t*>(wimg), flag);
-    EAS_LAUNCH_CHECK();
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)grid), lc.blockDim = dim3(NUM_THREADS), lc.dynamicSmemBytes = SMEM_BYTES, lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr, lc.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&lc, kerns[kind], a, s2, g, reinterpret_cast<const uint8_t*>(wimg), flag);
+    if (le != cudaSuccess) return (int)le;
   }
   return EAS_OK;
 }
