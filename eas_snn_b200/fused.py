@@ -383,7 +383,17 @@ class _SPP(nn.Module):
         # (training path) PyTorch's channels-last max-pool kernels are ~5x slower than its NCHW ones at these window
         # sizes -- 0.81 of a 6.9 ms SYOLOX-S step in profiles/r2_launches_train_summary.txt: pool an NCHW copy
         xp = x.contiguous() if not x.is_contiguous() else x
-        return self.conv2(torch.cat([x] + [m(xp) for m in self.m], dim=-3))
+        return self.conv2(_cat_channels([x] + [m(xp) for m in self.m]))
+
+
+def _cat_channels(parts):
+    """``torch.cat(parts, dim=-3)`` for ``[T, B, C, H, W]`` activations (training path).  When the parts are views of
+    channels-last buffers (cuDNN NHWC kernels, the neurons working in place) the concatenation is done on the memory as it
+    lies and handed back as the same kind of view; ``torch.cat`` would produce an NCHW tensor there and the next
+    channels-last convolution would convert it back (one copy kernel per concatenation and another per consumer)."""
+    if all(p.dim() == 5 and not p.is_contiguous() and p.permute(0, 1, 3, 4, 2).is_contiguous() for p in parts):
+        return torch.cat([p.permute(0, 1, 3, 4, 2) for p in parts], dim=-1).permute(0, 1, 4, 2, 3)
+    return torch.cat(parts, dim=-3)
 
 
 class _CSPLayer(nn.Module):
@@ -407,7 +417,7 @@ class _CSPLayer(nn.Module):
         return self.conv3.run(cat, T, out=out)
 
     def forward(self, x):
-        return self.conv3(torch.cat((self.m(self.conv1(x)), self.conv2(x)), dim=-3))
+        return self.conv3(_cat_channels([self.m(self.conv1(x)), self.conv2(x)]))
 
 
 class SpikingCSPDarknet(nn.Module):
