@@ -120,3 +120,21 @@ def test_convert_to_spiking_gives_the_reference_checkpoint_layout():
     n_fused = sum(isinstance(m, fused.FusedConvBNPLIF) for m in net.modules())
     assert n_fused == sum(eas.is_spiking_neuron(m) for m in net.modules()) == 34
     assert all(isinstance(m, fused.SeqToANNContainer) for m in net.dark5[1].m)
+
+
+def test_training_path_channel_concat_keeps_channels_last_views():
+    """fused._cat_channels == torch.cat(dim=-3) in value; on [T, B, C, H, W] views of channels-last buffers (the training
+    path with cuDNN NHWC kernels) the result is again such a view -- no NCHW round trip between concat and the next conv."""
+    import torch
+    from eas_snn_b200 import fused
+    T, B, H, W = 3, 2, 5, 7
+    parts_cl = [torch.randn(T * B, c, H, W).contiguous(memory_format=torch.channels_last).view(T, B, c, H, W) for c in (4, 8)]
+    out = fused._cat_channels(parts_cl)
+    assert torch.equal(out, torch.cat(parts_cl, dim=-3))
+    assert not out.is_contiguous() and out.permute(0, 1, 3, 4, 2).is_contiguous()
+    assert out.flatten(0, 1).is_contiguous(memory_format=torch.channels_last)      # what the next conv sees
+    parts = [p.contiguous() for p in parts_cl]
+    out2 = fused._cat_channels(parts)
+    assert out2.is_contiguous() and torch.equal(out2, out)
+    mixed = fused._cat_channels([parts_cl[0], parts[1]])
+    assert torch.equal(mixed, out)
