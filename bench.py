@@ -637,7 +637,7 @@ def run_ours(args):
             fr = torch.nn.functional.pad(t_emb(h), (0, 320 - W, 0, 256 - H))
             return sum((v.mean() - 0.2) ** 2 for v in t_bb(fr).values())
 
-        gstep = fused.GraphedTrainStep(t_loss, [t_hist], t_params, opt_g, allreduce=parallel.allreduce_gradients,
+        gstep = fused.GraphedTrainStep(t_loss, [t_hist], t_params, opt_g, allreduce="flat",
                                        after=lambda: eas.reset_net(t_bb))
         for _ in range(3):
             gstep(t_hist)
