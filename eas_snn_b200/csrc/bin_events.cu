@@ -159,7 +159,8 @@ bin_hist_smem_kernel(const SRC src, const int64_t* __restrict__ bounds, int64_t 
     const int64_t bk = bkc >> 1;
     const int64_t b = bk / Tm;
     const int k = (int)(bk - b * Tm);
-    const int64_t s = bounds[b * (Tm + 1) + k], e = bounds[b * (Tm + 1) + k + 1];
+    // (coherent loads: this grid may have been scheduled before the bounds kernel finished, see ld_cg_* in common.cuh)
+    const int64_t s = __ldcg(bounds + b * (Tm + 1) + k), e = __ldcg(bounds + b * (Tm + 1) + k + 1);
     const int y_lo = slab * slab_rows;
     const int rows = min(slab_rows, H - y_lo);
     const int npix = rows * W;

@@ -54,3 +54,28 @@ __device__ __forceinline__ void st_stream_u4(uint4* p, uint4 v) {
                "r"(v.z), "r"(v.w)
                : "memory");
 }
+
+// Coherent (L2) loads for data the PREVIOUS kernel of the stream wrote, in kernels launched with the programmatic
+// dependent-launch attribute: such a grid starts before that kernel has finished, which is outside the contract of
+// the read-only (.nc) path even though every dependent access comes after griddepcontrol.wait.
+__device__ __forceinline__ uint4 ld_cg_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ld_cg_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
+  uint32_t r;
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_cg_u8(const uint8_t* p) {
+  uint32_t r;
+  asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+

@@ -509,7 +509,7 @@ conv_bn_plif_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         for (int t = 0; t < RT; ++t) {
           if (kPrefRes && t < a.T && res_vec && ch0 + 16 <= a.Cout) {
             const uint4* rp = reinterpret_cast<const uint4*>(a.residual + ((int64_t)t * step + pix) * a.res_ld + ch0);
-            r[t][0] = ld_stream_u4(rp), r[t][1] = ld_stream_u4(rp + 1);
+            r[t][0] = ld_cg_u4(rp), r[t][1] = ld_cg_u4(rp + 1);
           }
         }
       };

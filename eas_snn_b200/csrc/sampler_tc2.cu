@@ -493,8 +493,8 @@ sampler_tc2_step_kernel(const StepArgs a, const Tc2State st, const Tc2Geo g, con
             v[rho][0] = ok ? ld_stream_u4(reinterpret_cast<const uint4*>(ev_img + off * 4)) : make_uint4(0u, 0u, 0u, 0u);
             v[rho][1] = ok ? ld_stream_u4(reinterpret_cast<const uint4*>(ev_img + (HW + off) * 4)) : make_uint4(0u, 0u, 0u, 0u);
           }
-          sp[rho] = (ok && !first) ? ((ld_stream_u8(sp_img + y * WQ + (x >> 2)) & 15u) |
-                                      (ld_stream_u8(sp_img + (a.H + y) * WQ + (x >> 2)) << 4))
+          sp[rho] = (ok && !first) ? ((ld_cg_u8(sp_img + y * WQ + (x >> 2)) & 15u) |
+                                      (ld_cg_u8(sp_img + (a.H + y) * WQ + (x >> 2)) << 4))
                                    : 0u;
         }
       };
@@ -770,14 +770,14 @@ sampler_tc2_step_kernel(const StepArgs a, const Tc2State st, const Tc2Geo g, con
         if (col_ok && r2 + 1 < s2.nrows) off1 = (s2.ya + r2 + 1) * a.W + gx;
         if (!first) {
           if (off0 >= 0) {
-            vq0 = ld_stream_f4(reinterpret_cast<const float4*>(vm_b + off0));
-            aq0 = ld_stream_f4(reinterpret_cast<const float4*>(acc_b + off0));
-            mt0 = ld_stream_u32(reinterpret_cast<const uint32_t*>(meta_b + off0));
+            vq0 = ld_cg_f4(reinterpret_cast<const float4*>(vm_b + off0));
+            aq0 = ld_cg_f4(reinterpret_cast<const float4*>(acc_b + off0));
+            mt0 = ld_cg_u32(reinterpret_cast<const uint32_t*>(meta_b + off0));
           }
           if (off1 >= 0) {
-            vq1 = ld_stream_f4(reinterpret_cast<const float4*>(vm_b + off1));
-            aq1 = ld_stream_f4(reinterpret_cast<const float4*>(acc_b + off1));
-            mt1 = ld_stream_u32(reinterpret_cast<const uint32_t*>(meta_b + off1));
+            vq1 = ld_cg_f4(reinterpret_cast<const float4*>(vm_b + off1));
+            aq1 = ld_cg_f4(reinterpret_cast<const float4*>(acc_b + off1));
+            mt1 = ld_cg_u32(reinterpret_cast<const uint32_t*>(meta_b + off1));
           }
         }
       }
