@@ -177,12 +177,21 @@ bin_hist_smem_kernel(const SRC src, const int64_t* __restrict__ bounds, int64_t 
       // the scan is issue bound (ncu: ALU pipe 60 %, ~50 thread instructions per event): chunk-relative 32-bit
       // indices and unsigned range tests keep the per-event work to a dozen instructions
       const uint32_t uW = (uint32_t)W, urows = (uint32_t)rows, uc = (uint32_t)c;
+      // One predicated red.shared per event, no branch: the scan is issue bound and a branch per event costs the
+      // reconvergence pair on top of the test; the shared-memory base is one 32-bit register instead of a generic
+      // pointer that the compiler re-derives (S2UR / ULEA) at every use.
+      uint32_t cnt_s = (uint32_t)__cvta_generic_to_shared(cnt);
+      asm volatile("mov.u32 %0, %0;" : "+r"(cnt_s));   // opaque: one register, not a constant to rematerialise per event
       auto count = [&](int xi, int yi, int ci) {
         const uint32_t yr = (uint32_t)(yi - y_lo);
-        if ((uint32_t)ci == uc && (uint32_t)xi < uW && yr < urows) {
-          const uint32_t pix = yr * uW + (uint32_t)xi;
-          atomicAdd(cnt + (pix >> 1), 1u << ((pix & 1u) << 4));
-        }
+        const uint32_t pix = yr * uW + (uint32_t)xi;
+        const uint32_t ok = ((uint32_t)ci == uc) & ((uint32_t)xi < uW) & (yr < urows);
+        asm volatile(
+            "{\n\t.reg .pred q;\n\t"
+            "setp.ne.u32 q, %2, 0;\n\t"
+            "@q red.shared.add.u32 [%0], %1;\n\t}"
+            ::"r"(cnt_s + ((pix + pix) & ~3u)), "r"((pix & 1u) * 0xffffu + 1u), "r"(ok)
+            : "memory");
       };
       const int n_chunk = (int)(ce - cs);   // <= 65535
       if constexpr (SRC::VW > 1) {
