@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-STRATEGY = {"auto": 0, "reds": 1, "tiles": 2}
+STRATEGY = {"auto": 0, "reds": 1, "tiles": 2, "tiles_pair": 3, "tiles_planes": 4}
 SAT_CAP = 4096          # EAS_HIST_U8_SAT_CAP (include/eas_b200.h)
 
 

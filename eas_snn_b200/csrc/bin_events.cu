@@ -18,6 +18,7 @@
 //      bin_hist_global_kernel ("reds"): event-parallel, 8 events per thread with 16 B loads,
 //         red.global.add.u32 into the (L2-resident when it fits) histogram after a memset.  Used for
 //         frames that do not fit in shared memory and for very long windows.
+#include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
 #include "hist_u8.cuh"
@@ -135,8 +136,11 @@ template <> struct Cvt<float> {  // counts < 2^24 are exact in fp32
   }
 };
 
-template <typename OUT_T, typename SRC>
-__global__ void __launch_bounds__(kSmemThreads, 3)
+// BOTH: one item = (window, micro-bin, slab) with the counters of BOTH polarities in shared memory (2 x the slab, one
+// 1024-thread CTA per SM): every event is scanned by n_slabs items instead of 2 * n_slabs, and the polarity test becomes
+// a plane offset.
+template <typename OUT_T, typename SRC, int NT, bool BOTH>
+__global__ void __launch_bounds__(NT, BOTH ? 1 : 3)
 bin_hist_smem_kernel(const SRC src, const int64_t* __restrict__ bounds, int64_t n_items,
                      int H, int W, int Tm, int n_slabs, int slab_rows, uint32_t* __restrict__ hist,
                      unsigned int* __restrict__ work_counter, uint32_t* __restrict__ sat_tail) {
@@ -154,9 +158,9 @@ bin_hist_smem_kernel(const SRC src, const int64_t* __restrict__ bounds, int64_t 
     const int64_t item = sh_item;
     if (item >= n_items) break;
     const int slab = (int)(item % n_slabs);
-    const int64_t bkc = item / n_slabs;  // (b*Tm + k)*2 + c
-    const int c = (int)(bkc & 1);
-    const int64_t bk = bkc >> 1;
+    const int64_t bkc0 = item / n_slabs;  // (b*Tm + k)*2 + c, or b*Tm + k with both polarities in one item
+    const int c = BOTH ? 0 : (int)(bkc0 & 1);
+    const int64_t bk = BOTH ? bkc0 : (bkc0 >> 1);
     const int64_t b = bk / Tm;
     const int k = (int)(bk - b * Tm);
     // (coherent loads: this grid may have been scheduled before the bounds kernel finished, see ld_cg_* in common.cuh)
@@ -166,11 +170,11 @@ bin_hist_smem_kernel(const SRC src, const int64_t* __restrict__ bounds, int64_t 
     const int npix = rows * W;
     const int nwords = (npix + 1) >> 1;
     const int nwords4 = (nwords + 3) & ~3;
-    uint32_t* __restrict__ out = hist + bkc * HW + (int64_t)y_lo * W;
+    constexpr int NP = BOTH ? 2 : 1;     // polarity planes held by this item
     const bool vec_ok = (npix & 3) == 0 && ((((int64_t)y_lo * W) & 3) == 0) && ((HW & 3) == 0);
     bool first = true;
     for (int64_t cs = s; first || cs < e; cs += kChunk) {
-      for (int w = threadIdx.x * 4; w < nwords4; w += kSmemThreads * 4)
+      for (int w = threadIdx.x * 4; w < NP * nwords4; w += NT * 4)
         *reinterpret_cast<uint4*>(cnt + w) = make_uint4(0u, 0u, 0u, 0u);
       __syncthreads();
       const int64_t ce = (e - cs > kChunk) ? cs + kChunk : e;
@@ -180,17 +184,19 @@ bin_hist_smem_kernel(const SRC src, const int64_t* __restrict__ bounds, int64_t 
       // One predicated red.shared per event, no branch: the scan is issue bound and a branch per event costs the
       // reconvergence pair on top of the test; the shared-memory base is one 32-bit register instead of a generic
       // pointer that the compiler re-derives (S2UR / ULEA) at every use.
+      const uint32_t plane_bytes = (uint32_t)nwords4 * 4u;
       uint32_t cnt_s = (uint32_t)__cvta_generic_to_shared(cnt);
       asm volatile("mov.u32 %0, %0;" : "+r"(cnt_s));   // opaque: one register, not a constant to rematerialise per event
       auto count = [&](int xi, int yi, int ci) {
         const uint32_t yr = (uint32_t)(yi - y_lo);
         const uint32_t pix = yr * uW + (uint32_t)xi;
-        const uint32_t ok = ((uint32_t)ci == uc) & ((uint32_t)xi < uW) & (yr < urows);
+        const uint32_t ok = (BOTH ? 1u : (uint32_t)((uint32_t)ci == uc)) & ((uint32_t)xi < uW) & (yr < urows);
+        const uint32_t plane = BOTH ? (uint32_t)ci * plane_bytes : 0u;
         asm volatile(
             "{\n\t.reg .pred q;\n\t"
             "setp.ne.u32 q, %2, 0;\n\t"
             "@q red.shared.add.u32 [%0], %1;\n\t}"
-            ::"r"(cnt_s + ((pix + pix) & ~3u)), "r"((pix & 1u) * 0xffffu + 1u), "r"(ok)
+            ::"r"(cnt_s + plane + ((pix + pix) & ~3u)), "r"((pix & 1u) * 0xffffu + 1u), "r"(ok)
             : "memory");
       };
       const int n_chunk = (int)(ce - cs);   // <= 65535
@@ -203,7 +209,7 @@ bin_hist_smem_kernel(const SRC src, const int64_t* __restrict__ bounds, int64_t 
         const int64_t avail = src.n - g0;               // events from g0 on that whole groups cover (clamped: int)
         const int n_full = (int)((avail < (1 << 20) ? avail : (int64_t)(1 << 20)) / VW * VW);
 #pragma unroll 2
-        for (int o = (int)threadIdx.x * VW; o < lead + n_chunk; o += kSmemThreads * VW) {
+        for (int o = (int)threadIdx.x * VW; o < lead + n_chunk; o += NT * VW) {
           if (o + VW <= n_full) {
             int xs[VW], ys[VW], cc[VW];
             src.loadv(g0 + o, xs, ys, cc);
@@ -220,78 +226,84 @@ bin_hist_smem_kernel(const SRC src, const int64_t* __restrict__ bounds, int64_t 
         }
       } else {
 #pragma unroll 4
-        for (int i = (int)threadIdx.x; i < n_chunk; i += kSmemThreads) {
+        for (int i = (int)threadIdx.x; i < n_chunk; i += NT) {
           int xi, yi, ci;
           src.xyc(cs + i, xi, yi, ci);
           count(xi, yi, ci);
         }
       }
       __syncthreads();
-      if constexpr (kU8) {
-        // compact output: one byte per bin, the exact count of a saturated bin goes to the side list (hist_u8.cuh)
-        const int64_t base = bkc * HW + (int64_t)y_lo * W;
-        uint8_t* __restrict__ out8 = reinterpret_cast<uint8_t*>(hist) + base;
-        const uint32_t idx0 = (uint32_t)base;
-        if (first && (npix & 15) == 0 && (base & 15) == 0) {
-          // 8 words = 16 counters -> one 16 B store
-          for (int w = threadIdx.x * 8; w < nwords; w += kSmemThreads * 8) {
-            const uint4 va = *reinterpret_cast<const uint4*>(cnt + w), vb = *reinterpret_cast<const uint4*>(cnt + w + 4);
-            const uint32_t cw[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-            uint32_t o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t c0 = cw[2 * j] & 0xffffu, c1 = cw[2 * j] >> 16, c2 = cw[2 * j + 1] & 0xffffu, c3 = cw[2 * j + 1] >> 16;
-              if ((c0 | c1 | c2 | c3) >= kHistU8Sat) {   // (a superset of "one of them saturates")
-                const uint32_t q = idx0 + 2u * (uint32_t)w + 4u * (uint32_t)j;
-                c0 = hist_u8_enc(sat_tail, q, c0), c1 = hist_u8_enc(sat_tail, q + 1, c1);
-                c2 = hist_u8_enc(sat_tail, q + 2, c2), c3 = hist_u8_enc(sat_tail, q + 3, c3);
+      for (int cpl = 0; cpl < NP; ++cpl) {
+        const uint32_t* __restrict__ cn = cnt + cpl * nwords4;
+        const int64_t bkc = BOTH ? bk * 2 + cpl : bkc0;
+        uint32_t* __restrict__ out = hist + bkc * HW + (int64_t)y_lo * W;
+        (void)out;
+        if constexpr (kU8) {
+          // compact output: one byte per bin, the exact count of a saturated bin goes to the side list (hist_u8.cuh)
+          const int64_t base = bkc * HW + (int64_t)y_lo * W;
+          uint8_t* __restrict__ out8 = reinterpret_cast<uint8_t*>(hist) + base;
+          const uint32_t idx0 = (uint32_t)base;
+          if (first && (npix & 15) == 0 && (base & 15) == 0) {
+            // 8 words = 16 counters -> one 16 B store
+            for (int w = threadIdx.x * 8; w < nwords; w += NT * 8) {
+              const uint4 va = *reinterpret_cast<const uint4*>(cn + w), vb = *reinterpret_cast<const uint4*>(cn + w + 4);
+              const uint32_t cw[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+              uint32_t o[4];
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint32_t c0 = cw[2 * j] & 0xffffu, c1 = cw[2 * j] >> 16, c2 = cw[2 * j + 1] & 0xffffu, c3 = cw[2 * j + 1] >> 16;
+                if ((c0 | c1 | c2 | c3) >= kHistU8Sat) {   // (a superset of "one of them saturates")
+                  const uint32_t q = idx0 + 2u * (uint32_t)w + 4u * (uint32_t)j;
+                  c0 = hist_u8_enc(sat_tail, q, c0), c1 = hist_u8_enc(sat_tail, q + 1, c1);
+                  c2 = hist_u8_enc(sat_tail, q + 2, c2), c3 = hist_u8_enc(sat_tail, q + 3, c3);
+                }
+                o[j] = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
               }
-              o[j] = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+              st_stream_u4(reinterpret_cast<uint4*>(out8 + 2 * w), make_uint4(o[0], o[1], o[2], o[3]));
             }
-            st_stream_u4(reinterpret_cast<uint4*>(out8 + 2 * w), make_uint4(o[0], o[1], o[2], o[3]));
+          } else {
+            for (int q = threadIdx.x; q < npix; q += NT) {
+              const uint32_t v = (cn[q >> 1] >> ((q & 1) << 4)) & 0xffffu;
+              if (first) {
+                out8[q] = (uint8_t)hist_u8_enc(sat_tail, idx0 + (uint32_t)q, v);
+              } else if (v) {   // a further chunk of a very long micro-bin (same thread as the first chunk's write)
+                const uint32_t old = out8[q];
+                if (old < kHistU8Sat) {
+                  out8[q] = (uint8_t)hist_u8_enc(sat_tail, idx0 + (uint32_t)q, old + v);
+                } else {
+                  uint32_t n = sat_tail[0];
+                  if (n > (uint32_t)EAS_HIST_U8_SAT_CAP) n = (uint32_t)EAS_HIST_U8_SAT_CAP;
+                  uint2* ent = reinterpret_cast<uint2*>(sat_tail + 4);
+                  for (uint32_t i = 0; i < n; ++i)
+                    if (ent[i].x == idx0 + (uint32_t)q) {
+                      ent[i].y += v;
+                      break;
+                    }
+                }
+              }
+            }
+          }
+        } else if (vec_ok) {
+          // 2 words = 4 counters -> one 16 B store
+          for (int w = threadIdx.x * 2; w < nwords; w += NT * 2) {
+            const uint2 v = *reinterpret_cast<const uint2*>(cn + w);
+            const uint32_t c0 = v.x & 0xffffu, c1 = v.x >> 16, c2 = v.y & 0xffffu, c3 = v.y >> 16;
+            uint4* dst = reinterpret_cast<uint4*>(out + 2 * w);
+            uint4 o;
+            if (first) {
+              o = make_uint4(Cvt<OUT_T>::enc(c0), Cvt<OUT_T>::enc(c1), Cvt<OUT_T>::enc(c2), Cvt<OUT_T>::enc(c3));
+            } else {
+              const uint4 old = *dst;
+              o = make_uint4(Cvt<OUT_T>::add(old.x, c0), Cvt<OUT_T>::add(old.y, c1), Cvt<OUT_T>::add(old.z, c2),
+                             Cvt<OUT_T>::add(old.w, c3));
+            }
+            st_stream_u4(dst, o);
           }
         } else {
-          for (int q = threadIdx.x; q < npix; q += kSmemThreads) {
-            const uint32_t v = (cnt[q >> 1] >> ((q & 1) << 4)) & 0xffffu;
-            if (first) {
-              out8[q] = (uint8_t)hist_u8_enc(sat_tail, idx0 + (uint32_t)q, v);
-            } else if (v) {   // a further chunk of a very long micro-bin (same thread as the first chunk's write)
-              const uint32_t old = out8[q];
-              if (old < kHistU8Sat) {
-                out8[q] = (uint8_t)hist_u8_enc(sat_tail, idx0 + (uint32_t)q, old + v);
-              } else {
-                uint32_t n = sat_tail[0];
-                if (n > (uint32_t)EAS_HIST_U8_SAT_CAP) n = (uint32_t)EAS_HIST_U8_SAT_CAP;
-                uint2* ent = reinterpret_cast<uint2*>(sat_tail + 4);
-                for (uint32_t i = 0; i < n; ++i)
-                  if (ent[i].x == idx0 + (uint32_t)q) {
-                    ent[i].y += v;
-                    break;
-                  }
-              }
-            }
+          for (int q = threadIdx.x; q < npix; q += NT) {
+            const uint32_t v = (cn[q >> 1] >> ((q & 1) << 4)) & 0xffffu;
+            out[q] = first ? Cvt<OUT_T>::enc(v) : Cvt<OUT_T>::add(out[q], v);
           }
-        }
-      } else if (vec_ok) {
-        // 2 words = 4 counters -> one 16 B store
-        for (int w = threadIdx.x * 2; w < nwords; w += kSmemThreads * 2) {
-          const uint2 v = *reinterpret_cast<const uint2*>(cnt + w);
-          const uint32_t c0 = v.x & 0xffffu, c1 = v.x >> 16, c2 = v.y & 0xffffu, c3 = v.y >> 16;
-          uint4* dst = reinterpret_cast<uint4*>(out + 2 * w);
-          uint4 o;
-          if (first) {
-            o = make_uint4(Cvt<OUT_T>::enc(c0), Cvt<OUT_T>::enc(c1), Cvt<OUT_T>::enc(c2), Cvt<OUT_T>::enc(c3));
-          } else {
-            const uint4 old = *dst;
-            o = make_uint4(Cvt<OUT_T>::add(old.x, c0), Cvt<OUT_T>::add(old.y, c1), Cvt<OUT_T>::add(old.z, c2),
-                           Cvt<OUT_T>::add(old.w, c3));
-          }
-          st_stream_u4(dst, o);
-        }
-      } else {
-        for (int q = threadIdx.x; q < npix; q += kSmemThreads) {
-          const uint32_t v = (cnt[q >> 1] >> ((q & 1) << 4)) & 0xffffu;
-          out[q] = first ? Cvt<OUT_T>::enc(v) : Cvt<OUT_T>::add(out[q], v);
         }
       }
       first = false;
@@ -408,8 +420,30 @@ SlabGeo slab_geo(int H, int W) {
 
 template <typename OUT_T, typename SRC>
 int launch_tiles(const SRC& src, const int64_t* bounds, int64_t n_items, int H, int W, int Tm, const SlabGeo& g,
-                 void* hist, unsigned int* counter, cudaStream_t stream, uint32_t* sat_tail = nullptr) {
-  auto kern = bin_hist_smem_kernel<OUT_T, SRC>;
+                 void* hist, unsigned int* counter, cudaStream_t stream, uint32_t* sat_tail = nullptr, int force = 0) {
+  // both polarities in one item (half as many scans) when two slabs fit one CTA's shared memory and there are enough
+  // (window, micro-bin, slab) items for every SM; EAS_BIN_PLANES=1 keeps the plane-per-item kernel (A/B runs)
+  // force: 3 = the pair kernel whenever it fits, 4 = never
+  const bool both = 2 * g.smem <= 200 * 1024 && force != 4 && getenv("EAS_BIN_PLANES") == nullptr &&
+                    (force == 3 || n_items / 2 >= 2 * EAS_NUM_SMS);
+  if (force == 3 && !both) return EAS_E_UNSUPPORTED;
+  if (both) {
+    auto kb = bin_hist_smem_kernel<OUT_T, SRC, 1024, true>;
+    cudaError_t eb = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * g.smem));
+    if (eb != cudaSuccess) return (int)eb;
+    cudaLaunchConfig_t lb = {};
+    int64_t gb = EAS_NUM_SMS;
+    if (gb > n_items / 2) gb = n_items / 2;
+    lb.gridDim = dim3((unsigned)gb), lb.blockDim = dim3(1024), lb.dynamicSmemBytes = 2 * g.smem, lb.stream = stream;
+    cudaLaunchAttribute ab[1];
+    ab[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    ab[0].val.programmaticStreamSerializationAllowed = 1;
+    lb.attrs = ab, lb.numAttrs = 1;
+    eb = cudaLaunchKernelEx(&lb, kb, src, bounds, n_items / 2, H, W, Tm, g.n_slabs, g.slab_rows, (uint32_t*)hist, counter,
+                            sat_tail);
+    return eb == cudaSuccess ? EAS_OK : (int)eb;
+  }
+  auto kern = bin_hist_smem_kernel<OUT_T, SRC, kSmemThreads, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return (int)e;
   const int per_sm = (int)((220 * 1024) / (g.smem + 1024));
@@ -504,7 +538,7 @@ extern "C" int eas_bin_dat(const void* rec, int64_t n_rec, const int64_t* ranges
   EAS_REQUIRE(B >= 0 && n_rec >= 0, EAS_E_SHAPE);
   EAS_REQUIRE(H > 0 && W > 0 && H <= 16384 && W <= 16384 && Tm > 0 && Tm <= 1024, EAS_E_SHAPE);
   EAS_REQUIRE((int64_t)H * W < (1ll << 30), EAS_E_SHAPE);
-  EAS_REQUIRE(strategy >= 0 && strategy <= 2, EAS_E_UNSUPPORTED);
+  EAS_REQUIRE(strategy >= 0 && strategy <= 4, EAS_E_UNSUPPORTED);
   EAS_REQUIRE(out_dtype == EAS_I32 || out_dtype == EAS_F32 || out_dtype == EAS_U8, EAS_E_UNSUPPORTED);
   if (B == 0) return EAS_OK;
   EAS_REQUIRE(ranges && hist && ws && (rec || n_rec == 0), EAS_E_NULL);
@@ -529,12 +563,12 @@ extern "C" int eas_bin_dat(const void* rec, int64_t n_rec, const int64_t* ranges
   // window lengths live on the device: "auto" takes the write-once tiles whenever the frame fits them
   // (event windows of tens of ms), the event-parallel kernel otherwise
   if (strategy == 0) strategy = (g.fits && (n_items >= EAS_NUM_SMS || out_dtype == EAS_U8)) ? 2 : 1;
-  if (strategy == 2) {
+  if (strategy >= 2) {
     EAS_REQUIRE(g.fits, EAS_E_UNSUPPORTED);
     if (out_dtype == EAS_U8)
-      return launch_tiles<uint8_t>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream, sat_tail);
-    return out_dtype == EAS_F32 ? launch_tiles<float>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream)
-                                : launch_tiles<int32_t>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream);
+      return launch_tiles<uint8_t>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream, sat_tail, strategy);
+    return out_dtype == EAS_F32 ? launch_tiles<float>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream, nullptr, strategy)
+                                : launch_tiles<int32_t>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream, nullptr, strategy);
   }
   EAS_REQUIRE(out_dtype != EAS_U8, EAS_E_UNSUPPORTED);   // the byte form is written by the tiles kernel only
   const int64_t HW = (int64_t)H * W;
@@ -563,7 +597,7 @@ extern "C" int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64
   EAS_REQUIRE(B >= 0 && n_events >= 0, EAS_E_SHAPE);
   EAS_REQUIRE(H > 0 && W > 0 && Tm > 0 && Tm <= 1024, EAS_E_SHAPE);
   EAS_REQUIRE((int64_t)H * W < (1ll << 30), EAS_E_SHAPE);
-  EAS_REQUIRE(strategy >= 0 && strategy <= 2, EAS_E_UNSUPPORTED);
+  EAS_REQUIRE(strategy >= 0 && strategy <= 4, EAS_E_UNSUPPORTED);
   EAS_REQUIRE(out_dtype == EAS_I32 || out_dtype == EAS_F32 || out_dtype == EAS_U8, EAS_E_UNSUPPORTED);
   if (B == 0) return EAS_OK;
   EAS_REQUIRE(offsets && hist && ws, EAS_E_NULL);
@@ -597,12 +631,12 @@ extern "C" int eas_bin_events_ex(const int16_t* x, const int16_t* y, const int64
     const bool enough = n_items >= EAS_NUM_SMS && n_events / (B * Tm) <= (1 << 17);
     strategy = (fits && (enough || out_dtype == EAS_U8)) ? 2 : 1;
   }
-  if (strategy == 2) {
+  if (strategy >= 2) {
     EAS_REQUIRE(fits, EAS_E_UNSUPPORTED);
     if (out_dtype == EAS_U8)
-      return launch_tiles<uint8_t>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream, sat_tail);
-    return out_dtype == EAS_F32 ? launch_tiles<float>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream)
-                                : launch_tiles<int32_t>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream);
+      return launch_tiles<uint8_t>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream, sat_tail, strategy);
+    return out_dtype == EAS_F32 ? launch_tiles<float>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream, nullptr, strategy)
+                                : launch_tiles<int32_t>(src, bounds, n_items, H, W, Tm, g, hist, counter, stream, nullptr, strategy);
   } else {
     EAS_REQUIRE(out_dtype != EAS_U8, EAS_E_UNSUPPORTED);   // the byte form is written by the tiles kernel only
     cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)B * Tm * 2 * HW * sizeof(int32_t), stream);

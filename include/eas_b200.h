@@ -60,7 +60,9 @@ size_t eas_bin_events_ws_bytes(int64_t B, int Tm);
 int eas_bin_events(const int16_t* x, const int16_t* y, const int64_t* t, const uint8_t* p,
                    const int64_t* offsets, int64_t B, int64_t n_events, int H, int W, int Tm,
                    int32_t* hist, void* ws, size_t ws_bytes, void* stream);
-/* Same with options: strategy 0 = auto, 1 = global reductions, 2 = shared-memory tiles;
+/* Same with options: strategy 0 = auto, 1 = global reductions, 2 = shared-memory tiles (the kernel that holds both
+ * polarities of a slab per work item when two slabs fit a CTA and the batch has items for every SM, else one plane per
+ * item), 3 / 4 = those two tiles kernels explicitly;
  * out_dtype EAS_I32, or EAS_F32 (the counts as fp32, exact below 2^24: what the sampler's first
  * convolution consumes, and the dtype the reference casts its histogram to on the device), or EAS_U8:
  * the compact form the sampler reads directly (eas_sampler_cfg.in_dtype = EAS_U8) -- a quarter of the

@@ -19,7 +19,7 @@ def _dev(arrs, cuda):
             torch.from_numpy(p).to(cuda), torch.from_numpy(off).to(cuda))
 
 
-@pytest.mark.parametrize("strategy", ["reds", "tiles", "auto"])
+@pytest.mark.parametrize("strategy", ["reds", "tiles", "tiles_pair", "tiles_planes", "auto"])
 def test_golden_cases(cuda, strategy):
     z = load_golden("binning")
     for name in z["names"]:
@@ -34,7 +34,7 @@ def test_golden_cases(cuda, strategy):
             name, strategy, int((g != want).sum()), int(g.sum()), int(want.sum()))
 
 
-@pytest.mark.parametrize("strategy", ["reds", "tiles"])
+@pytest.mark.parametrize("strategy", ["reds", "tiles", "tiles_pair", "tiles_planes"])
 def test_ragged_batch_vs_oracle(cuda, strategy):
     """Ragged batch incl. empty windows, single events and a window at the 16 B alignment edge."""
     rng = np.random.default_rng(11)
@@ -68,9 +68,10 @@ def test_gen1_batch_vs_oracle_and_properties(cuda):
     # idempotence / determinism
     assert torch.equal(a, eas.bin_events(*d, H, W, 4, strategy="tiles"))
     # fp32 counts (what the sampler consumes) are the same numbers
-    for s in ("tiles", "reds"):
+    for s in ("tiles", "tiles_pair", "tiles_planes", "reds"):
         f = eas.bin_events(*d, H, W, 4, strategy=s, dtype=torch.float32)
         assert f.dtype == torch.float32 and torch.equal(f, a.float())
+        assert torch.equal(eas.bin_events(*d, H, W, 4, strategy=s), a)
 
 
 def test_mpx_window_properties(cuda):
@@ -119,8 +120,8 @@ def test_letterbox_frames_match_the_reference_resize(cuda):
 
 
 # ---- the compact byte histogram (EAS_U8): same information as the int32 histogram --------------------------------
-def _compact_vs_dense(d, H, W, Tm, want_i32):
-    ch = eas.bin_events(*d, H, W, Tm, dtype=torch.uint8)
+def _compact_vs_dense(d, H, W, Tm, want_i32, strategy="auto"):
+    ch = eas.bin_events(*d, H, W, Tm, dtype=torch.uint8, strategy=strategy)
     assert isinstance(ch, eas.CompactHist) and ch.shape == tuple(want_i32.shape)
     ch.check()
     want = torch.from_numpy(want_i32)
@@ -147,7 +148,8 @@ def test_compact_histogram_golden_cases(cuda):
             with pytest.raises(RuntimeError):
                 eas.bin_events(*_dev((x, y, t, p, off), cuda), H, W, Tm, dtype=torch.uint8)
             continue
-        ch = _compact_vs_dense(_dev((x, y, t, p, off), cuda), H, W, Tm, want)
+        for strategy in ("tiles_planes", "tiles_pair"):
+            ch = _compact_vs_dense(_dev((x, y, t, p, off), cuda), H, W, Tm, want, strategy)
         n_sat += int(ch.tail[0])
     assert n_sat > 0, "no golden exercised the saturation list"
 
@@ -171,7 +173,8 @@ def test_compact_histogram_hot_pixels_and_gen1_batch(cuda):
     want = ob.micro_sum_batch(x, y, t, p, off, H, W, 4).astype(np.int32)
     assert (want >= 255).sum() >= 8 * 3
     d = _dev((x, y, t, p, off), cuda)
-    _compact_vs_dense(d, H, W, 4, want)
+    for strategy in ("tiles_planes", "tiles_pair", "auto"):
+        _compact_vs_dense(d, H, W, 4, want, strategy)
     rec = torch.from_numpy(eas.pack_records(x, y, t, p)).to(cuda)
     rng_ = torch.from_numpy(np.stack([off[:-1], off[1:]], 1)).to(cuda)
     ch = eas.bin_dat(rec, rng_, H, W, 4, dtype=torch.uint8)

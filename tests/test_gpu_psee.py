@@ -27,7 +27,7 @@ def test_windows_and_histograms_match_reference_loader(cuda, name):
     assert np.array_equal(count, z[f"{name}/count"])
     nz = count > 0
     assert np.array_equal(r[nz, 0], z[f"{name}/first"][nz])
-    for strategy in ("tiles", "reds", "auto"):
+    for strategy in ("tiles", "tiles_pair", "tiles_planes", "reds", "auto"):
         for dtype in (torch.int32, torch.float32):
             hist = recd.histograms(ranges, H, W, Tm, strategy=strategy, dtype=dtype)
             assert np.array_equal(hist.cpu().numpy().astype(np.int32), z[f"{name}/hist"]), (strategy, dtype)
