@@ -14,7 +14,10 @@
 //         from an atomic counter, counts a slab in shared memory as packed 16-bit lanes (<= 72 KB, so
 //         3 CTAs per SM overlap their zero / scan / write phases) and writes it once with 16 B
 //         stores: no global atomics, no pre-zeroing, HBM traffic = 5 B/event (re-read from L2 by
-//         the other slabs) + 4 B/bin.  Chunks of <= 65535 events make 16-bit overflow impossible.
+//         the other slabs) + 4 B/bin (1 B/bin for the compact byte histogram, hist_u8.cuh).  Chunks of
+//         <= 65535 events make 16-bit overflow impossible.  The kernel is issue bound (~20 SASS
+//         instructions per scanned event), so the variant that big batches get holds BOTH polarities of a
+//         slab per item (2 x 73 KB, one 1024-thread CTA per SM): half as many scans of every event.
 //      bin_hist_global_kernel ("reds"): event-parallel, 8 events per thread with 16 B loads,
 //         red.global.add.u32 into the (L2-resident when it fits) histogram after a memset.  Used for
 //         frames that do not fit in shared memory and for very long windows.
