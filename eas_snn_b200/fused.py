@@ -591,8 +591,8 @@ class GraphedTrainStep:
         for q in params:
             dense = q.is_contiguous() or q.is_contiguous(memory_format=torch.channels_last) if q.dim() == 4 \
                 else q.is_contiguous()
-            q.grad = (self.flat_grad[o:o + q.numel()].as_strided(q.size(), q.stride()) if dense
-                      else torch.zeros_like(q))
+            q.grad = (self.flat_grad[o:o + q.numel()].as_strided(q.size(), q.stride())
+                      if dense and q.dtype == self.flat_grad.dtype and q.device == dev else torch.zeros_like(q))
             o += q.numel()
         self._loose = [q.grad for q in params if q.grad.untyped_storage().data_ptr() != self.flat_grad.untyped_storage().data_ptr()]
 
